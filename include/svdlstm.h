@@ -1,0 +1,145 @@
+/*
+ * svdlstm.h -- C-ABI of the B200-native SVD-factored LSTM hot path (libsvdlstm.so).
+ *
+ * The reference (dncoble/LSTM-acceleration-with-singular-value-decomposition) is pure
+ * Python on Keras; it has no FFI.  Its drop-in boundary is the Keras layer protocol of
+ * code/svd_classes_v3.py.  The Python classes of this repo keep that protocol (same names,
+ * constructor kwargs, get_weights() orderings) and bind the entry points below through
+ * ctypes.  Each entry point cites the reference interface it replaces (file:line relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const float*` / `float*` is a DEVICE pointer owned by
+ *     the caller (PyTorch tensors in this repo); row-major, float32, row-vector convention
+ *     (svd_classes_v3.py:128), gate order i,f,c,o along the 4H axis (:144).
+ *   - weight pointers are BORROWED until the next set_*_weights for that layer or destroy.
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     no hidden synchronisation unless stated.
+ *   - return 0 = ok; <0 = argument / shape / state error; >0 = cudaError_t.  The message is in
+ *     svdlstm_last_error() (thread-local).
+ *   - there is no CPU path: without a CUDA device every compute entry point fails.
+ */
+#ifndef SVDLSTM_H_
+#define SVDLSTM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svdlstm_model_s* svdlstm_handle;
+
+/* forward flags (Keras LSTM kwargs used by SingularLSTM.call, svd_classes_v3.py:385-437) */
+#define SVDLSTM_RETURN_SEQUENCES      1   /* :428-431 */
+#define SVDLSTM_GO_BACKWARDS          2   /* :413     */
+#define SVDLSTM_TIME_MAJOR            4   /* :417     */
+#define SVDLSTM_ZERO_OUTPUT_FOR_MASK  8   /* :418     */
+
+/* engines */
+#define SVDLSTM_ENGINE_AUTO     0   /* FP32: wavefront kernel when the model fits it, else general */
+#define SVDLSTM_ENGINE_GENERAL  1   /* FP32 CUDA-core batched persistent kernel (any shape)        */
+#define SVDLSTM_ENGINE_WAVEFRONT 2  /* FP32 register-resident warp-per-layer wavefront (H,D,r<=32) */
+#define SVDLSTM_ENGINE_TC_BF16  3   /* tcgen05 BF16 tensor-core persistent kernel (reduced precision) */
+
+/* ---- model handle ------------------------------------------------------------------------
+ * A handle describes a stack of L LSTM layers (+ optional Dense top), i.e. what the
+ * reference builds as keras.Sequential([SingularLSTM...]+[Dense]) (svd_classes_v3.py:471-540,
+ * 554-598, 605-676).  Host metadata only; no device work.                                   */
+int svdlstm_create(svdlstm_handle* out, int n_layers, int input_dim, const int* units);
+void svdlstm_destroy(svdlstm_handle h);
+
+/* Stock LSTMCell weights  get_weights() = [W (D,4H), U (H,4H), b (4H,)]
+ * (what make_LSTM_singular_model reads at svd_classes_v3.py:557).                          */
+int svdlstm_set_full_weights(svdlstm_handle h, int layer, const float* W, const float* U,
+                             const float* b);
+
+/* SingularLSTMCell weights in get_weights() order (svd_classes_v3.py:113):
+ *   w[0]=kernel sigma_w, w[1]=recurrent_kernel sigma_u, w[2]=w_left, w[3]=w_right,
+ *   w[4]=u_left, w[5]=u_right, w[6]=bias.
+ * merged (:35-56,81-112): sigma_w (1,k_w) w_left (D,k_w) w_right (k_w,4H); same for u.
+ * split  (:58-107): sigma_w (1,4k_w) w_left (D,4k_w) w_right (k_w,4H) (gate g = axis-1 quarter g).
+ * k_w/k_u are the kept ranks (per gate when split).                                          */
+int svdlstm_set_singular_weights(svdlstm_handle h, int layer, int merged,
+                                 const float* const* w, int k_w, int k_u);
+
+/* ReducedLSTMCell weights in get_weights() order (svd_classes_v3.py:278, :308-315):
+ *   merged: w = [w_left (D,r_w), w_right (r_w,4H-r_w), u_left (H,r_u), u_right (r_u,4H-r_u), bias],
+ *           ranks = [r_w, r_u]
+ *   split : w = [w_left_g (D,rw_g), w_right_g (rw_g,H-rw_g), u_left_g (H,ru_g), u_right_g (ru_g,H-ru_g)]
+ *           for g in i,f,c,o, then bias;  ranks = [rw_i,ru_i, rw_f,ru_f, rw_c,ru_c, rw_o,ru_o]   */
+int svdlstm_set_reduced_weights(svdlstm_handle h, int layer, int merged,
+                                const float* const* w, const int* ranks);
+
+/* Dense / TimeDistributed(Dense) top: kernel (H_last, n_out), bias (n_out)
+ * (svd_classes_v3.py:532-539, 590-597, 670-675).  kernel==NULL removes the top.            */
+int svdlstm_set_dense_top(svdlstm_handle h, const float* kernel, const float* bias, int n_out);
+
+/* SingularLSTM.call / Sequential.predict (svd_classes_v3.py:385-437; svd_acceleration_v3.py:151):
+ * one persistent launch runs all T steps of all layers (+ Dense top).
+ *   x     (B,T,D)  [or (T,B,D) with TIME_MAJOR]
+ *   h0,c0 NULL (zero state, :393) or the per-layer states concatenated: layer l occupies
+ *         B*H_l floats after those of layers < l.  h_n,c_n same layout, may be NULL.
+ *   mask  NULL or (B,T) bytes (non-zero = valid step), Keras mask semantics.
+ *   y     (B,T,n) with RETURN_SEQUENCES else (B,n); n = n_out if a Dense top is set, else H_last.
+ *         With GO_BACKWARDS outputs are in processing order (Keras does not re-reverse).     */
+int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y,
+                    const float* h0, const float* c0, float* h_n, float* c_n,
+                    const uint8_t* mask, int flags, int engine, void* stream);
+
+/* Number of kernels the last forward on this handle launched, and which engine ran. */
+int svdlstm_last_launches(svdlstm_handle h);
+int svdlstm_last_engine(svdlstm_handle h);
+
+/* Weight-count helper == sum(a.size for a in model.get_weights()) without the Dense top
+ * (svd_acceleration_v3.py:160-166).                                                          */
+int64_t svdlstm_count_weights(svdlstm_handle h);
+
+/* ---- batched one-sided Jacobi SVD -----------------------------------------------------------
+ * Replaces np.linalg.svd(mat, full_matrices=False) at svd_classes_v3.py:491,562 and
+ * old_versions/svd_classes.py:10,15,231.  A: batch x (m,n) row-major contiguous.
+ * Outputs (k=min(m,n)): U batch x (m,k), S batch x (k) descending, Vt batch x (k,n).
+ * Any of U/Vt may be NULL (values only).  sweeps (device int[batch], may be NULL) receives
+ * the number of Jacobi sweeps used.  Internally float64.                                      */
+int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int n, float* U, float* S,
+                               float* Vt, int* sweeps, void* stream);
+
+/* B = (U_r * S_r) V1 ; C = V1^-1 V2  with V_r = [V1 (r,r) | V2 (r,n-r)]
+ * (svd_classes_v3.py:622-626, 656-660).  Inputs already sliced to the kept rank r:
+ * U_r (m,r) with row stride ldu, S_r (r), V_r (r,n) with row stride ldv.  Outputs B (m,r), C (r,n-r)
+ * contiguous.  pivot_ratio (device float[1], may be NULL) = min|pivot| / max|pivot| of the
+ * partial-pivoting elimination of V1 (small => V1 ill-conditioned; the reference calls inv()
+ * unguarded).                                                                                 */
+int svdlstm_reduce_factors(const float* U_r, int ldu, const float* S_r, const float* V_r, int ldv,
+                           int m, int r, int n, float* B, float* C, float* pivot_ratio,
+                           void* stream);
+
+/* ---- fused Hoyer + orthogonality penalties ----------------------------------------------------
+ * One launch evaluates every regulariser of a model: HoyerRegularizer.__call__
+ * (svd_classes_v3.py:460-462) on sigma vectors and keras OrthogonalRegularizer(mode='rows')
+ * (call sites :514,:573) on the factor matrices.  items[i] is an (rows,cols) row-major matrix
+ * (a vector is rows=1).  out[4*i..4*i+3] (device doubles) =
+ *   { sum|x|, sum x^2, sum_{i!=j}|Pn_ij| (Gram of L2-normalised rows), ||X X^T - I||_F^2 }.
+ * gram[i]==0 skips the two Gram sums (sigma vectors).  columns[i]!=0 uses columns instead of rows. */
+typedef struct {
+  const float* data;
+  int32_t rows, cols, ld;
+  int32_t gram;      /* 0: L1/L2 sums only; 1: also Gram sums */
+  int32_t columns;   /* 0: rows mode (Keras default here); 1: columns mode */
+} svdlstm_penalty_item;
+int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items, double* out, void* stream);
+
+/* ---- rank-sweep squared error -----------------------------------------------------------------
+ * sse[r] = sum_i (pred[r,i]-target[i])^2, deterministic two-stage reduction in float64 -- the
+ * device half of the RMSE of svd_acceleration_v3.py:187-190 / old_versions/svd_acceleration.py:79-81.
+ * pred (n_ranks, n) contiguous, target (n), sse device double[n_ranks].                         */
+int svdlstm_sweep_sse(const float* pred, const float* target, int n_ranks, int64_t n, double* sse,
+                      void* stream);
+
+const char* svdlstm_last_error(void);
+const char* svdlstm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDLSTM_H_ */

@@ -1,0 +1,145 @@
+"""ctypes binding of libsvdlstm.so (the C-ABI declared in include/svdlstm.h).
+
+There is NO CPU fallback anywhere in this package: if the shared library is missing, or no CUDA
+device is visible, every compute entry point raises.  PyTorch is used only for device memory,
+streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvdlstm.so")
+
+RETURN_SEQUENCES = 1
+GO_BACKWARDS = 2
+TIME_MAJOR = 4
+ZERO_OUTPUT_FOR_MASK = 8
+
+ENGINE_AUTO = 0
+ENGINE_GENERAL = 1
+ENGINE_WAVEFRONT = 2
+ENGINE_TC_BF16 = 3
+ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc_bf16": 3, None: 0}
+
+EXPORTS = [
+    "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",
+    "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
+    "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_svd_jacobi_batched",
+    "svdlstm_reduce_factors", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
+    "svdlstm_version",
+]
+
+
+class PenaltyItem(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
+                ("ld", ctypes.c_int32), ("gram", ctypes.c_int32), ("columns", ctypes.c_int32)]
+
+
+_lib = None
+# kernels launched through this binding since import (bench.py's `gpu_launches` reads it)
+launch_counter = 0
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libsvdlstm.so is not built (%s missing). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `python lstm-acceleration-with-singular-value-decomposition_b200/build.py`. "
+            "This package has no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cip = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)
+    L.svdlstm_create.argtypes = [ctypes.POINTER(vp), ci, ci, cip]
+    L.svdlstm_create.restype = ci
+    L.svdlstm_destroy.argtypes = [vp]
+    L.svdlstm_destroy.restype = None
+    L.svdlstm_set_full_weights.argtypes = [vp, ci, vp, vp, vp]
+    L.svdlstm_set_full_weights.restype = ci
+    L.svdlstm_set_singular_weights.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ci, ci]
+    L.svdlstm_set_singular_weights.restype = ci
+    L.svdlstm_set_reduced_weights.argtypes = [vp, ci, ci, ctypes.POINTER(vp), cip]
+    L.svdlstm_set_reduced_weights.restype = ci
+    L.svdlstm_set_dense_top.argtypes = [vp, vp, vp, ci]
+    L.svdlstm_set_dense_top.restype = ci
+    L.svdlstm_forward.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    L.svdlstm_forward.restype = ci
+    L.svdlstm_last_launches.argtypes = [vp]
+    L.svdlstm_last_launches.restype = ci
+    L.svdlstm_last_engine.argtypes = [vp]
+    L.svdlstm_last_engine.restype = ci
+    L.svdlstm_count_weights.argtypes = [vp]
+    L.svdlstm_count_weights.restype = ctypes.c_int64
+    L.svdlstm_svd_jacobi_batched.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp]
+    L.svdlstm_svd_jacobi_batched.restype = ci
+    L.svdlstm_reduce_factors.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.svdlstm_reduce_factors.restype = ci
+    L.svdlstm_penalties.argtypes = [ctypes.POINTER(PenaltyItem), ci, vp, vp]
+    L.svdlstm_penalties.restype = ci
+    L.svdlstm_sweep_sse.argtypes = [vp, vp, ci, ctypes.c_int64, vp, vp]
+    L.svdlstm_sweep_sse.restype = ci
+    L.svdlstm_last_error.argtypes = []
+    L.svdlstm_last_error.restype = ctypes.c_char_p
+    L.svdlstm_version.argtypes = []
+    L.svdlstm_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    """0 ok; <0 argument/shape error -> ValueError (as Keras raises on bad set_weights);
+    >0 cudaError_t -> RuntimeError."""
+    if rc == 0:
+        return
+    msg = lib().svdlstm_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("svdlstm: no CUDA device visible; this package has no CPU fallback "
+                           "(the numpy oracle under oracle/ is test infrastructure only)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def dev_tensor(a, device: Optional[torch.device] = None) -> torch.Tensor:
+    """numpy / torch -> contiguous float32 CUDA tensor."""
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.detach().to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32)), device=device)
+
+
+def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def cur_stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def int_array(vals: Sequence[int]):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def add_launches(n: int) -> None:
+    global launch_counter
+    launch_counter += int(n)

@@ -1,0 +1,409 @@
+"""Sequential container + the reference's model builders ("rank-reduction API").
+
+    make_LSTM_singular_model        code/svd_classes_v3.py:548-598
+    make_split_LSTM_singular_model  code/svd_classes_v3.py:469-540
+    make_LSTM_reduced_model         code/svd_classes_v3.py:604-676   (+ keyword-only ``rank=``)
+
+The SVDs run on device (K2, batched one-sided Jacobi) instead of np.linalg.svd (:491,:562); the
+B / C construction runs on device (K2b) instead of np.linalg.inv (:626,:660).  ``Sequential.predict``
+fuses every LSTM layer and the Dense top into ONE persistent launch.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell, OrthogonalRegularizer,
+                     ReducedLSTMCell, SingularLSTM, SingularLSTMCell, TimeDistributed, _losses_of)
+
+
+# --------------------------------------------------------------------------------------------------
+# device linear algebra wrappers (K2 / K2b)
+# --------------------------------------------------------------------------------------------------
+def svd_batched(A, compute_uv=True, return_sweeps=False):
+    """Batched thin SVD on device.  A: (batch, m, n) or (m, n).  Returns (U, S, Vt) like
+    np.linalg.svd(full_matrices=False) -- U (..,m,k), S (..,k) descending, Vt (..,k,n)."""
+    a = C.dev_tensor(A)
+    squeeze = a.dim() == 2
+    if squeeze:
+        a = a.unsqueeze(0)
+    if a.dim() != 3:
+        raise ValueError("svd_batched expects (m,n) or (batch,m,n)")
+    batch, m, n = (int(s) for s in a.shape)
+    k = min(m, n)
+    dev = a.device
+    S = torch.empty((batch, k), dtype=torch.float32, device=dev)
+    U = torch.empty((batch, m, k), dtype=torch.float32, device=dev) if compute_uv else None
+    Vt = torch.empty((batch, k, n), dtype=torch.float32, device=dev) if compute_uv else None
+    sw = torch.zeros(batch, dtype=torch.int32, device=dev) if return_sweeps else None
+    C.check(C.lib().svdlstm_svd_jacobi_batched(C.ptr(a), batch, m, n, C.ptr(U), C.ptr(S), C.ptr(Vt), C.ptr(sw),
+                                               C.cur_stream()))
+    C.add_launches(1)
+    if squeeze:
+        S = S[0]
+        U = U[0] if U is not None else None
+        Vt = Vt[0] if Vt is not None else None
+    out = (U, S, Vt) if compute_uv else S
+    if return_sweeps:
+        return out, sw
+    return out
+
+
+def reduce_factors(U_r, S_r, V_r, return_pivot_ratio=False):
+    """B = (U_r * S_r) @ V1, C = inv(V1) @ V2 with V_r = [V1 | V2] (svd_classes_v3.py:622-626)."""
+    U_r = C.dev_tensor(U_r)
+    S_r = C.dev_tensor(S_r).reshape(-1)
+    V_r = C.dev_tensor(V_r)
+    m, r = int(U_r.shape[0]), int(U_r.shape[1])
+    n = int(V_r.shape[1])
+    if int(V_r.shape[0]) != r or int(S_r.numel()) != r:
+        raise ValueError("reduce_factors: inconsistent ranks")
+    if r == 0:
+        raise ValueError("reduce_factors: every singular value was pruned (rank 0)")
+    dev = U_r.device
+    B = torch.empty((m, r), dtype=torch.float32, device=dev)
+    Cm = torch.empty((r, n - r), dtype=torch.float32, device=dev)
+    pr = torch.zeros(1, dtype=torch.float32, device=dev)
+    C.check(C.lib().svdlstm_reduce_factors(C.ptr(U_r), U_r.stride(0), C.ptr(S_r), C.ptr(V_r), V_r.stride(0), m, r, n,
+                                           C.ptr(B), C.ptr(Cm) if Cm.numel() else None, C.ptr(pr), C.cur_stream()))
+    C.add_launches(2 + 4 * r)
+    if return_pivot_ratio:
+        return B, Cm, pr
+    return B, Cm
+
+
+# --------------------------------------------------------------------------------------------------
+# Sequential
+# --------------------------------------------------------------------------------------------------
+class Sequential:
+    """keras.models.Sequential stand-in: InputLayer + LSTM layers + Dense top."""
+
+    def __init__(self, layers=None, engine=None):
+        self._input: Optional[InputLayer] = None
+        self.layers: List = []
+        self.engine = engine
+        self._fused: Optional[Handle] = None
+        for l in (layers or []):
+            self.add(l)
+
+    def add(self, layer):
+        if isinstance(layer, InputLayer):
+            self._input = layer
+        else:
+            self.layers.append(layer)
+        self._fused = None
+
+    @property
+    def input_shape(self):
+        if self._input is not None and self._input.input_shape is not None:
+            return (None,) + tuple(self._input.input_shape)
+        first = self.layers[0]
+        d = first.cell.input_dim if getattr(first, "cell", None) is not None else None
+        return (None, None, d)
+
+    def _lstm_layers(self):
+        return [l for l in self.layers if isinstance(l, SingularLSTM)]
+
+    def _dense(self):
+        last = self.layers[-1] if self.layers else None
+        if isinstance(last, TimeDistributed):
+            return last.layer
+        if isinstance(last, Dense):
+            return last
+        return None
+
+    def build(self, input_shape=None):
+        d = (input_shape or self.input_shape)[-1]
+        if d is None:
+            raise ValueError("Sequential needs an InputLayer(input_shape=[None, D]) or an explicit input_shape")
+        for l in self._lstm_layers():
+            l.build((None, None, d))
+            d = l.units
+        dense = self._dense()
+        if dense is not None and not dense.built:
+            dense.build((None, d))
+
+    def get_weights(self):
+        out = []
+        for l in self.layers:
+            out += l.get_weights()
+        return out
+
+    def count_params(self):
+        return int(sum(np.size(w) for w in self.get_weights()))
+
+    @property
+    def losses(self):
+        """All regulariser penalties of the model from ONE fused K3 launch (Keras `model.losses`)."""
+        items = []
+        for l in self._lstm_layers():
+            items += l.cell.regularization_items()
+        return _losses_of(items)
+
+    def _fusable(self):
+        lstms = self._lstm_layers()
+        if not lstms or len(lstms) > 8:
+            return False
+        n_tail = len(self.layers) - len(lstms)
+        if n_tail > 1 or (n_tail == 1 and self._dense() is None):
+            return False
+        if self.layers[:len(lstms)] != lstms:
+            return False
+        for i, l in enumerate(lstms):
+            last = i == len(lstms) - 1
+            if l.go_backwards or l.stateful or l.time_major or l.return_state:
+                return False
+            if not last and not l.return_sequences:
+                return False
+        dense = self._dense()
+        if dense is not None and dense.units > 64:
+            return False
+        return True
+
+    def _fused_handle(self) -> Handle:
+        if self._fused is None:
+            lstms = self._lstm_layers()
+            h = Handle(lstms[0].cell.input_dim, [l.units for l in lstms])
+            for i, l in enumerate(lstms):
+                l.cell.bind(h, i)
+            dense = self._dense()
+            if dense is not None:
+                h.set_dense_top(dense.kernel.tensor, dense.bias.tensor)
+            self._fused = h
+        return self._fused
+
+    def __call__(self, X, engine=None):
+        """Device-in / device-out forward (torch CUDA tensors)."""
+        x = C.dev_tensor(X)
+        if x.dim() != 3:
+            raise ValueError("expected input of shape (batch, time, features)")
+        self.build((None, None, int(x.shape[-1])))
+        eng = engine if engine is not None else self.engine
+        if self._fusable():
+            lstms = self._lstm_layers()
+            y, _, _ = self._fused_handle().forward(x, return_sequences=lstms[-1].return_sequences, engine=eng)
+            return y
+        a = x
+        for l in self.layers:
+            a = l.call(a, engine=eng) if isinstance(l, SingularLSTM) else l.call(a)
+        return a
+
+    def predict(self, X, batch_size=32, verbose=0, engine=None):
+        """Keras ``model.predict`` (svd_acceleration_v3.py:148,151): host array in, host array out.
+        Sequences are independent, so the whole batch runs as one launch regardless of batch_size."""
+        return self.__call__(X, engine=engine).cpu().numpy()
+
+    def last_engine(self):
+        return self._fused.last_engine() if self._fused is not None else None
+
+
+# --------------------------------------------------------------------------------------------------
+# builders
+# --------------------------------------------------------------------------------------------------
+def _regs(hoyer, orthogonal):
+    if hoyer is not None and hoyer != 0:
+        kr, rr = HoyerRegularizer(hoyer), HoyerRegularizer(hoyer)
+    else:
+        kr = rr = None
+    if orthogonal is not None and orthogonal != 0:
+        uvr, train_uv = OrthogonalRegularizer(factor=orthogonal, mode='rows'), True
+    else:
+        uvr, train_uv = None, False
+    return kr, rr, uvr, train_uv
+
+
+def _full_weights(layer):
+    if not isinstance(layer.cell, LSTMCell):
+        raise ValueError("builder expects a model of stock LSTM layers (get_weights() -> [W,U,b])")
+    if not layer.built:
+        raise ValueError("source model is not built")
+    return layer.cell.kernel.tensor, layer.cell.recurrent_kernel.tensor, layer.cell.bias.tensor
+
+
+def _copy_dense_top(model, smodel, time_distributed):
+    src = model._dense()
+    if src is None:
+        raise ValueError("builder expects the last layer of the source model to be Dense")
+    dense_top = Dense(src.units)
+    top = TimeDistributed(dense_top) if time_distributed else dense_top
+    smodel.add(top)
+    top.set_weights([model.layers[-1].weights[0].numpy(), model.layers[-1].weights[1].numpy()])
+
+
+def make_split_LSTM_singular_model(model, hoyer=None, orthogonal=None, return_sequences=False):
+    """svd_classes_v3.py:469-540: one SVD per gate block i,f,c,o of W and U (batched on device),
+    factors re-concatenated along axis 1.  (The reference drops `orthogonal` on this path, :552;
+    it is forwarded here.)"""
+    model.build()
+    smodel = Sequential()
+    smodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
+    lstm_layers = model.layers[:-1]
+    for i, layer in enumerate(lstm_layers):
+        w, u, b = _full_weights(layer)
+        units = layer.units
+        wu = []
+        for mat in (w, u):
+            rows = int(mat.shape[0])
+            blocks = mat.view(rows, 4, units).permute(1, 0, 2).contiguous()     # (4, rows, units)
+            left, sigma, right = svd_batched(blocks)                            # (4,rows,k) (4,k) (4,k,units)
+            k = int(sigma.shape[1])
+            unsplit_left = left.permute(1, 0, 2).reshape(rows, 4 * k)
+            unsplit_sigma = sigma.reshape(1, 4 * k)
+            unsplit_right = right.permute(1, 0, 2).reshape(k, 4 * units)
+            wu.append([unsplit_left, unsplit_sigma, unsplit_right])
+        kr, rr, uvr, train_uv = _regs(hoyer, orthogonal)
+        cell = SingularLSTMCell(units, w=wu[0], u=wu[1], b=b, kernel_regularizer=kr, recurrent_regularizer=rr,
+                                train_uv=train_uv, uv_regularizer=uvr, merged_kernel=False)
+        rs = True
+        if i == len(lstm_layers) - 1 and not return_sequences:
+            rs = False
+        smodel.add(SingularLSTM(units, cell=cell, return_sequences=rs))
+    _copy_dense_top(model, smodel, return_sequences)
+    smodel.build()
+    return smodel
+
+
+def make_LSTM_singular_model(model, hoyer=None, orthogonal=None, merged_kernel=True, return_sequences=False):
+    """svd_classes_v3.py:548-598: W (D,4H) and U (H,4H) of every LSTM layer -> left, sigma (1,k), right."""
+    if not merged_kernel:
+        return make_split_LSTM_singular_model(model, hoyer=hoyer, orthogonal=orthogonal, return_sequences=return_sequences)
+    model.build()
+    smodel = Sequential()
+    smodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
+    lstm_layers = model.layers[:-1]
+    for i, layer in enumerate(lstm_layers):
+        w, u, b = _full_weights(layer)
+        units = layer.units
+        wu = []
+        for mat in (w, u):
+            left, sigma, right = svd_batched(mat)
+            wu.append([left, sigma.reshape(1, -1), right])
+        kr, rr, uvr, train_uv = _regs(hoyer, orthogonal)
+        cell = SingularLSTMCell(units, w=wu[0], u=wu[1], b=b, kernel_regularizer=kr, recurrent_regularizer=rr,
+                                train_uv=train_uv, uv_regularizer=uvr)
+        rs = True
+        if i == len(lstm_layers) - 1 and not return_sequences:
+            rs = False
+        smodel.add(SingularLSTM(units, cell=cell, return_sequences=rs))
+    _copy_dense_top(model, smodel, return_sequences)
+    smodel.build()
+    return smodel
+
+
+def _reduce_one(U, S, V, cutoff, rank, use_abs=False, where=""):
+    """svd_classes_v3.py:618-627.  Threshold keep = S > cutoff (drops negative sigma regardless of
+    magnitude, as the reference does; ``use_abs`` opts into |S| > cutoff) or explicit top-``rank``."""
+    S = S.reshape(-1)
+    if rank is not None:
+        keep_idx = torch.arange(min(int(rank), S.numel()), device=S.device)
+    else:
+        s_host = S.cpu()
+        keep = (s_host.abs() if use_abs else s_host) > cutoff
+        keep_idx = torch.nonzero(keep).reshape(-1).to(S.device)
+    if keep_idx.numel() == 0:
+        raise ValueError("make_LSTM_reduced_model: cutoff removed every singular value of %s" % where)
+    U_r = U.index_select(1, keep_idx).contiguous()
+    V_r = V.index_select(0, keep_idx).contiguous()
+    S_r = S.index_select(0, keep_idx).contiguous()
+    B, Cm, pr = reduce_factors(U_r, S_r, V_r, return_pivot_ratio=True)
+    return [B, Cm], pr
+
+
+def make_LSTM_reduced_model(model, cutoff=.05, merged_kernel=True, *, rank=None, use_abs=False, check_condition=True):
+    """svd_classes_v3.py:604-676.  From a model of SingularLSTMCells build the 2-factor model.
+    ``rank=`` (keyword-only extension) keeps the top-``rank`` factors of every matrix instead of
+    thresholding.  Output layers always return sequences + TimeDistributed(Dense) (:630,:665,:670)."""
+    rmodel = Sequential()
+    rmodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
+    pivots = []
+    for li, layer in enumerate(model.layers[:-1]):
+        cell = layer.cell
+        if not isinstance(cell, SingularLSTMCell):
+            raise ValueError("make_LSTM_reduced_model expects a model of SingularLSTMCells")
+        if bool(cell.merged_kernel) != bool(merged_kernel):
+            raise ValueError("merged_kernel=%s but layer %d holds a %s SingularLSTMCell"
+                             % (merged_kernel, li, "merged" if cell.merged_kernel else "split"))
+        units = layer.units
+        w_s, u_s, w_l, w_r, u_l, u_r, b = [v.tensor for v in cell.weights]
+        if merged_kernel:
+            wu = []
+            for nm, mat in (("W", [w_l, w_s, w_r]), ("U", [u_l, u_s, u_r])):
+                f, pr = _reduce_one(mat[0], mat[1], mat[2], cutoff, rank, use_abs, "layer %d %s" % (li, nm))
+                wu.append(f)
+                pivots.append(("layer %d %s" % (li, nm), pr))
+            rcell = ReducedLSTMCell(units, w=wu[0], u=wu[1], b=b)
+        else:
+            w, u = [], []
+            w_l4, w_s4, w_r4 = (torch.chunk(a, 4, dim=1) for a in (w_l, w_s, w_r))
+            u_l4, u_s4, u_r4 = (torch.chunk(a, 4, dim=1) for a in (u_l, u_s, u_r))
+            for g in range(4):
+                fw, pw = _reduce_one(w_l4[g], w_s4[g], w_r4[g], cutoff, rank, use_abs, "layer %d W gate %d" % (li, g))
+                fu, pu = _reduce_one(u_l4[g], u_s4[g], u_r4[g], cutoff, rank, use_abs, "layer %d U gate %d" % (li, g))
+                w.append(fw); u.append(fu)
+                pivots += [("layer %d W gate %d" % (li, g), pw), ("layer %d U gate %d" % (li, g), pu)]
+            rcell = ReducedLSTMCell(units, w=w, u=u, b=b, merged_kernel=False)
+        rmodel.add(SingularLSTM(units, cell=rcell, return_sequences=True))
+    _copy_dense_top(model, rmodel, True)
+    rmodel.build()
+    if check_condition and pivots:
+        ratios = torch.cat([p for _, p in pivots]).cpu().numpy()
+        rmodel.pivot_ratios = {name: float(r) for (name, _), r in zip(pivots, ratios)}
+        bad = [n for n, r in rmodel.pivot_ratios.items() if not (r > 1e-6)]
+        if bad:
+            warnings.warn("make_LSTM_reduced_model: V1 is (near-)singular for %s; the reference calls "
+                          "np.linalg.inv unguarded here (svd_classes_v3.py:626). Use the 3-factor model "
+                          "for these matrices." % ", ".join(bad))
+    return rmodel
+
+
+def truncate_singular_model(model, rank):
+    """Top-r truncation of a 3-factor model (keep first r columns / entries / rows of every factor;
+    SURVEY App. A) -- the explicit-rank sweep primitive for the 3-factor form."""
+    smodel = Sequential()
+    smodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
+    for layer in model.layers[:-1]:
+        cell = layer.cell
+        s_w, s_u, w_l, w_r, u_l, u_r, b = [v.tensor for v in cell.weights]
+        H = layer.units
+        if cell.merged_kernel:
+            rw, ru = min(rank, cell.rank_w), min(rank, cell.rank_u)
+            w = [w_l[:, :rw], s_w[:, :rw], w_r[:rw]]
+            u = [u_l[:, :ru], s_u[:, :ru], u_r[:ru]]
+        else:
+            def cut(l, s, r_, k):
+                kk = min(rank, k)
+                ls = [l[:, g * k:g * k + kk] for g in range(4)]
+                ss = [s[:, g * k:g * k + kk] for g in range(4)]
+                return [torch.cat(ls, 1), torch.cat(ss, 1), r_[:kk]]
+            w = cut(w_l, s_w, w_r, cell.rank_w)
+            u = cut(u_l, s_u, u_r, cell.rank_u)
+        ncell = SingularLSTMCell(H, w=w, u=u, b=b, merged_kernel=cell.merged_kernel,
+                                 kernel_regularizer=cell.kernel_regularizer, recurrent_regularizer=cell.recurrent_regularizer,
+                                 train_uv=cell.train_uv, uv_regularizer=cell.uv_regularizer)
+        smodel.add(SingularLSTM(H, cell=ncell, return_sequences=layer.return_sequences))
+    td = isinstance(model.layers[-1], TimeDistributed)
+    _copy_dense_top(model, smodel, td)
+    smodel.build()
+    return smodel
+
+
+def full_model_from_weights(layers, dense, return_sequences=True):
+    """[(W (D,4H), U (H,4H), b (4H,)), ...] + (dense_kernel (H,n), dense_bias (n,)) -> Sequential of
+    stock LSTM layers + Dense: the stand-in for keras.models.load_model (svd_acceleration_v3.py:115)."""
+    m = Sequential()
+    m.add(InputLayer(input_shape=[None, int(np.shape(layers[0][0])[0])]))
+    for i, (W, U, b) in enumerate(layers):
+        H = int(np.shape(U)[0])
+        rs = True if i < len(layers) - 1 else return_sequences
+        m.add(LSTM(H, weights=[W, U, b], return_sequences=rs))
+    dk, db = dense
+    d = Dense(int(np.shape(dk)[1]))
+    top = TimeDistributed(d) if return_sequences else d
+    m.add(top)
+    top.set_weights([dk, db])
+    m.build()
+    return m

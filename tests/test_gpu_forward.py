@@ -1,0 +1,228 @@
+"""GPU parity tests (run with -m gpu on a B200): CUDA forward path vs the float64 oracle on the same
+weights and inputs, through the reference-facing Python API -> C-ABI.
+
+Tolerance (north_star: "within 1e-5 relative per output"): |y - ref| <= 1e-5*|ref| + 2e-6.  The
+absolute term covers outputs crossing zero (h in (-1,1); 2e-6 is ~30 float32 ulps of 1)."""
+import numpy as np
+import pytest
+import torch
+
+import svdlstm
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 2e-6
+
+
+def assert_parity(y, ref, what=""):
+    y = np.asarray(y, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert y.shape == ref.shape, (what, y.shape, ref.shape)
+    err = np.abs(y - ref)
+    tol = RTOL * np.abs(ref) + ATOL
+    worst = np.max(err - tol)
+    assert worst <= 0, "%s: max abs err %.3e (rel %.3e) exceeds tolerance" % (
+        what, err.max(), (err / (np.abs(ref) + 1e-6)).max())
+
+
+def oracle_twin(oracle, model, dtype=np.float64):
+    """Oracle model holding exactly the device model's weights (get_weights() orderings are the contract)."""
+    cells = []
+    lstms = model.layers[:-1]
+    for layer in lstms:
+        c = layer.cell
+        w = c.get_weights()
+        if isinstance(c, svdlstm.SingularLSTMCell):
+            cells.append(oracle.SingularCell(c.units, [w[2], w[0], w[3]], [w[4], w[1], w[5]], w[6],
+                                             merged_kernel=c.merged_kernel, dtype=dtype))
+        elif isinstance(c, svdlstm.ReducedLSTMCell):
+            if c.merged_kernel:
+                cells.append(oracle.ReducedCell(c.units, [w[0], w[1]], [w[2], w[3]], w[4], True, dtype=dtype))
+            else:
+                ww = [[w[4 * g], w[4 * g + 1]] for g in range(4)]
+                uu = [[w[4 * g + 2], w[4 * g + 3]] for g in range(4)]
+                cells.append(oracle.ReducedCell(c.units, ww, uu, w[16], False, dtype=dtype))
+        else:
+            cells.append(oracle.FullCell(c.units, w[0], w[1], w[2], dtype=dtype))
+    dk, db = model.layers[-1].get_weights()
+    return oracle.Model(cells, (dk, db), return_sequences=lstms[-1].return_sequences)
+
+
+@pytest.fixture(scope="module")
+def full(dropbear_weights):
+    layers, dense = dropbear_weights
+    return svdlstm.full_model_from_weights(layers, dense, return_sequences=True)
+
+
+@pytest.fixture(scope="module")
+def x_small():
+    return np.random.default_rng(0).standard_normal((3, 64, 16)).astype(np.float32)
+
+
+@pytest.mark.parametrize("engine", ["general", "wavefront"])
+def test_full_model_parity_and_kat(oracle, full, kat, x_small, engine):
+    y = full.predict(kat["sin_x"].astype(np.float32), engine=engine)[0, :, 0]
+    assert_parity(y, kat["sin_y_full"], "SURVEY App. D KAT (%s)" % engine)
+    assert_parity(full.predict(x_small, engine=engine), oracle_twin(oracle, full).predict(x_small), "full " + engine)
+
+
+@pytest.mark.parametrize("engine", ["general", "wavefront"])
+@pytest.mark.parametrize("merged", [True, False])
+def test_singular_and_reduced_parity_all_ranks(oracle, full, x_small, merged, engine):
+    sm = svdlstm.make_LSTM_singular_model(full, hoyer=0.01, merged_kernel=merged, return_sequences=True)
+    y_full = oracle_twin(oracle, full).predict(x_small)
+    y_sm = sm.predict(x_small, engine=engine)
+    assert_parity(y_sm, oracle_twin(oracle, sm).predict(x_small), "3-factor same-weights")
+    # device SVD (Jacobi) + device forward == the full model (algebraic identity at full rank)
+    assert np.max(np.abs(y_sm - y_full)) < 2e-5
+    for r in (15, 12, 8, 4, 1):
+        tm = svdlstm.truncate_singular_model(sm, r)
+        assert_parity(tm.predict(x_small, engine=engine), oracle_twin(oracle, tm).predict(x_small), "3F top-%d" % r)
+        rm = svdlstm.make_LSTM_reduced_model(sm, merged_kernel=merged, rank=r)
+        assert_parity(rm.predict(x_small, engine=engine), oracle_twin(oracle, rm).predict(x_small), "2F top-%d" % r)
+        # 2-factor and 3-factor forms of the same top-r truncation agree (they differ only in cost)
+        assert np.max(np.abs(rm.predict(x_small, engine=engine) - tm.predict(x_small, engine=engine))) < 5e-5
+    rm = svdlstm.make_LSTM_reduced_model(sm, cutoff=.05, merged_kernel=merged)
+    assert_parity(rm.predict(x_small, engine=engine), oracle_twin(oracle, rm).predict(x_small), "2F cutoff .05")
+    if merged:   # cutoff .05 prunes nothing on merged matrices => reduced == full
+        assert np.max(np.abs(rm.predict(x_small, engine=engine) - y_full)) < 5e-5
+
+
+def test_device_builders_match_oracle_builders(oracle, full, dropbear_weights, x_small):
+    """End to end: device Jacobi SVD + K2b vs np.linalg.svd / inv (the reference's own calls)."""
+    layers, dense = dropbear_weights
+    ofull = oracle.model_from_weights(layers, dense, dtype=np.float64)
+    for merged in (True, False):
+        osm = oracle.make_LSTM_singular_model(ofull, merged_kernel=merged, return_sequences=True, svd_dtype=np.float64)
+        sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=merged, return_sequences=True)
+        for r in (12, 5):
+            y_dev = svdlstm.make_LSTM_reduced_model(sm, merged_kernel=merged, rank=r).predict(x_small)
+            y_or = oracle.make_LSTM_reduced_model(osm, merged_kernel=merged, rank=r).predict(x_small)
+            assert np.max(np.abs(y_dev - y_or)) < 5e-5, (merged, r)
+        # threshold semantics: same kept ranks as the oracle at a cutoff that really prunes
+        cut = 1.0
+        rm = svdlstm.make_LSTM_reduced_model(sm, cutoff=cut, merged_kernel=merged)
+        orm = oracle.make_LSTM_reduced_model(osm, cutoff=cut, merged_kernel=merged)
+        assert [w.shape for w in rm.get_weights()] == [np.shape(w) for w in orm.get_weights()]
+        assert np.max(np.abs(rm.predict(x_small) - orm.predict(x_small))) < 1e-4
+        assert svdlstm.count_weights(rm) == oracle.count_weights(orm)
+
+
+def test_auto_engine_picks_wavefront_and_long_sequence(oracle, full):
+    x = np.random.default_rng(1).standard_normal((1, 6000, 16)).astype(np.float32)
+    y = full.predict(x)
+    assert full.last_engine() == svdlstm.ENGINE_WAVEFRONT
+    assert_parity(y, oracle_twin(oracle, full).predict(x), "T=6000 wavefront")
+    yg = full.predict(x, engine="general")
+    assert np.max(np.abs(y - yg)) < 1e-5
+
+
+def test_layer_kwargs(oracle, dropbear_weights):
+    (W, U, b) = dropbear_weights[0][0]
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((4, 20, 16)).astype(np.float32)
+    ocell = oracle.FullCell(15, W, U, b)
+    h0 = rng.standard_normal((4, 15)).astype(np.float32) * 0.3
+    c0 = rng.standard_normal((4, 15)).astype(np.float32) * 0.3
+    mask = np.ones((4, 20), bool)
+    mask[1, 3:9] = False
+    mask[2, :4] = False
+    for engine in ("general", "wavefront"):
+        def mk(**kw):
+            return svdlstm.LSTM(15, weights=[W, U, b], engine=engine, **kw)
+        out = mk(return_sequences=True, return_state=True)(x, initial_state=[h0, c0])
+        ref = oracle.rnn_layer(ocell, x, initial_state=[h0, c0], return_sequences=True, return_state=True)
+        for a, r in zip(out, ref):
+            assert_parity(a.cpu().numpy(), r, "initial_state/return_state " + engine)
+        assert_parity(mk()(x).cpu().numpy(), oracle.rnn_layer(ocell, x), "last output " + engine)
+        assert_parity(mk(return_sequences=True, go_backwards=True)(x).cpu().numpy(),
+                      oracle.rnn_layer(ocell, x, go_backwards=True, return_sequences=True), "go_backwards " + engine)
+        xt = np.ascontiguousarray(np.swapaxes(x, 0, 1))
+        assert_parity(mk(return_sequences=True, time_major=True)(xt).cpu().numpy(),
+                      oracle.rnn_layer(ocell, xt, time_major=True, return_sequences=True), "time_major " + engine)
+        # stateful: two chunks == one pass (svd_classes_v3.py:421-426)
+        st = mk(return_sequences=True, stateful=True)
+        y12 = torch.cat([st(x[:, :7]), st(x[:, 7:])], 1).cpu().numpy()
+        assert_parity(y12, oracle.rnn_layer(ocell, x, return_sequences=True), "stateful " + engine)
+        st.reset_states()
+        assert_parity(st(x[:, :7]).cpu().numpy(), oracle.rnn_layer(ocell, x[:, :7], return_sequences=True), "reset_states")
+    for zero in (False, True):
+        lay = svdlstm.LSTM(15, weights=[W, U, b], return_sequences=True, return_state=True, zero_output_for_mask=zero)
+        out = lay(x, mask=mask)
+        ref = oracle.rnn_layer(ocell, x, mask=mask, return_sequences=True, return_state=True, zero_output_for_mask=zero)
+        for a, r in zip(out, ref):
+            assert_parity(a.cpu().numpy(), r, "mask zero=%s" % zero)
+    with pytest.raises(ValueError):
+        svdlstm.LSTM(15, weights=[W, U, b], engine="wavefront")(x, mask=mask)
+
+
+def test_cell_call_contract(oracle, full, dropbear_weights):
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True)
+    rm = svdlstm.make_LSTM_reduced_model(sm, rank=7)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 16)).astype(np.float32)
+    h = rng.standard_normal((5, 15)).astype(np.float32) * 0.5
+    c = rng.standard_normal((5, 15)).astype(np.float32) * 0.5
+    for model in (full, sm, rm):
+        cell = model.layers[0].cell
+        out, (h1, c1) = cell.call(x, [h, c])
+        oc = oracle_twin(oracle, model).cells[0]
+        hr, cr = oc.step(x.astype(np.float64), h.astype(np.float64), c.astype(np.float64))
+        assert out is h1
+        assert_parity(h1.cpu().numpy(), hr, "cell h")
+        assert_parity(c1.cpu().numpy(), cr, "cell c")
+    assert [v.name for v in sm.layers[0].cell.weights] == ["kernel", "recurrent_kernel", "w_left", "w_right", "u_left", "u_right", "bias"]
+    assert [p.name for p in sm.layers[0].get_prunable_weights()] == ["kernel", "recurrent_kernel"]
+    assert sm.layers[0].cell.kernel.numpy().shape == (1, 16)
+
+
+def test_set_weights_errors_and_update(oracle, full, x_small):
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    lay = sm.layers[1]
+    w = lay.get_weights()
+    with pytest.raises(ValueError, match="expecting 7 weights"):
+        lay.set_weights(w[:6])
+    bad = list(w)
+    bad[2] = bad[2][:, :5]
+    with pytest.raises(ValueError, match="not compatible"):
+        lay.set_weights(bad)
+    w2 = [a.copy() for a in w]
+    w2[0][0, -3:] = 0.0            # zero three singular values (what Hoyer fine-tuning drives towards)
+    lay.set_weights(w2)
+    assert_parity(sm.predict(x_small), oracle_twin(oracle, sm).predict(x_small), "after set_weights")
+    # S > cutoff now prunes those three
+    rm = svdlstm.make_LSTM_reduced_model(sm, cutoff=.05)
+    assert rm.layers[1].cell.ranks[0] == 12
+    assert np.max(np.abs(rm.predict(x_small) - sm.predict(x_small))) < 5e-5
+    with pytest.raises(ValueError):
+        svdlstm.make_LSTM_reduced_model(sm, merged_kernel=False)
+    with pytest.raises(ValueError):
+        svdlstm.SingularLSTMCell(15, w=[w[2], w[0], w[3]], u=[w[4], w[1], w[5][:, :30]], b=w[6]).build((None, 15))
+
+
+def test_medium_model_general_engine(oracle):
+    """C3-shaped but small enough for the float64 oracle: L=2, H=64, D=16, ranks 8/32/64."""
+    layers, dense = svdlstm.synthetic_layers(16, 64, 2, seed=0)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    x = np.random.default_rng(4).standard_normal((9, 24, 16)).astype(np.float32)
+    assert full.predict(x).shape == (9, 24, 1)
+    assert full.last_engine() == svdlstm.ENGINE_GENERAL
+    assert_parity(full.predict(x), oracle_twin(oracle, full).predict(x), "H=64 full")
+    for merged in (True, False):
+        sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=merged, return_sequences=True)
+        for r in (8, 32, 64):
+            tm = svdlstm.truncate_singular_model(sm, r)
+            assert_parity(tm.predict(x), oracle_twin(oracle, tm).predict(x), "H=64 3F r=%d merged=%s" % (r, merged))
+            rm = svdlstm.make_LSTM_reduced_model(sm, merged_kernel=merged, rank=r)
+            assert_parity(rm.predict(x), oracle_twin(oracle, rm).predict(x), "H=64 2F r=%d merged=%s" % (r, merged))
+
+
+def test_batch_permutation_and_padding_properties(full):
+    """Size-independent properties at a batch that is not a multiple of the CTA tile."""
+    x = torch.randn(37, 50, 16, generator=torch.Generator().manual_seed(5)).cuda()
+    perm = torch.randperm(37, generator=torch.Generator().manual_seed(6)).cuda()
+    for engine in ("general", "wavefront"):
+        y = full(x, engine=engine)
+        assert torch.equal(full(x[perm], engine=engine), y[perm])
+        assert torch.equal(full(x[:5], engine=engine), y[:5])
+        assert torch.isfinite(y).all()

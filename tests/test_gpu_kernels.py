@@ -1,0 +1,202 @@
+"""GPU parity tests for K2 (Jacobi SVD), K2b (B, C construction), K3 (penalties), K4 (sweep SSE), the
+rank sweep and the old explicit-rank API -- each against numpy / the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import svdlstm
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_svd(A, U, S, Vt, rtol=1e-5):
+    A64 = A.astype(np.float64)
+    s_ref = np.linalg.svd(A64, compute_uv=False)
+    k = min(A.shape)
+    assert S.shape == (k,) and U.shape == (A.shape[0], k) and Vt.shape == (k, A.shape[1])
+    assert np.all(np.diff(S) <= 0), "singular values must be sorted descending"
+    assert np.max(np.abs(S - s_ref) / s_ref) < rtol, np.max(np.abs(S - s_ref) / s_ref)
+    rec = (U.astype(np.float64) * S.astype(np.float64)) @ Vt.astype(np.float64)
+    assert np.max(np.abs(rec - A64)) < 5e-6 * max(1.0, s_ref[0])
+    assert np.max(np.abs(U.T.astype(np.float64) @ U - np.eye(k))) < 5e-6
+    assert np.max(np.abs(Vt.astype(np.float64) @ Vt.T - np.eye(k))) < 5e-6
+
+
+def test_svd_shipped_matrices_vs_numpy(dropbear_weights, kat):
+    layers, _ = dropbear_weights
+    for i, (W, U_, b) in enumerate(layers):
+        for nm, M in (("W", W), ("U", U_)):
+            U, S, Vt = (t.cpu().numpy() for t in svdlstm.svd_batched(M))
+            _check_svd(M, U, S, Vt)
+            # vs the numpy (LAPACK gesdd, float32) goldens = what the reference computes at :562
+            assert np.max(np.abs(S - kat["svd_%s%d_s" % (nm, i)]) / kat["svd_%s%d_s" % (nm, i)]) < 1e-5
+            l_ref, r_ref = kat["svd_%s%d_l" % (nm, i)], kat["svd_%s%d_r" % (nm, i)]
+            sign = np.sign(np.sum(Vt * r_ref, axis=1))         # singular vectors up to sign
+            assert np.max(np.abs(Vt * sign[:, None] - r_ref)) < 2e-4
+            assert np.max(np.abs(U * sign[None, :] - l_ref)) < 2e-4
+            # per-gate blocks, batched in one call (:482-502)
+            H = U_.shape[0]
+            blocks = np.stack([M[:, g * H:(g + 1) * H] for g in range(4)])
+            Sg = svdlstm.svd_batched(blocks, compute_uv=False).cpu().numpy()
+            for g in range(4):
+                ref = kat["svd_%s%d_g%d_s" % (nm, i, g)]
+                assert np.max(np.abs(Sg[g] - ref) / ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(16, 1024), (60, 16), (64, 64), (1, 7), (5, 1), (256, 1024), (300, 40)])
+def test_svd_random_shapes(shape):
+    rng = np.random.default_rng(sum(shape))
+    A = rng.standard_normal(shape).astype(np.float32)
+    (U, S, Vt), sw = svdlstm.svd_batched(A, return_sweeps=True)
+    _check_svd(A, U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy())
+    assert 1 <= int(sw[0]) <= 40
+
+
+def test_svd_batched_and_graded_spectrum():
+    rng = np.random.default_rng(7)
+    # graded spectrum: smallest sigma 1e-4 of the largest must still be accurate to 1e-5 relative
+    q1, _ = np.linalg.qr(rng.standard_normal((24, 24)))
+    q2, _ = np.linalg.qr(rng.standard_normal((96, 96)))
+    s = np.logspace(0, -4, 24)
+    A = ((q1 * s) @ q2[:24]).astype(np.float32)
+    batch = np.stack([A, 2 * A, A[::-1].copy()])
+    U, S, Vt = (t.cpu().numpy() for t in svdlstm.svd_batched(batch))
+    for bi in range(3):
+        _check_svd(batch[bi], U[bi], S[bi], Vt[bi])
+    assert np.allclose(S[1], 2 * S[0], rtol=1e-6)
+
+
+def test_reduce_factors_vs_oracle(oracle, dropbear_weights, kat):
+    W = dropbear_weights[0][0][0]
+    l, s, r = np.linalg.svd(W, full_matrices=False)
+    for rank in (16, 8, 3, 1):
+        B, Cm, pr = svdlstm.reduce_factors(l[:, :rank], s[:rank], r[:rank], return_pivot_ratio=True)
+        Bo, Co = oracle._reduce_one(l.astype(np.float64), s.astype(np.float64), r.astype(np.float64), rank=rank)
+        assert np.max(np.abs(B.cpu().numpy() - Bo)) < 2e-6
+        assert np.max(np.abs(Cm.cpu().numpy() - Co)) < 1e-5 * max(1.0, np.abs(Co).max())
+        assert 0 < float(pr[0]) <= 1
+    # reference goldens (np.linalg.inv in float32, svd_classes_v3.py:625-626)
+    B, Cm = svdlstm.reduce_factors(l[:, :8], s[:8], r[:8])
+    assert np.max(np.abs(B.cpu().numpy() - kat["red_rank8_wB"])) < 1e-5
+    assert np.max(np.abs(Cm.cpu().numpy() - kat["red_rank8_wC"])) < 2e-4
+    # singular V1 is flagged, not silently inverted
+    V = np.zeros((2, 5), np.float32)
+    V[0, 2] = 1
+    V[1, 3] = 1
+    _, _, pr = svdlstm.reduce_factors(np.eye(4, 2, dtype=np.float32), np.ones(2, np.float32), V, return_pivot_ratio=True)
+    assert float(pr[0]) == 0.0
+
+
+def test_penalties_vs_oracle(oracle):
+    rng = np.random.default_rng(8)
+    items = [rng.standard_normal((1, 15)), rng.standard_normal((16, 60)), rng.standard_normal((70, 33)),
+             np.linalg.qr(rng.standard_normal((40, 40)))[0], rng.standard_normal((130, 257)), rng.standard_normal((1, 5000))]
+    items = [a.astype(np.float32) for a in items]
+    spec = [(a, a.shape[0] > 1, False) for a in items] + [(items[2], True, True)]
+    raw = svdlstm.evaluate_penalties(spec)
+    raw2 = svdlstm.evaluate_penalties(spec)
+    assert np.array_equal(raw, raw2), "fixed-order reduction must be bit-reproducible"
+    for (a, gram, cols), got in zip(spec, raw):
+        ref = oracle.penalty_raw_sums(a, mode="columns" if cols else "rows")
+        assert math.isclose(got[0], ref[0], rel_tol=1e-6) and math.isclose(got[1], ref[1], rel_tol=1e-6)
+        if gram:
+            assert math.isclose(got[2], ref[2], rel_tol=1e-6, abs_tol=1e-4)
+            assert math.isclose(got[3], ref[3], rel_tol=1e-6, abs_tol=1e-6)
+    s = items[0]
+    assert math.isclose(svdlstm.HoyerRegularizer(0.01)(s), oracle.hoyer_regularizer(s.astype(np.float64), 0.01), rel_tol=1e-5)
+    assert math.isclose(svdlstm.HoyerRegularizer(1.0).l1_over_l2(s), oracle.hoyer_l1_over_l2(s), rel_tol=1e-6)
+    X = items[1]
+    assert math.isclose(svdlstm.OrthogonalRegularizer(0.3)(X), oracle.orthogonal_regularizer_rows(X, 0.3), rel_tol=1e-6)
+    assert svdlstm.OrthogonalRegularizer(1.0)(items[3]) < 1e-6
+    assert svdlstm.OrthogonalRegularizer(1.0).fro_sq(items[3]) < 1e-9
+    with pytest.raises(ValueError):
+        svdlstm.OrthogonalRegularizer(0.3)(np.ones(4, np.float32))
+
+
+def test_model_losses_fused(oracle, dropbear_weights):
+    layers, dense = dropbear_weights
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, hoyer=0.01, orthogonal=0.1, merged_kernel=True)
+    before = svdlstm.launches()
+    losses = sm.losses
+    assert svdlstm.launches() - before == 1          # ONE fused launch for all 18 regularised weights
+    assert len(losses) == 3 * 6
+    ref = []
+    for layer in sm.layers[:-1]:
+        w = layer.get_weights()
+        ref += [oracle.hoyer_regularizer(w[0].astype(np.float64), 0.01), oracle.hoyer_regularizer(w[1].astype(np.float64), 0.01)]
+        ref += [oracle.orthogonal_regularizer_rows(w[i], 0.1) for i in (2, 3, 4, 5)]
+    assert np.allclose(losses, ref, rtol=1e-5, atol=1e-7)
+    assert sm.layers[0].cell.train_uv and sm.layers[0].cell.w_left.trainable
+
+
+def test_sweep_sse_and_metric_goldens(series):
+    y, p = series["y_test"], series["pred"]
+    assert abs(svdlstm.rmse(y, p) - 0.20285040751787883) < 1e-9
+    assert abs(svdlstm.reference_rmse(y, p, y.size) - 0.20285040751787883) < 1e-9
+    rng = np.random.default_rng(9)
+    pred = rng.standard_normal((7, 100003)).astype(np.float32)
+    tgt = rng.standard_normal(100003).astype(np.float32)
+    sse = svdlstm.sweep_sse(pred, tgt).cpu().numpy()
+    ref = ((pred.astype(np.float64) - tgt.astype(np.float64)) ** 2).sum(1)
+    assert np.allclose(sse, ref, rtol=1e-13)
+    assert np.array_equal(sse, svdlstm.sweep_sse(pred, tgt).cpu().numpy())
+
+
+def test_rank_sweep_matches_oracle_and_is_shard_invariant(oracle, dropbear_weights):
+    layers, dense = dropbear_weights
+    full = svdlstm.full_model_from_weights(layers, dense)
+    X = np.random.default_rng(10).standard_normal((13, 40, 16)).astype(np.float32)
+    ranks = [15, 11, 6, 2]
+    res = svdlstm.rank_sweep(full, X, ranks, form="reduced")
+    ofull = oracle.model_from_weights(layers, dense)
+    osm = oracle.make_LSTM_singular_model(ofull, merged_kernel=True, return_sequences=True, svd_dtype=np.float64)
+    y_full = ofull.predict(X)
+    for i, r in enumerate(ranks):
+        yr = oracle.make_LSTM_reduced_model(osm, rank=r).predict(X)
+        assert abs(res["rmse"][i] - oracle.rmse(y_full, yr)) < 2e-5
+        assert np.max(np.abs(res["preds"][i].cpu().numpy() - yr[..., 0])) < 5e-5
+    assert res["rmse"][0] < 1e-5 and res["rmse"][-1] > res["rmse"][1]
+    # "virtual ranks": any partition of the sequences gives bit-identical per-(rank, sequence) outputs
+    _, models = svdlstm.build_rank_models(full, ranks)
+    for world in (2, 4):
+        parts = []
+        for vr in range(world):
+            lo, hi = svdlstm.shard_bounds(13, world, vr)
+            parts.append(svdlstm.rank_sweep(full, X[lo:hi], ranks, models=models)["preds"])
+        assert torch.equal(torch.cat(parts, 1), svdlstm.rank_sweep(full, X, ranks, models=models)["preds"])
+
+
+def test_old_explicit_rank_api(oracle, dropbear_weights, kat):
+    A2 = svdlstm.reduce_matrix_rank(kat["toy_A"], 2)
+    assert np.linalg.matrix_rank(A2.astype(np.float64), tol=1e-4) == 2
+    assert np.max(np.abs(A2 - kat["toy_A_rank2"])) < 5e-6
+    M1, M2 = svdlstm.reduce_two_step(kat["toy_A"], 2)
+    O1, O2 = oracle.reduce_two_step(kat["toy_A"], 2)
+    assert np.max(np.abs(M1 - O1)) < 1e-5 and np.max(np.abs(M2 - O2)) < 1e-5
+    layers, dense = dropbear_weights
+    sub = [layers[1], layers[2]]                       # square layers (the old API "assumes a square model")
+    full = svdlstm.full_model_from_weights(sub, dense)
+    sv = svdlstm.get_model_singular_values(full)
+    ref = oracle.get_model_singular_values(oracle.model_from_weights(sub, dense))
+    assert sv.shape == (2, 2, 4, 15) and np.max(np.abs(sv - ref) / ref) < 1e-5
+    x = np.random.default_rng(11).standard_normal((2, 30, 15)).astype(np.float32)
+    svdlstm.set_model_matrix_rank(full, (0, 1, 2), 9)
+    om = oracle.model_from_weights([tuple(a.copy() for a in l) for l in sub], dense)
+    oracle.set_model_matrix_rank(om, (0, 1, 2), 9)
+    assert np.max(np.abs(full.predict(x) - om.predict(x))) < 2e-5
+    assert np.linalg.matrix_rank(full.layers[0].get_weights()[1][:, 30:45].astype(np.float64), tol=1e-4) == 9
+
+
+def test_weight_counts_device_models(dropbear_weights):
+    layers, dense = dropbear_weights
+    full = svdlstm.full_model_from_weights(layers, dense)
+    assert svdlstm.count_weights(full) == 5656 == full.count_params()
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=False)
+    rm = svdlstm.make_LSTM_reduced_model(sm, merged_kernel=False, rank=8)
+    expect = sum(svdlstm.reduced_split_weight_count(W.shape[0], 15, 8, 8) for W, _, _ in layers) + 16
+    assert svdlstm.count_weights(rm) == expect
+    assert rm._fused_handle().count_weights() == expect - 16
+    assert 0 < svdlstm.weight_reduction_percent(full, rm) < 100

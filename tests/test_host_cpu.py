@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic: sharding, the sweep's exchange step under gloo (world_size 2),
+weight I/O, metrics helpers."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import svdlstm
+from svdlstm import sweep as sweep_mod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 65536, 1000003):
+        for w in (1, 2, 3, 4, 8):
+            b = [svdlstm.shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, N, R, per, out_dir):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    preds_all = torch.tensor(rng.standard_normal((R, N, per)).astype(np.float32))
+    tgt_all = torch.tensor(rng.standard_normal((N, per)).astype(np.float32))
+    lo, hi = sweep_mod.shard_bounds(N, world, rank)
+    p = preds_all[:, lo:hi].contiguous()
+    d = (p.double() - tgt_all[lo:hi].double()[None])
+    sse = (d * d).reshape(R, -1).sum(1)
+    cnt = torch.tensor([float((hi - lo) * per)], dtype=torch.float64)
+    sse_g, cnt_g, preds_g = sweep_mod.exchange_results(p, sse, cnt, N, gather_predictions=True)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), sse=sse_g.numpy(), cnt=cnt_g.numpy(), preds=preds_g.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N", [11, 16])
+def test_sweep_exchange_gloo_world2(tmp_path, N):
+    R, per, world = 3, 5, 2
+    port = 29500 + (os.getpid() % 2000) + N
+    mp.spawn(_gloo_worker, args=(world, port, N, R, per, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    preds_all = rng.standard_normal((R, N, per)).astype(np.float32)
+    tgt_all = rng.standard_normal((N, per)).astype(np.float32)
+    sse_ref = ((preds_all.astype(np.float64) - tgt_all.astype(np.float64)[None]) ** 2).reshape(R, -1).sum(1)
+    outs = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(world)]
+    for o in outs:
+        assert np.array_equal(o["preds"], preds_all)          # un-padded, sequence order
+        assert np.allclose(o["sse"], sse_ref, rtol=1e-13)
+        assert o["cnt"][0] == N * per
+    # every rank holds bit-identical reductions (summed in rank order)
+    assert np.array_equal(outs[0]["sse"], outs[1]["sse"])
+
+
+def test_exchange_without_dist_is_identity():
+    p = torch.zeros(2, 3, 4)
+    s = torch.ones(2, dtype=torch.float64)
+    c = torch.tensor([12.0], dtype=torch.float64)
+    s2, c2, p2 = sweep_mod.exchange_results(p, s, c, 3)
+    assert s2 is s and c2 is c and p2 is p
+
+
+def test_weights_csv_roundtrip(tmp_path, dropbear_weights):
+    layers, dense = dropbear_weights
+    for transposed in (True, False):
+        d = str(tmp_path / ("t%d" % transposed))
+        svdlstm.save_model_weights_csv(layers, dense, d, layer_names=["lstm_69", "lstm_70", "lstm_71"], transposed=transposed)
+        l2, d2 = svdlstm.load_model_weights_csv(d, transposed=transposed)
+        for (W, U, b), (W2, U2, b2) in zip(layers, l2):
+            assert np.array_equal(W, W2) and np.array_equal(U, U2) and np.array_equal(b, b2)
+        assert np.array_equal(dense[0], d2[0]) and np.array_equal(dense[1], d2[1])
+    # shipped layout: Wi.csv is units x input_dim (transposed)
+    wi = np.loadtxt(os.path.join(str(tmp_path / "t1"), "lstm_69", "Wi.csv"), delimiter=",")
+    assert wi.shape == (15, 16)
+    l3, d3 = svdlstm.load_model_weights_npz(os.path.join(ROOT, "tests", "golden", "dropbear_weights.npz"))
+    assert len(l3) == 3 and l3[0][0].shape == (16, 60) and d3[0].shape == (15, 1)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/model_weights"), reason="reference fixtures not on this box")
+def test_loader_reads_the_reference_fixture(dropbear_weights):
+    layers, dense = svdlstm.load_model_weights_csv("/root/reference/code/model_weights",
+                                                   layer_names=["lstm_69", "lstm_70", "lstm_71"])
+    for (W, U, b), (W2, U2, b2) in zip(layers, dropbear_weights[0]):
+        assert np.array_equal(W, W2) and np.array_equal(U, U2) and np.array_equal(b, b2)
+    assert sum(W.size + U.size + b.size for W, U, b in layers) + 16 == 5656
+
+
+def test_metrics_host_helpers(series):
+    y, p = series["y_test"].astype(np.float64), series["pred"].astype(np.float64)
+    assert abs(svdlstm.signaltonoise(y, p) - 12.433968928917704) < 1e-7
+    inv = svdlstm.signaltonoise(y, p, invert=True, dB=False)
+    assert math.isclose(inv, 1.0 / svdlstm.signaltonoise(y, p, dB=False), rel_tol=1e-12)
+    assert svdlstm.full_weight_count(16, 15) + 2 * svdlstm.full_weight_count(15, 15) + 16 == 5656
+    assert svdlstm.reduced_merged_weight_count(16, 15, 16, 15) == 16 * 60 + 15 * 60 + 60   # full rank == dense
+    assert svdlstm.reduced_split_weight_count(15, 15, 15, 15) == svdlstm.full_weight_count(15, 15)
+
+
+def test_synthetic_layers_shapes():
+    layers, dense = svdlstm.synthetic_layers(16, 32, 2, seed=0)
+    assert layers[0][0].shape == (16, 128) and layers[1][0].shape == (32, 128) and dense[0].shape == (32, 1)
+    U = layers[0][1][:, :32].astype(np.float64)
+    assert np.allclose(U.T @ U, np.eye(32), atol=1e-5)
+    assert np.all(layers[0][2][32:64] == 1) and np.all(layers[0][2][:32] == 0)
+
+
+def test_regularizer_surface():
+    h = svdlstm.HoyerRegularizer(0.01)
+    assert h.get_config() == {"hoyer": np.float32(0.01)}
+    assert svdlstm.HoyerRegularizer(None).hoyer == 0
+    with pytest.raises(ValueError):
+        svdlstm.OrthogonalRegularizer(0.1, mode="diag")
+    o = svdlstm.OrthogonalRegularizer(0.5)
+    assert o.from_raw([0, 0, 3.0, 0], (4, 9)) == 0.5 * 0.5 * 3.0 / 6.0
