@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SVD-factored LSTM hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--rank R] [--engine auto|general|tc_bf16] [--batch B] [--seq-len T] [--quick]
+
+Workload (BASELINE.json configs[2], the config the metric "low-rank LSTM timesteps/sec (batch 4096)" is
+quoted on): synthetic 2-layer SVD-LSTM, D=16, H=256, seq_len=1024, batch=4096 per GPU, 3-factor form
+truncated to rank R (default 128), Dense(1) top.  One "step" = one forward pass of the whole batch
+through all T timesteps, all layers and the Dense top.  value = sequence-timesteps/s over all GPUs
+(weak scaling: every GPU runs its own 4096 sequences; the path shards by independent sequences with
+no data-path collective).  The batch-1 half of the metric (us/step vs rank on the shipped DROPBEAR
+model, configs[1]) is measured in the same run and reported under "batch1_us_per_step".
+
+The CPU oracle is used ONLY for the `cpu_baseline` leg and for `--impl reference` (a bounded sample of
+the same workload on the host cores); it is never on the measured GPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rank", type=int, default=128)
+    ap.add_argument("--engine", default=None)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--seq-len", type=int, default=1024)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--quick", action="store_true", help="small shapes (CI / profiling)")
+    ap.add_argument("--no-batch1", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    if a.quick:
+        a.batch, a.seq_len = 512, 64
+    return a
+
+
+def flops_per_seq_step(D, H, L, r, form="singular"):
+    """Algorithmic GEMM FLOPs per sequence-timestep: 2*sum_l[r_w(D_l+4H) + r_u*5H]."""
+    macs = 0
+    d = D
+    for _ in range(L):
+        rw, ru = min(r, d, 4 * H), min(r, H)
+        if form == "singular":
+            macs += rw * (d + 4 * H) + ru * 5 * H
+        else:
+            macs += rw * (d + 4 * H - rw) + ru * (5 * H - ru)
+        d = H
+    return 2 * macs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(a, svdlstm):
+    layers, dense = svdlstm.synthetic_layers(16, a.hidden, a.layers, seed=0)
+    full = svdlstm.full_model_from_weights(layers, dense, return_sequences=True)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    model = svdlstm.truncate_singular_model(sm, a.rank)
+    return layers, dense, model
+
+
+def cpu_forward_sample(layers, dense, rank, Bs, Ts, seed=0):
+    """Reference maths (oracle port, float32, batched numpy => multithreaded BLAS) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import svdlstm_oracle as O
+    ofull = O.model_from_weights(layers, dense, dtype=np.float32)
+    osm = O.make_LSTM_singular_model(ofull, merged_kernel=True, return_sequences=True, svd_dtype=np.float32, dtype=np.float32)
+    om = O.truncate_singular_model(osm, rank, dtype=np.float32)
+    x = np.random.default_rng(seed).standard_normal((Bs, Ts, 16)).astype(np.float32)
+    om.predict(x[:, :2])                      # warm-up
+    t0 = time.perf_counter()
+    om.predict(x)
+    dt = time.perf_counter() - t0
+    return Bs * Ts / dt, dt
+
+
+def reference_arm(a):
+    """--impl reference: the reference's maths (oracle port; TF/Keras itself is not installable here)
+    on the host cores, bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers, dense = None, None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import svdlstm_oracle as O
+    layers, dense = O.synthetic_layers(16, a.hidden, a.layers, seed=0)
+    Bs, Ts = (256, 8) if not a.quick else (64, 4)
+    cores = os.cpu_count() or 1
+    vals = []
+    for i in range(a.warmup + a.steps):
+        v, dt = cpu_forward_sample(layers, dense, a.rank, Bs, Ts, seed=i)
+        if i >= a.warmup:
+            vals.append((v, dt))
+    v = float(np.mean([x[0] for x in vals]))
+    ms = float(np.mean([x[1] for x in vals])) * 1e3
+    sample = "B=%d of %d sequences x T=%d of %d steps per step, float32 numpy (multithreaded BLAS)" % (Bs, a.batch, Ts, a.seq_len)
+    line = {"impl": "reference", "metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": v, "unit": "sequence-timesteps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a),
+            "cpu_baseline": {"value": v, "unit": "sequence-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "sequence-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(a):
+    return {"workload": "synthetic %d-layer SVD-LSTM (3-factor, merged) D=16 H=%d seq_len=%d batch=%d/GPU rank=%d + Dense(1)"
+                        % (a.layers, a.hidden, a.seq_len, a.batch, a.rank),
+            "rank": a.rank, "form": "singular", "batch_per_gpu": a.batch, "seq_len": a.seq_len, "hidden": a.hidden, "layers": a.layers,
+            "l2": "inputs larger than L2 (x is %.0f MB per GPU)" % (a.batch * a.seq_len * 16 * 4 / 1e6),
+            "parallelism": "independent sequences per GPU, no data-path collective"}
+
+
+def batch1_table(svdlstm, torch):
+    """configs[1]: shipped DROPBEAR model, batch 1, us/timestep at full rank and truncated ranks."""
+    layers, dense = svdlstm.load_model_weights_npz(os.path.join(ROOT, "tests", "golden", "dropbear_weights.npz"))
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    T = 20000
+    x = torch.randn(1, T, 16, generator=torch.Generator().manual_seed(0)).cuda()
+    out = {}
+
+    def tm(model, label, engine=None):
+        model(x[:, :256], engine=engine)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(x, engine=engine)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[label] = round(best * 1e3 / T, 4)
+
+    tm(full, "full")
+    for r in (15, 12, 8, 4, 1):
+        tm(svdlstm.truncate_singular_model(sm, r), "3F_r%d" % r)
+        tm(svdlstm.make_LSTM_reduced_model(sm, rank=r), "2F_r%d" % r)
+    tm(full, "full_general_engine", engine="general")
+    # algorithmic on-chip bytes/step of the 3-factor model at full rank: 28 140 B
+    byt = 28140.0
+    return {"unit": "us/timestep", "T": T, "model": "DROPBEAR 3x15 LSTM + Dense(1), batch 1", "us_per_step": out,
+            "onchip_roofline": {"bytes_per_step_3F_r15": byt, "achieved_gbs": round(byt / (out["3F_r15"] * 1e-6) / 1e9, 2),
+                                "peak_gbs_1sm": 251.5, "frac": round(byt / (out["3F_r15"] * 1e-6) / 1e9 / 251.5, 4),
+                                "note": "peak = 128 B/clk x 1965 MHz, one SM (the latency chain uses one CTA)"},
+            "realtime_budget_us": 400.0}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    import torch
+    import svdlstm
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (native) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    layers, dense, model = build_workload(a, svdlstm)
+    B, T, D = a.batch, a.seq_len, 16
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, T, D, generator=gen).pin_memory()
+    x = x_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    engine = a.engine
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        y = model(x, engine=engine)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = svdlstm.launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(a.steps):
+        evs[i][0].record()
+        y = model(x, engine=engine)
+        evs[i][1].record()
+    t1.record()
+    barrier()
+    launches = svdlstm.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))
+    tt = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / a.steps
+    value = world * B * T / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host X -> device -> forward -> y back to host -----
+    e2e = None
+    if not a.no_e2e:
+        y_host = torch.empty((B, T, 1), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            y_host.copy_(model(x_host.to(dev, non_blocking=True), engine=engine), non_blocking=True)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            y_host.copy_(model(x_host.to(dev, non_blocking=True), engine=engine), non_blocking=True)
+        s1.record()
+        barrier()
+        te = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te[0]) / a.steps
+        e2e = {"value": world * B * T / (e2e_ms * 1e-3), "unit": "sequence-timesteps/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    fl = flops_per_seq_step(D, a.hidden, a.layers, a.rank) * B * T
+    achieved = fl / (kern_ms * 1e-3) / 1e12
+    eng_id = model.last_engine()
+    eng_name = {0: "auto", 1: "general(fp32 cuda cores)", 2: "wavefront(fp32)", 3: "tc_bf16(tcgen05)"}.get(eng_id, str(eng_id))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
+                "kernel": eng_name, "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms}
+    line = {"metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": value, "unit": "sequence-timesteps/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if eng_id == 3 else "f32", "data": "synthetic", "config": workload_config(a),
+            "engine": eng_name, "roofline": roofline, "clocks": clocks, "gpu_launches": launches}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not a.no_batch1 and world == 1:
+        line["batch1_us_per_step"] = batch1_table(svdlstm, torch)
+    if not a.no_cpu_baseline and world == 1:
+        Bs, Ts = (256, 8) if not a.quick else (64, 4)
+        v, dt = cpu_forward_sample(layers, dense, a.rank, Bs, Ts)
+        line["cpu_baseline"] = {"value": v, "unit": "sequence-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "B=%d of %d sequences x T=%d of %d steps, float32 numpy oracle (multithreaded BLAS), %.1f s"
+                                          % (Bs, B, Ts, T, dt)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
