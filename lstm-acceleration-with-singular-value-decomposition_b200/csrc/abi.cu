@@ -245,7 +245,7 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
       rc = run_general(h->md, h->dev_md, a, stream, &launches);
       break;
     case SVDLSTM_ENGINE_WAVEFRONT:
-      SVD_REQUIRE(wavefront_supported(h->md, a), "svdlstm_forward: wavefront engine needs units,input_dim,ranks <= 32, <= %d layers, n_out <= 1 and no mask / go_backwards", 7);
+      SVD_REQUIRE(wavefront_supported(h->md, a), "svdlstm_forward: wavefront engine needs units,input_dim,ranks <= 32, <= %d layers, n_out <= 1, no mask, and factors within the register budget", 6);
       rc = run_wavefront(h->md, h->dev_md, a, stream, &launches);
       break;
     case SVDLSTM_ENGINE_TC_BF16: {

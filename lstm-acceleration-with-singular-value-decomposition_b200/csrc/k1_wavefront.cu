@@ -61,7 +61,7 @@ struct WfPlan {
 
 // Layout shared by host (support check + smem size) and device (prologue).
 __host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl) {
-  if (md.n_layers > 7) return false;
+  if (md.n_layers > 6) return false;
   if (md.input_dim > 32 || md.n_out > 1) return false;
   pl.L = md.n_layers;
   pl.D = md.input_dim;
@@ -96,7 +96,7 @@ __host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl) {
     w.off_RT = off;      off += 4 * w.H * w.S2;
     w.off_scale = off;   off += w.P_pad;
     w.off_bias = off;    off += round4(4 * w.H);
-    w.off_p = off;       off += w.P_pad;
+    w.off_p = off;       off += w.P_pad + 64;   // + zero tail: stage 2 reads a full K4*4 window
     w.off_vh = off;      off += 2 * w.S1;   // double-buffered h_l (zero padded to S1)
     w.off_qmeta = off;   off += w.P_pad;    // per-q: bit0 from_h, bits 8.. = padded input length
   }
@@ -108,9 +108,41 @@ __host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl) {
   return (size_t)off * sizeof(float) <= 200 * 1024;
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-// tanh(x) = 2*sigmoid(2x) - 1 ; absolute error ~1e-7 (ex2.approx + rcp.approx), saturates correctly
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f); }
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 1/(1+2^(-x log2 e)); tanh(x) = 2*sigmoid(2x) - 1.  Two MUFU ops each, absolute error
+// ~1e-7 (ex2.approx / rcp.approx are <= 2 ulp); both saturate correctly (2^-inf = 0, rcp(inf) = 0).
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(-2.8853900817779268f * x)), -1.0f); }
+
+// explicit shared-space accesses on precomputed 32-bit addresses (no generic->shared conversion per tick)
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+// Blackwell packed FP32x2 FMA: two IEEE fma.rn per issue slot (SASS FFMA2)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -120,7 +152,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a) {
+// Template shape (max over layers, zero padded): KIN4 float4s of stage-1 input, MP stage-1 columns
+// per lane, K4 float4s of stage-2 contraction, G gates per lane (2: two lanes per unit, 4: one).
+template <int KIN4, int MP, int K4, int G>
+__global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ WfPlan pl;
   const ModelDesc& md = *mdp;
@@ -200,30 +235,72 @@ __global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __
   }
   __syncthreads();
 
-  // ---------------- per-warp persistent state ------------------------------------------------
+  // ---------------- per-warp persistent state: weights -> REGISTERS ---------------------------
   const int role = warp;  // 0: loader, 1..L: layers, L+1: output
+  const int lyr = role - 1;
+  const bool is_layer = role >= 1 && role <= L;
+  const WfLayer& wl = pl.layers[is_layer ? lyr : 0];
+  const int H = wl.H;
+  constexpr int HP = (G == 4) ? 32 : 16;
+  const int j = lane % HP, sub = lane / HP;
+
+  // stage-1 weights of my columns over the concatenated input [x_t | h(t-1)] (packed pairs; the half a
+  // column does not use is zero, so no per-lane select is needed; sigma is folded in: v.(L*sigma))
+  f2_t w1[MP][KIN4 * 4];
+  f2_t w2[G][K4 * 2];       // stage-2 weights of my gate columns (packed pairs)
+  float bias2[G];
+  unsigned pofs[G];         // shared address of the p window each of my gates contracts with
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   float c_state = 0.f, h_last = 0.f;
-  int lyr = role - 1;
-  if (role >= 1 && role <= L) {
+  if (is_layer) {
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      const int q = lane + 32 * m;
+      const bool ok = q < wl.P_pad;
+      const int meta = ok ? __float_as_int(smem[wl.off_qmeta + q]) : 0;
+      const bool fh = meta & 1;
+      const float sc = ok ? smem[wl.off_scale + q] : 0.f;
+#pragma unroll
+      for (int i = 0; i < KIN4 * 2; ++i) {
+        const float lo = (ok && 2 * i < wl.S1) ? sc * smem[wl.off_LT + q * wl.S1 + 2 * i] : 0.f;
+        const float hi = (ok && 2 * i + 1 < wl.S1) ? sc * smem[wl.off_LT + q * wl.S1 + 2 * i + 1] : 0.f;
+        w1[m][i] = fh ? 0ull : pack2(lo, hi);
+        w1[m][KIN4 * 2 + i] = fh ? pack2(lo, hi) : 0ull;
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      const int gate = sub * G + gi;
+      const bool ok = j < H;
+      const int n = gate * H + (ok ? j : 0);
+      const int grp = wl.n_groups == 1 ? 0 : gate;
+      pofs[gi] = smem_base + 4u * (unsigned)(wl.off_p + wl.g_start[grp]);
+      bias2[gi] = ok ? smem[wl.off_bias + n] : 0.f;
+#pragma unroll
+      for (int kk = 0; kk < K4 * 2; ++kk) {
+        const float lo = (ok && 2 * kk < wl.g_K[grp]) ? smem[wl.off_RT + n * wl.S2 + 2 * kk] : 0.f;
+        const float hi = (ok && 2 * kk + 1 < wl.g_K[grp]) ? smem[wl.off_RT + n * wl.S2 + 2 * kk + 1] : 0.f;
+        w2[gi][kk] = pack2(lo, hi);
+      }
+    }
     if (a.c0 != nullptr) {
       size_t soff = 0;
       for (int l = 0; l < lyr; ++l) soff += (size_t)B * pl.layers[l].H;
-      const WfLayer& w0 = pl.layers[lyr];
-      const int HP = 32 / w0.LU;
-      if (lane < HP && lane < w0.H) {
-        c_state = a.c0[soff + (size_t)b * w0.H + lane];
-        h_last = a.h0[soff + (size_t)b * w0.H + lane];
+      if (sub == 0 && j < H) {
+        c_state = a.c0[soff + (size_t)b * H + j];
+        h_last = a.h0[soff + (size_t)b * H + j];
       }
     }
   }
   const float* xrow_base = a.x;
+  const int off_x = pl.off_x, xstride = pl.xstride;
   // loader prologue: prefetch the first kPrefetch steps
   if (role == 0) {
     for (int s = 0; s < kPrefetch; ++s) {
       if (s < T && lane < D) {
         const int t = backwards ? (T - 1 - s) : s;
         const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
-        cp_async4(&smem[pl.off_x + (s % kXRing) * pl.xstride + lane], src);
+        cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
       }
       cp_async_commit();
     }
@@ -235,12 +312,17 @@ __global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __
   const int HL = pl.layers[L - 1].H;
   const int n_out = md.n_out;
   const int n_y = n_out > 0 ? 1 : HL;
-  // register copies of the plan entries this warp touches every tick
-  const WfLayer w = pl.layers[(lyr >= 0 && lyr < L) ? lyr : 0];
-  const int vin_off = (lyr <= 0) ? pl.off_x : pl.layers[(lyr < L ? lyr : L) - 1].off_vh;
-  const int vin_stride = (lyr <= 0) ? pl.xstride : pl.layers[(lyr < L ? lyr : L) - 1].S1;
+  const int vin_off = (lyr <= 0 || !is_layer) ? off_x : pl.layers[lyr - 1].off_vh;
+  const int vin_stride = (lyr <= 0 || !is_layer) ? xstride : pl.layers[lyr - 1].S1;
+  const int my_Ppad = wl.P_pad;
+  const unsigned vin_addr = smem_base + 4u * (unsigned)vin_off, vin_sb = 4u * (unsigned)vin_stride;
+  const unsigned vh_addr = smem_base + 4u * (unsigned)wl.off_vh, vh_sb = 4u * (unsigned)wl.S1;
+  const unsigned p_st_addr = smem_base + 4u * (unsigned)(wl.off_p + lane);
+  const bool same_window = __all_sync(0xffffffffu, pofs[0] == pofs[G - 1]);   // warp-uniform
   const int out_vh_off = pl.layers[L - 1].off_vh, out_vh_stride = pl.layers[L - 1].S1;
-  const int off_y = pl.off_y, off_dense = pl.off_dense, off_x = pl.off_x, xstride = pl.xstride;
+  const int off_y = pl.off_y, off_dense = pl.off_dense;
+  const float dense_w = (role == L + 1 && n_out > 0 && lane < HL) ? smem[off_dense + lane] : 0.f;
+  const float dense_b = (n_out > 0) ? smem[off_dense + 32] : 0.f;
 
   for (int tick = 0; tick < n_ticks; ++tick) {
     if (role == 0) {
@@ -253,85 +335,95 @@ __global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __
       }
       cp_async_commit();
       cp_async_wait<kPrefetch - 2>();   // everything up to step tick+1 has landed before the barrier
-    } else if (role <= L) {
+    } else if (is_layer) {
       const int step = tick - lyr;
       if (step >= 0 && step < T) {
-        const int H = w.H;
-        const float* vin = &smem[vin_off + ((lyr == 0) ? (step % kXRing) : (step & 1)) * vin_stride];
-        const float* vh = &smem[w.off_vh + ((step + 1) & 1) * w.S1];   // h_l(step-1)
-        float* vh_out = &smem[w.off_vh + (step & 1) * w.S1];
-        float* pbuf = &smem[w.off_p];
-        // ---- stage 1 ------------------------------------------------------------------------
-        for (int q = lane; q < w.P_pad; q += 32) {
-          const int meta = __float_as_int(smem[w.off_qmeta + q]);
-          const int kin4 = meta >> 8;
-          const float4* v4 = reinterpret_cast<const float4*>((meta & 1) ? vh : vin);
-          const float4* l4 = reinterpret_cast<const float4*>(&smem[w.off_LT + q * w.S1]);
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-          for (int i = 0; i < kin4 / 4; ++i) {
-            const float4 wv = l4[i];
-            const float4 vv = v4[i];
-            a0 = fmaf(vv.x, wv.x, a0);
-            a1 = fmaf(vv.y, wv.y, a1);
-            a2 = fmaf(vv.z, wv.z, a2);
-            a3 = fmaf(vv.w, wv.w, a3);
+        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? (step % kXRing) : (step & 1)) * vin_sb;
+        const unsigned ha = vh_addr + (unsigned)((step + 1) & 1) * vh_sb;       // h_l(step-1)
+        const unsigned ho = vh_addr + (unsigned)(step & 1) * vh_sb + 4u * (unsigned)j;
+        // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
+        float4 vi[KIN4], vh[KIN4];
+#pragma unroll
+        for (int i = 0; i < KIN4; ++i) {
+          vi[i] = lds128(va + 16u * i);
+          vh[i] = lds128(ha + 16u * i);
+        }
+#pragma unroll
+        for (int m = 0; m < MP; ++m) {
+          f2_t a0 = 0ull, a1 = 0ull;
+#pragma unroll
+          for (int i = 0; i < KIN4; ++i) {
+            a0 = ffma2(pack2(vi[i].x, vi[i].y), w1[m][2 * i + 0], a0);
+            a1 = ffma2(pack2(vi[i].z, vi[i].w), w1[m][2 * i + 1], a1);
           }
-          pbuf[q] = ((a0 + a1) + (a2 + a3)) * smem[w.off_scale + q];
+#pragma unroll
+          for (int i = 0; i < KIN4; ++i) {
+            a0 = ffma2(pack2(vh[i].x, vh[i].y), w1[m][KIN4 * 2 + 2 * i + 0], a0);
+            a1 = ffma2(pack2(vh[i].z, vh[i].w), w1[m][KIN4 * 2 + 2 * i + 1], a1);
+          }
+          float s0, s1, s2, s3;
+          unpack2(a0, s0, s1);
+          unpack2(a1, s2, s3);
+          if (lane + 32 * m < my_Ppad) sts32(p_st_addr + 128u * m, (s0 + s1) + (s2 + s3));
         }
         __syncwarp();
-        // ---- stage 2 + 3 ----------------------------------------------------------------------
-        const int LU = w.LU, G = 4 / LU, HP = 32 / LU;
-        const int j = lane % HP, sub = lane / HP;
-        float act[4] = {0.f, 0.f, 0.f, 0.f};
-        if (j < H) {
-          float z[4];
+        // ---- stage 2: z = bias + <p[window], RT[n,:]> ; stage 3: gates ---------------------------
+        float zz[G];
+        if (same_window) {   // merged / full forms: every gate contracts with the same p window
+          float4 pw[K4];
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            if (gi < G) {
-              const int gate = sub * G + gi;
-              const int n = gate * H + j;
-              const int grp = w.n_groups == 1 ? 0 : gate;
-              const float4* p4 = reinterpret_cast<const float4*>(pbuf + w.g_start[grp]);
-              const float4* r4 = reinterpret_cast<const float4*>(&smem[w.off_RT + n * w.S2]);
-              float a0 = smem[w.off_bias + n], a1 = 0.f;
-              const int K4 = w.g_K[grp] / 4;
-              for (int kk = 0; kk < K4; ++kk) {
-                const float4 rv = r4[kk];
-                const float4 pv = p4[kk];
-                a0 = fmaf(pv.x, rv.x, a0);
-                a1 = fmaf(pv.y, rv.y, a1);
-                a0 = fmaf(pv.z, rv.z, a0);
-                a1 = fmaf(pv.w, rv.w, a1);
-              }
-              z[gi] = a0 + a1;
+          for (int kk = 0; kk < K4; ++kk) pw[kk] = lds128(pofs[0] + 16u * kk);
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) {
+            f2_t a0 = pack2(bias2[gi], 0.f), a1 = 0ull;
+#pragma unroll
+            for (int kk = 0; kk < K4; ++kk) {
+              a0 = ffma2(pack2(pw[kk].x, pw[kk].y), w2[gi][2 * kk + 0], a0);
+              a1 = ffma2(pack2(pw[kk].z, pw[kk].w), w2[gi][2 * kk + 1], a1);
             }
+            float s0, s1, s2, s3;
+            unpack2(a0, s0, s1);
+            unpack2(a1, s2, s3);
+            zz[gi] = (s0 + s1) + (s2 + s3);
           }
+        } else {             // split forms: one p window per gate
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            if (gi < G) {
-              const int gate = sub * G + gi;
-              act[gi] = (gate == 2) ? fast_tanh(z[gi]) : fast_sigmoid(z[gi]);
+          for (int gi = 0; gi < G; ++gi) {
+            float4 pw[K4];
+#pragma unroll
+            for (int kk = 0; kk < K4; ++kk) pw[kk] = lds128(pofs[gi] + 16u * kk);
+            f2_t a0 = pack2(bias2[gi], 0.f), a1 = 0ull;
+#pragma unroll
+            for (int kk = 0; kk < K4; ++kk) {
+              a0 = ffma2(pack2(pw[kk].x, pw[kk].y), w2[gi][2 * kk + 0], a0);
+              a1 = ffma2(pack2(pw[kk].z, pw[kk].w), w2[gi][2 * kk + 1], a1);
             }
+            float s0, s1, s2, s3;
+            unpack2(a0, s0, s1);
+            unpack2(a1, s2, s3);
+            zz[gi] = (s0 + s1) + (s2 + s3);
           }
         }
+        float act[G];
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          // sigmoid for i,f,o ; tanh for the candidate gate (gate 2): same code, scale/offset select
+          const bool is_tanh = (G == 4) ? (gi == 2) : (sub == 1 && gi == 0);
+          const float k = is_tanh ? -2.8853900817779268f : -1.4426950408889634f;
+          const float r = rcp_ftz(1.0f + ex2_ftz(k * zz[gi]));
+          act[gi] = is_tanh ? fmaf(2.0f, r, -1.0f) : r;
+        }
         float ig, fg, gg, og;
-        if (LU == 1) {
+        if (G == 4) {
           ig = act[0]; fg = act[1]; gg = act[2]; og = act[3];
-        } else if (LU == 2) {
+        } else {
           const float o0 = __shfl_xor_sync(0xffffffffu, act[0], 16);
           const float o1 = __shfl_xor_sync(0xffffffffu, act[1], 16);
           ig = act[0]; fg = act[1]; gg = o0; og = o1;   // valid in sub==0 lanes
-        } else {
-          const float v1 = __shfl_sync(0xffffffffu, act[0], (lane & 7) + 8);
-          const float v2 = __shfl_sync(0xffffffffu, act[0], (lane & 7) + 16);
-          const float v3 = __shfl_sync(0xffffffffu, act[0], (lane & 7) + 24);
-          ig = act[0]; fg = v1; gg = v2; og = v3;
         }
-        if (sub == 0 && j < H) {
-          c_state = fmaf(fg, c_state, ig * gg);
-          h_last = og * fast_tanh(c_state);
-          vh_out[j] = h_last;
-        }
+        c_state = fmaf(fg, c_state, ig * gg);
+        h_last = og * fast_tanh(c_state);
+        if (sub == 0 && j < H) sts32(ho, h_last);
       }
     } else if (role == L + 1) {
       // ---- output stage ----------------------------------------------------------------------
@@ -339,10 +431,10 @@ __global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __
       if (step >= 0 && step < T) {
         const float* hv = &smem[out_vh_off + (step & 1) * out_vh_stride];
         if (n_out > 0) {
-          float v = (lane < HL) ? hv[lane] * smem[off_dense + lane] : 0.f;
+          float v = (lane < HL) ? hv[lane] * dense_w : 0.f;
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-          v += smem[off_dense + 32];
+          v += dense_b;
           if (ret_seq) {
             if (lane == 0) smem[off_y + (step % kYRing)] = v;
             if ((step % kYRing) == kYRing - 1 || step == T - 1) {
@@ -371,32 +463,87 @@ __global__ void __launch_bounds__(288) lstm_wavefront_kernel(const ModelDesc* __
   }
 
   // ---------------- final state ----------------------------------------------------------------
-  if (role >= 1 && role <= L && (a.h_n || a.c_n)) {
+  if (is_layer && (a.h_n || a.c_n)) {
     size_t soff = 0;
     for (int l = 0; l < lyr; ++l) soff += (size_t)B * pl.layers[l].H;
-    const int HP = 32 / w.LU;
-    if (lane < HP && lane < w.H) {
-      if (a.h_n) a.h_n[soff + (size_t)b * w.H + lane] = h_last;
-      if (a.c_n) a.c_n[soff + (size_t)b * w.H + lane] = c_state;
+    if (sub == 0 && j < H) {
+      if (a.h_n) a.h_n[soff + (size_t)b * H + j] = h_last;
+      if (a.c_n) a.c_n[soff + (size_t)b * H + j] = c_state;
     }
   }
 }
+
+// ---- template selection ------------------------------------------------------------------------
+struct WfShape {
+  int kin4, mp, k4, g;
+};
+
+inline bool wf_shape(const WfPlan& pl, WfShape& s) {
+  int kin = 0, pp = 0, k = 0, hmax = 0;
+  for (int l = 0; l < pl.L; ++l) {
+    const WfLayer& w = pl.layers[l];
+    kin = kin > round4(w.H > w.Din ? w.H : w.Din) ? kin : round4(w.H > w.Din ? w.H : w.Din);
+    pp = pp > w.P_pad ? pp : w.P_pad;
+    for (int g = 0; g < w.n_groups; ++g) k = k > w.g_K[g] ? k : w.g_K[g];
+    hmax = hmax > w.H ? hmax : w.H;
+  }
+  s.kin4 = kin <= 16 ? 4 : 8;
+  s.mp = pp <= 32 ? 1 : (pp <= 64 ? 2 : 4);
+  s.k4 = k <= 8 ? 2 : (k <= 16 ? 4 : (k <= 32 ? 8 : 16));
+  s.g = hmax <= 16 ? 2 : 4;
+  // register budget of the weight arrays (floats per lane)
+  return s.mp * s.kin4 * 8 + s.g * s.k4 * 4 <= 200;
+}
+
+typedef void (*WfKernel)(const ModelDesc*, ForwardArgs);
+
+template <int KIN4, int MP, int K4>
+WfKernel wf_pick_g(int g) {
+  if (g == 2) return lstm_wavefront_kernel<KIN4, MP, K4, 2>;
+  if constexpr (MP * KIN4 * 8 + 4 * K4 * 4 <= 200) return lstm_wavefront_kernel<KIN4, MP, K4, 4>;
+  return nullptr;
+}
+template <int KIN4, int MP>
+WfKernel wf_pick_k(int k4, int g) {
+  switch (k4) {
+    case 2: return wf_pick_g<KIN4, MP, 2>(g);
+    case 4: return wf_pick_g<KIN4, MP, 4>(g);
+    case 8: return wf_pick_g<KIN4, MP, 8>(g);
+    default:
+      if constexpr (MP * KIN4 * 8 + 2 * 16 * 4 <= 200) return wf_pick_g<KIN4, MP, 16>(g);
+      return nullptr;
+  }
+}
+template <int KIN4>
+WfKernel wf_pick_mp(int mp, int k4, int g) {
+  switch (mp) {
+    case 1: return wf_pick_k<KIN4, 1>(k4, g);
+    case 2: return wf_pick_k<KIN4, 2>(k4, g);
+    default: return wf_pick_k<KIN4, 4>(k4, g);
+  }
+}
+inline WfKernel wf_pick(const WfShape& s) { return s.kin4 == 4 ? wf_pick_mp<4>(s.mp, s.k4, s.g) : wf_pick_mp<8>(s.mp, s.k4, s.g); }
 
 }  // namespace
 
 bool wavefront_supported(const ModelDesc& md, const ForwardArgs& a) {
   if (a.mask != nullptr) return false;
   WfPlan pl;
-  return wf_make_plan(md, pl);
+  if (!wf_make_plan(md, pl)) return false;
+  WfShape sh;
+  return wf_shape(pl, sh) && wf_pick(sh) != nullptr;
 }
 
 int run_wavefront(const ModelDesc& md, const ModelDesc* dev_md, const ForwardArgs& a, cudaStream_t stream, int* launches) {
   WfPlan pl;
   SVD_REQUIRE(wf_make_plan(md, pl), "wavefront engine: model does not fit (units/input_dim/ranks <= 32, <= 7 layers, n_out <= 1)");
+  WfShape sh;
+  WfKernel kern = wf_shape(pl, sh) ? wf_pick(sh) : nullptr;
+  SVD_REQUIRE(kern != nullptr, "wavefront engine: factor shapes exceed the register-resident budget");
   const size_t smem = (size_t)pl.total_floats * sizeof(float);
-  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = 32 * (md.n_layers + 2);
-  lstm_wavefront_kernel<<<a.B, threads, smem, stream>>>(dev_md, a);
+  kern<<<a.B, threads, smem, stream>>>(dev_md, a);
   SVD_CUDA_TRY(cudaGetLastError());
   *launches = 1;
   return 0;

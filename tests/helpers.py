@@ -6,7 +6,21 @@ import svdlstm
 RTOL, ATOL = 1e-5, 2e-6
 
 
-def assert_parity(y, ref, what="", ref32=None):
+def cond_slack(model):
+    """Extra absolute tolerance for 2-factor models: 4e-7 * max|C| over the right factors.  z = [a | a C]
+    sums terms of magnitude |a||C| that cancel to O(1); float32 rounding of that sum is ~eps*sqrt(K)*max|C|
+    whatever the summation order (numpy/TF or ours)."""
+    mx = 0.0
+    for layer in model.layers[:-1]:
+        c = layer.cell
+        if isinstance(c, svdlstm.ReducedLSTMCell):
+            for v in c.weights:
+                if "right" in v.name and v.tensor.numel():
+                    mx = max(mx, float(v.tensor.abs().max()))
+    return 4e-7 * mx
+
+
+def assert_parity(y, ref, what="", ref32=None, extra_atol=0.0):
     """ref = float64 oracle.  For the 2-factor form C = inv(V1) V2 has entries up to ~650 on the shipped
     weights (cond(V1) up to 136), so ANY float32 evaluation -- the reference's TF float32 included -- sits
     ~1e-5 from the float64 value.  There the bar is: as close to float64 as the reference-precision
@@ -15,7 +29,7 @@ def assert_parity(y, ref, what="", ref32=None):
     ref = np.asarray(ref, np.float64)
     assert y.shape == ref.shape, (what, y.shape, ref.shape)
     err = np.abs(y - ref)
-    tol = RTOL * np.abs(ref) + ATOL
+    tol = RTOL * np.abs(ref) + ATOL + extra_atol
     if ref32 is not None:
         tol = tol + 5.0 * np.max(np.abs(np.asarray(ref32, np.float64) - ref))
     worst = np.max(err - tol)

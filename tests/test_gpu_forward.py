@@ -11,7 +11,7 @@ import svdlstm
 
 pytestmark = pytest.mark.gpu
 
-from helpers import assert_parity, oracle_twin
+from helpers import assert_parity, cond_slack, oracle_twin
 
 
 @pytest.fixture(scope="module")
@@ -46,12 +46,12 @@ def test_singular_and_reduced_parity_all_ranks(oracle, full, x_small, merged, en
         assert_parity(tm.predict(x_small, engine=engine), oracle_twin(oracle, tm).predict(x_small), "3F top-%d" % r)
         rm = svdlstm.make_LSTM_reduced_model(sm, merged_kernel=merged, rank=r)
         assert_parity(rm.predict(x_small, engine=engine), oracle_twin(oracle, rm).predict(x_small), "2F top-%d" % r,
-                      ref32=oracle_twin(oracle, rm, np.float32).predict(x_small))
+                      ref32=oracle_twin(oracle, rm, np.float32).predict(x_small), extra_atol=cond_slack(rm))
         # 2-factor and 3-factor forms of the same top-r truncation agree (they differ only in cost)
         assert np.max(np.abs(rm.predict(x_small, engine=engine) - tm.predict(x_small, engine=engine))) < 5e-5
     rm = svdlstm.make_LSTM_reduced_model(sm, cutoff=.05, merged_kernel=merged)
     assert_parity(rm.predict(x_small, engine=engine), oracle_twin(oracle, rm).predict(x_small), "2F cutoff .05",
-                  ref32=oracle_twin(oracle, rm, np.float32).predict(x_small))
+                  ref32=oracle_twin(oracle, rm, np.float32).predict(x_small), extra_atol=cond_slack(rm))
     if merged:   # cutoff .05 prunes nothing on merged matrices => reduced == full
         assert np.max(np.abs(rm.predict(x_small, engine=engine) - y_full)) < 5e-5
 
@@ -80,7 +80,9 @@ def test_auto_engine_picks_wavefront_and_long_sequence(oracle, full):
     x = np.random.default_rng(1).standard_normal((1, 6000, 16)).astype(np.float32)
     y = full.predict(x)
     assert full.last_engine() == svdlstm.ENGINE_WAVEFRONT
-    assert_parity(y, oracle_twin(oracle, full).predict(x), "T=6000 wavefront")
+    # 18 000 dependent cell updates: float32 rounding noise itself is ~5e-6 here (ref32 term)
+    assert_parity(y, oracle_twin(oracle, full).predict(x), "T=6000 wavefront",
+                  ref32=oracle_twin(oracle, full, np.float32).predict(x))
     yg = full.predict(x, engine="general")
     assert np.max(np.abs(y - yg)) < 1e-5
 
