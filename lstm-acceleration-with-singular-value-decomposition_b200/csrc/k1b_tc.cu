@@ -20,6 +20,7 @@
 // (reference code/svd_classes_v3.py:116-145, 317-328, 405-434) at BF16 precision; the FP32 engines
 // remain the parity path.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -102,6 +103,23 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (lo, hi) words: per-MMA descriptor update is ONE 32-bit add on the lo word
+__device__ __forceinline__ void umma_lh(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,6 +191,7 @@ struct TcLayerParams {
   int has_s1w;            // layers >= 1
   int in_stages;          // depth of the input prefetch ring (2 or 3)
   uint32_t a1u_bytes, a1w_bytes, a2_bytes;
+  long long* dbg;         // optional timeline buffer (CTA 0): 16 clock64 stamps per step; nullptr = off
 };
 
 struct TcSmemPlan {
@@ -198,6 +217,8 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
 enum { BAR_IN_FULL = 0, BAR_IN_EMPTY = kInStages, BAR_S1_FULL = 2 * kInStages, BAR_T_READY, BAR_S2_FULL0, BAR_S2_FULL1,
        BAR_S2_EMPTY0, BAR_S2_EMPTY1, BAR_H_READY, BAR_H_FREE, BAR_COUNT };
 static_assert(BAR_COUNT * 8 <= 128, "barrier block too small");
+
+#define TC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && t < 64) p.dbg[t * 16 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -291,58 +312,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       // weights landed?
       mbar_wait(bar(BAR_H_FREE), 0);
       uint32_t ph_in = 0, ph_t = 0, ph_hready = 0, ph_s2e = 0;
-      const uint32_t sbo_a1u = (uint32_t)H * 16u, sbo_a1w = (uint32_t)p.Kin * 16u;
       const int K2 = p.ru_pad + p.rin_pad;
-      const uint32_t sbo_a2 = (uint32_t)K2 * 16u;
-      const uint32_t a2_tile_bytes = 128u * (uint32_t)K2 * 2u;
+      // descriptor words: hi = SBO | version, lo = start address | LBO.  K advances by 16 elements per MMA:
+      // +256 B on K-major weight images (lo += 16), +1024 B on MN-major activation tiles (lo += 64).
+      const uint32_t act_hi = desc_hi(kActSBO);
+      const uint32_t a1u_hi = desc_hi((uint32_t)H * 16u), a1u_lo0 = desc_lo(sbase + sp.a1u, 128u);
+      const uint32_t a1w_hi = desc_hi((uint32_t)p.Kin * 16u), a1w_lo0 = desc_lo(sbase + sp.a1w, 128u);
+      const uint32_t a2_hi = desc_hi((uint32_t)K2 * 16u), a2_lo0 = desc_lo(sbase + sp.a2, 128u);
+      const uint32_t a2_tile_lo = (128u * (uint32_t)K2 * 2u) >> 4;
+      const uint32_t h_lo0 = desc_lo(sbase + sp.hbuf, kActLBO), t_lo0 = desc_lo(sbase + sp.tbuf, kActLBO);
+      const uint32_t in_lo0 = desc_lo(sbase + sp.inbuf, kActLBO), in_stage_lo = in_tile >> 4;
+      const int n_s1u = H / 16, n_s1w = p.has_s1w ? p.Kin / 16 : 0;
+      const int n_s2t = p.has_s1w ? K2 / 16 : p.ru_pad / 16;     // K slices of S2 read from the t buffer
+      const int n_s2x = p.has_s1w ? 0 : p.rin_pad / 16;          // K slices of S2 read from the x stage (layer 0)
       for (int t = 0; t < T; ++t) {
         const int s = t % nst;
         if (t > 0) {
           mbar_wait(bar(BAR_H_READY), ph_hready);
           ph_hready ^= 1u;
         }
+        TC_STAMP(0);   // MMA: h(t-1) ready seen
         mbar_wait(bar(BAR_IN_FULL + s), (ph_in >> s) & 1u);
         ph_in ^= 1u << s;
         tc_fence_after();
+        TC_STAMP(1);   // MMA: in(t) ready seen
+        const uint32_t in_lo = in_lo0 + (uint32_t)s * in_stage_lo;
         // ---- S1u: t_u = A1u . h(t-1)    K = H
-        for (int kk = 0; kk < H / 16; ++kk) {
-          const uint64_t ad = make_smem_desc(sbase + sp.a1u + (uint32_t)kk * 256u, 128u, sbo_a1u);
-          const uint64_t bd = make_smem_desc(sbase + sp.hbuf + (uint32_t)kk * 2u * kActLBO, kActLBO, kActSBO);
-          umma(tm_s1u, ad, bd, idesc_mn, kk > 0);
+        {
+          uint32_t alo = a1u_lo0, blo = h_lo0;
+#pragma unroll 8
+          for (int kk = 0; kk < n_s1u; ++kk) {
+            umma_lh(tm_s1u, alo, a1u_hi, blo, act_hi, idesc_mn, kk > 0);
+            alo += 16u;
+            blo += 64u;
+          }
         }
         // ---- S1w: t_w = A1w . in(t)     K = Kin
-        if (p.has_s1w) {
-          for (int kk = 0; kk < p.Kin / 16; ++kk) {
-            const uint64_t ad = make_smem_desc(sbase + sp.a1w + (uint32_t)kk * 256u, 128u, sbo_a1w);
-            const uint64_t bd = make_smem_desc(sbase + sp.inbuf + s * in_tile + (uint32_t)kk * 2u * kActLBO, kActLBO, kActSBO);
-            umma(tm_s1w, ad, bd, idesc_mn, kk > 0);
+        {
+          uint32_t alo = a1w_lo0, blo = in_lo;
+#pragma unroll 8
+          for (int kk = 0; kk < n_s1w; ++kk) {
+            umma_lh(tm_s1w, alo, a1w_hi, blo, act_hi, idesc_mn, kk > 0);
+            alo += 16u;
+            blo += 64u;
           }
         }
         umma_commit(bar(BAR_S1_FULL));
         if (p.has_s1w) umma_commit(bar(BAR_IN_EMPTY + s));   // in(t) consumed once S1w completes
+        TC_STAMP(2);   // MMA: S1 issued + committed
         // ---- S2: z = A2 . [t_u ; t_w | x(t)]
         mbar_wait(bar(BAR_T_READY), ph_t);
         ph_t ^= 1u;
         tc_fence_after();
+        TC_STAMP(3);   // MMA: t operand ready seen
+        uint32_t tile_lo = a2_lo0;
         for (int ub = 0; ub < nub; ++ub) {
           const int buf = ub & 1;
           // wait until the epilogue drained this TMEM buffer (first use of each buffer passes: parity trick)
           mbar_wait(bar(BAR_S2_EMPTY0 + buf), ((ph_s2e >> buf) & 1u) ^ 1u);
           ph_s2e ^= 1u << buf;
           tc_fence_after();
+#pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint32_t a_tile = sbase + sp.a2 + (uint32_t)(ub * 4 + g) * a2_tile_bytes;
             const uint32_t d = tm_s2 + (uint32_t)buf * 128u + (uint32_t)g * 32u;
-            for (int kk = 0; kk < K2 / 16; ++kk) {
-              const uint64_t ad = make_smem_desc(a_tile + (uint32_t)kk * 256u, 128u, sbo_a2);
-              uint32_t baddr;
-              if (p.has_s1w || kk * 16 < p.ru_pad) baddr = sbase + sp.tbuf + (uint32_t)kk * 2u * kActLBO;
-              else baddr = sbase + sp.inbuf + s * in_tile + (uint32_t)(kk * 16 - p.ru_pad) / 8u * kActLBO;
-              const uint64_t bd = make_smem_desc(baddr, kActLBO, kActSBO);
-              umma(d, ad, bd, idesc_mn, kk > 0);
+            uint32_t alo = tile_lo, blo = t_lo0;
+#pragma unroll 4
+            for (int kk = 0; kk < n_s2t; ++kk) {
+              umma_lh(d, alo, a2_hi, blo, act_hi, idesc_mn, kk > 0);
+              alo += 16u;
+              blo += 64u;
             }
+            blo = in_lo;
+            for (int kk = 0; kk < n_s2x; ++kk) {
+              umma_lh(d, alo, a2_hi, blo, act_hi, idesc_mn, 1u);
+              alo += 16u;
+              blo += 64u;
+            }
+            tile_lo += a2_tile_lo;
           }
           umma_commit(bar(BAR_S2_FULL0 + buf));
+          TC_STAMP(4 + ub);   // MMA: S2 block ub issued + committed
         }
         if (!p.has_s1w) umma_commit(bar(BAR_IN_EMPTY + s));   // layer 0: x(t) is consumed by S2
       }
@@ -368,6 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       mbar_wait(bar(BAR_S1_FULL), ph_s1);
       ph_s1 ^= 1u;
       tc_fence_after();
+      if (threadIdx.x == 64) TC_STAMP(8);   // EPI: S1 accumulators seen
       {
         const bool do_u = (q * 32) < p.ru_pad;       // warp-uniform: any valid row in this quarter?
         const bool do_w = p.has_s1w && (q * 32) < p.rin_pad;
@@ -420,6 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar(BAR_T_READY));
+      if (threadIdx.x == 64) TC_STAMP(9);   // EPI: t operand written + arrived
 
       // ---- epilogue 2: gates + cell update per unit block ------------------------------------------
       // h(t-1) tile must have been copied out before it is overwritten
@@ -434,6 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           mbar_wait(bar(BAR_S2_FULL0 + buf), (ph_s2f >> buf) & 1u);
           ph_s2f ^= 1u << buf;
           tc_fence_after();
+          if (threadIdx.x == 64) TC_STAMP(10 + 2 * ub);   // EPI: z block ub seen
           const uint32_t tb = tm_s2 + (uint32_t)buf * 128u + lane_addr;
           const int unit = ub * 128 + row;
 #pragma unroll
@@ -466,10 +518,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           }
           tc_fence_before();
           mbar_arrive(bar(BAR_S2_EMPTY0 + buf));
+          if (threadIdx.x == 64) TC_STAMP(11 + 2 * ub);   // EPI: block ub done
         }
       }
       fence_proxy_async();
       mbar_arrive(bar(BAR_H_READY));
+      if (threadIdx.x == 64) TC_STAMP(14);      // EPI: h(t) published
     }
   }
 
@@ -654,6 +708,7 @@ static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const 
   p.a2_bytes = (uint32_t)4 * H * (p.ru_pad + p.rin_pad) * 2;
   p.a1u = p.a1w = p.a2 = nullptr;
   p.bias = nullptr;
+  p.dbg = nullptr;
   p.in_seq = nullptr;
   p.out_seq = nullptr;
   p.T = 0;
@@ -740,9 +795,13 @@ int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const 
   }
   pack_x_kernel<<<dim3(64, n_cta), 256, 0, stream>>>(a.x, B, T, md.input_dim, Dpad, st->xseq);
   ++nl;
+  static long long* dbg_buf = nullptr;
+  const char* dbg_env = getenv("SVDLSTM_TC_TIMELINE");
+  if (dbg_env && !dbg_buf) SVD_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * 64 * 16 * kMaxLayers));
   for (int l = 0; l < L; ++l) {
     TcLayerParams p = st->layers[l].prm;
     p.T = T;
+    p.dbg = dbg_env ? dbg_buf + (size_t)l * 64 * 16 : nullptr;
     p.in_seq = (l == 0) ? st->xseq : st->seq[(l - 1) & 1];
     p.out_seq = st->seq[l & 1];
     const TcSmemPlan sp = tc_plan(p);
@@ -754,6 +813,18 @@ int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const 
                                                           md.dense_bias, md.n_out, a.y);
   ++nl;
   SVD_CUDA_TRY(cudaGetLastError());
+  if (dbg_env) {   // debugging aid: dump the per-step timeline of CTA 0 (cycles relative to the step's first stamp)
+    static long long host[64 * 16 * kMaxLayers];
+    SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+    SVD_CUDA_TRY(cudaMemcpy(host, dbg_buf, sizeof(long long) * 64 * 16 * L, cudaMemcpyDeviceToHost));
+    for (int l = 0; l < L; ++l)
+      for (int t = 20; t < 24 && t < T; ++t) {
+        const long long* r = host + ((size_t)l * 64 + t) * 16;
+        fprintf(stderr, "[tc timeline] layer %d step %d:", l, t);
+        for (int i = 0; i < 15; ++i) fprintf(stderr, " %lld", r[i] ? r[i] - r[0] : -1);
+        fprintf(stderr, "  | step period %lld\n", r[0] - (r - 16)[0]);
+      }
+  }
   *launches = nl;
   return 0;
 }
