@@ -1,26 +1,36 @@
-// K1b: tcgen05 BF16 tensor-core persistent recurrent kernel (reduced-precision engine).
+// K1b: tcgen05 tensor-core persistent recurrent kernel (reduced-precision engine, FP16 operands, FP32
+// accumulation and cell state).
 //
-// One CTA owns a tile of N=32 sequences for all T steps of ONE layer; layers run back to back,
-// handing the bf16 hidden sequence over through HBM in the exact shared-memory operand image the
-// next layer's MMAs consume (one 1-D bulk copy per step).  Per step the low-rank cell is two
-// dependent thin contractions on the 5th-gen tensor cores, SWAP-AB so that the weight dimension fills
-// the 128-row MMA and the batch tile is the (small) N:
-//   S1u: t_u[r_u x N]  = (L_u sigma_u)^T [r_u x H]   . h(t-1) [H x N]
-//   S1w: t_w[r_w x N]  = (L_w sigma_w)^T [r_w x Hin] . in(t)  [Hin x N]      (layers >= 1)
-//   S2 : z [4H x N]    = [R_u ; R_w]^T   [4H x K2]   . [t_u ; t_w | x(t)]    (layer 0: x enters S2 directly
-//                                                                             through the dense 16x4H W)
-// Accumulators live in TMEM (S1: 2 x 32 columns; S2: two buffers of 4 gates x 32 columns, so the
-// gate/cell epilogue of unit block ub overlaps the MMAs of block ub+1).  Weight factors are packed
-// once (bf16, K-major core-matrix images) and stay resident in shared memory for the whole launch.
-// Warp roles: warp 0 = bulk-copy producer (input prefetch ring + output stores), warp 1 = MMA issuer
-// (one elected thread), warps 2-5 = epilogue (TMEM -> registers -> activations -> bf16 operand in smem).
-// Cell state c stays in FP32 registers for all T steps.
+// One CTA owns a tile of N=32 sequences for all T steps of ONE layer; layers run back to back and hand
+// the hidden sequence over through HBM in the exact shared-memory operand image the next layer's MMAs
+// consume (one 1-D bulk copy per step).  Per step the low-rank cell is two dependent thin contractions
+// on the 5th-gen tensor cores, SWAP-AB so that the weight dimension fills the 128-row MMA and the batch
+// tile is the (small) N:
+//   S1u: t_u[r_u x N]  = (L_u sigma_u)^T [r_u x H]   . h(t-1) [H x N]      (+ Dense-top rows: y(t-1))
+//   S1w: t_w[r_w x N]  = (L_w sigma_w)^T [r_w x Hin] . in(t)  [Hin x N]    (layers >= 1; issued one
+//                                                                           step early: no recurrence)
+//   S2 : z [4H x N]    = [R_u ; R_w]^T   [4H x K2]   . [t_u ; t_w | x(t)]  (layer 0: x enters S2 directly
+//                                                                           through the dense 16x4H W)
+// Accumulators live in TMEM (S1: <= 5 x 32 columns; S2: two buffers of 4 gates x 32 columns, so the
+// gate/cell epilogue of one 128-unit block overlaps the MMAs of the next).  The weight factors are one
+// "weight stream": a fixed sequence of K-major 128-row chunks (<= 16 KB, <= 4 MMAs each) consumed in
+// the same order every step.  If the stream fits shared memory it is loaded once and stays RESIDENT;
+// otherwise it is re-streamed from L2 every step through a ring of 16 KB slots (full/empty mbarriers),
+// which is what lets ranks up to 256 (1.3 MB of factors per layer) run on the tensor cores at all.
+// Warp roles: warp 0 = weight streamer, warp 1 = MMA issuer (whole warp converged, one elected lane
+// issues: the divergent single-thread form costs 2-3x more cycles per tcgen05.mma, see
+// scripts/ubench_umma.cu), warp 2 = input ring + hidden-sequence stores (bulk copies), warps 4-11 =
+// epilogue (TMEM -> registers -> activations -> FP16 operand in smem; two warps per TMEM lane quarter,
+// 16 columns each).  Cell state c stays in FP32 registers for all T steps.  The Dense(1) top of the last
+// layer rides in spare rows of the S1u tile (its output for step t-1 falls out of step t's first MMA chain).
 //
 // Replaces SingularLSTMCell.call / ReducedLSTMCell.call + backend.rnn for large batches
-// (reference code/svd_classes_v3.py:116-145, 317-328, 405-434) at BF16 precision; the FP32 engines
+// (reference code/svd_classes_v3.py:116-145, 317-328, 405-434) at reduced precision; the FP32 engines
 // remain the parity path.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,9 +38,16 @@ namespace svdlstm {
 
 namespace {
 
-constexpr int kN = 32;            // sequences per CTA (MMA N)
-constexpr int kInStages = 3;      // max input prefetch ring depth
-constexpr int kTcThreads = 192;   // 6 warps
+constexpr int kN = 32;               // sequences per CTA (MMA N)
+constexpr int kInStagesMax = 3;      // max input prefetch ring depth
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kTcThreads = 32 * (4 + kEpiWarps);
+constexpr int kMaxWSlots = 12;
+constexpr uint32_t kSlotBytes = 16384;
+constexpr int kMaxUB = 4;            // unit blocks of 128 (H <= 512)
+constexpr uint32_t kSmemCap = 227u * 1024u;
+constexpr int kDbgPerLayer = 64 * 16 + 256;   // timeline: 16 stamps x 64 steps + per-chunk issue stamps of step 20
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -59,14 +76,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch (CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must surface as a trapped launch (CUDA error), never as a hung GPU.  The spin
+// loop lives out of line: the kernel has ~40 wait sites and its hot code must stay inside the instruction cache.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -92,37 +112,79 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] . B[smem desc]   (kind::f16: bf16 x bf16 -> fp32)
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ".reg .pred q;\n\t"
+      ".reg .b32 rx;\n\t"
+      "elect.sync rx|q, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
 }
-// same, descriptors given as (lo, hi) words: per-MMA descriptor update is ONE 32-bit add on the lo word
-__device__ __forceinline__ void umma_lh(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
-                                        uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] . B[smem desc]   (kind::f16: f16 x f16 -> fp32).  Executed by the whole (converged)
+// warp; only the elected lane issues.  Descriptors are given as (lo, hi) words: stepping K is one add on lo.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t elected) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+// NM (1..4) back-to-back MMAs of one weight chunk in ONE asm block: the K step of both descriptors is an
+// immediate add on the lo word (A +256 B, B +1024 B per K=16) and the predicates are set up once per chunk.
+#define SVD_UMMA_HEAD                                                   \
+  "{\n\t"                                                               \
+  ".reg .pred p, q, one;\n\t"                                           \
+  ".reg .b64 da, db;\n\t"                                               \
+  ".reg .b32 ta, tb;\n\t"                                               \
+  "setp.ne.b32 q, %7, 0;\n\t"                                           \
+  "setp.ne.b32 p, %6, 0;\n\t"                                           \
+  "setp.eq.b32 one, 0, 0;\n\t"                                          \
+  "mov.b64 da, {%1, %2};\n\t"                                           \
+  "mov.b64 db, {%3, %4};\n\t"                                           \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+#define SVD_UMMA_NEXT(aoff, boff)                                       \
+  "add.u32 ta, %1, " #aoff ";\n\t"                                      \
+  "add.u32 tb, %3, " #boff ";\n\t"                                      \
+  "mov.b64 da, {ta, %2};\n\t"                                           \
+  "mov.b64 db, {tb, %4};\n\t"                                           \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, one;\n\t"
+#define SVD_UMMA_OPERANDS                                                                                              \
+  ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(first_accumulates), "r"(elected) : "memory"
+template <int NM>
+__device__ __forceinline__ void umma_f16_x(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t first_accumulates, uint32_t elected) {
+  static_assert(NM >= 1 && NM <= 4, "1..4 MMAs per chunk");
+  if constexpr (NM == 1) asm volatile(SVD_UMMA_HEAD "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4)
+    asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) SVD_UMMA_NEXT(48, 192) "}\n" SVD_UMMA_OPERANDS);
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar),
+      "r"(elected)
       : "memory");
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }   // bit 46: sm_100 descriptor
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -138,88 +200,152 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
 // ------------------------------------------------------------------------------------------------
-// descriptors (cute/arch/mma_sm100_desc.hpp bit layout; SWIZZLE_NONE canonical layouts)
-//   K-major : elem(mn,k) at (mn%8)*16 + (mn/8)*SBO + (k%8)*2 + (k/8)*LBO
-//   MN-major: elem(mn,k) at (mn%8)*2  + (mn/8)*SBO + (k%8)*16 + (k/8)*LBO
+// operand images (SWIZZLE_NONE canonical layouts, cute/arch/mma_sm100_desc.hpp bit layout)
+//   K-major  A chunk [rows x kc]: elem(row,k) at (row/8)*(kc*16) + (k/8)*128 + (row%8)*16 + (k%8)*2     LBO=128, SBO=kc*16
+//   MN-major B tile  [K x N=32] : elem(k,n)   at (k/8)*512 + (n/8)*128 + (k%8)*16 + (n%8)*2             LBO=512, SBO=128
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
-  return d;                 // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
-}
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4)                      // c_format  F32
-         | (1u << 7)                    // a_format  BF16
-         | (1u << 10)                   // b_format  BF16
-         | ((uint32_t)a_mn_major << 15) // a_major
-         | ((uint32_t)b_mn_major << 16) // b_major
+         | (0u << 7)                    // a_format  F16
+         | (0u << 10)                   // b_format  F16
+         | (0u << 15)                   // A K-major
+         | (1u << 16)                   // B MN-major
          | ((uint32_t)(N >> 3) << 17)   // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
-
-// MN-major activation tile image [K x N=32]: k-groups of 8 are 512 B apart, n-groups of 8 128 B apart.
 constexpr uint32_t kActLBO = 512, kActSBO = 128;
 __host__ __device__ inline uint32_t act_tile_bytes(int K) { return (uint32_t)(K / 8) * 512u; }
 __host__ __device__ inline uint32_t act_offset(int k, int n) {
   return (uint32_t)(k / 8) * 512u + (uint32_t)(n / 8) * 128u + (uint32_t)(k % 8) * 16u + (uint32_t)(n % 8) * 2u;
 }
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
 // ------------------------------------------------------------------------------------------------
 // per-layer launch parameters
 // ------------------------------------------------------------------------------------------------
 struct TcLayerParams {
-  const uint8_t* a1u;     // (L_u sigma_u)^T  K-major image, rows r_u_pad8, K = H
-  const uint8_t* a1w;     // (L_w sigma_w)^T  K-major image, rows r_w_pad8, K = Hin   (nullptr for layer 0)
-  const uint8_t* a2;      // [R_u ; R_w|W0]^T K-major image, 4H rows in (unit-block, gate) tiles of 128, K = K2
-  const float* bias;      // [4H] in tile order
-  const uint8_t* in_seq;  // activation tile images [cta][t], K = Kin
-  uint8_t* out_seq;       // activation tile images [cta][t], K = H
-  int H, Kin, T;
-  int ru, rw;             // true ranks
-  int ru_pad, rin_pad;    // multiples of 16: K extents of the two parts of the S2 contraction
-  int has_s1w;            // layers >= 1
-  int in_stages;          // depth of the input prefetch ring (2 or 3)
-  uint32_t a1u_bytes, a1w_bytes, a2_bytes;
-  long long* dbg;         // optional timeline buffer (CTA 0): 16 clock64 stamps per step; nullptr = off
+  const uint8_t* wimg;      // weight stream image: [segment W][segment U][segment 2]
+  const float* bias;        // [nub][4][128]; gates i,f,o pre-scaled by 0.5 (sigmoid(x) = 0.5 tanh(x/2) + 0.5)
+  const uint8_t* in_seq;    // activation tile images [cta][t], K = Kin
+  uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
+  float* y;                 // (B, T, n_dense) fused Dense-top output            (n_dense > 0)
+  const float* dense_bias;
+  int H, Kin, T, B;
+  int ru, rw;               // true ranks
+  int ru_pad, rw_pad;       // multiples of 16: K extents of t_u / t_w inside the S2 contraction (rw_pad = 0 on layer 0)
+  int kx;                   // layer 0: K extent of the x part of S2 (= Kin); else 0
+  int rows_u, rows_w;       // rows of the S1 A operands, multiples of 8 (rows_u includes the Dense-top rows)
+  int n_dense;              // Dense-top outputs fused into S1u (0 = none)
+  int has_s1w;              // layers >= 1
+  int store_h;              // hand h(t) tiles to the next layer through HBM
+  int in_stages;            // depth of the input prefetch ring
+  int streaming, w_slots;   // weight stream: 0 = resident; 1 = ring of w_slots 16 KB slots
+  uint32_t segw_bytes, segu_bytes, seg2_bytes;
+  long long* dbg;           // optional timeline buffer (CTA 0): 16 clock64 stamps per step; nullptr = off
 };
 
 struct TcSmemPlan {
-  uint32_t a1u, a1w, a2, hbuf, tbuf, inbuf, bars, tmem_slot, total;
+  uint32_t w, hbuf, tbuf, inbuf, bars, tmem_slot, total;
 };
 
 __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   TcSmemPlan s;
   uint32_t off = 0;
-  s.a1u = off; off += (p.a1u_bytes + 127u) & ~127u;
-  s.a1w = off; off += (p.a1w_bytes + 127u) & ~127u;
-  s.a2 = off;  off += (p.a2_bytes + 127u) & ~127u;
+  s.w = off;
+  off += p.streaming ? (uint32_t)p.w_slots * kSlotBytes : ((p.segw_bytes + p.segu_bytes + p.seg2_bytes + 1023u) & ~1023u);
   s.hbuf = off; off += act_tile_bytes(p.H);
-  s.tbuf = off; off += act_tile_bytes(p.ru_pad + (p.has_s1w ? p.rin_pad : 0));
+  s.tbuf = off; off += act_tile_bytes(p.ru_pad + p.rw_pad);
   s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin);
-  s.bars = off; off += 128;
+  s.bars = off; off += 512;
   s.tmem_slot = off; off += 16;
-  s.total = off + 2048;   // tail guard: 128-row MMA tiles over-read past short (r < 128 row) images
+  s.total = off;
   return s;
 }
 
 // barrier slots (8 B each) inside the `bars` block
-enum { BAR_IN_FULL = 0, BAR_IN_EMPTY = kInStages, BAR_S1_FULL = 2 * kInStages, BAR_T_READY, BAR_S2_FULL0, BAR_S2_FULL1,
-       BAR_S2_EMPTY0, BAR_S2_EMPTY1, BAR_H_READY, BAR_H_FREE, BAR_COUNT };
-static_assert(BAR_COUNT * 8 <= 128, "barrier block too small");
+enum {
+  BAR_W_FULL = 0,
+  BAR_W_EMPTY = kMaxWSlots,
+  BAR_IN_FULL = 2 * kMaxWSlots,
+  BAR_IN_EMPTY = BAR_IN_FULL + kInStagesMax,
+  BAR_S1_FULL = BAR_IN_EMPTY + kInStagesMax,
+  BAR_T_READY,
+  BAR_S2_FULL0,
+  BAR_S2_FULL1,
+  BAR_S2_EMPTY0,
+  BAR_S2_EMPTY1,
+  BAR_H_READY,                        // kMaxUB of them
+  BAR_H_DONE = BAR_H_READY + kMaxUB,
+  BAR_H_STORED,
+  BAR_COUNT
+};
+static_assert(BAR_COUNT * 8 <= 512, "barrier block too small");
 
+// ------------------------------------------------------------------------------------------------
+// the weight stream: ONE definition of the chunk order, shared by the packer (host), the streamer
+// warp and the MMA warp.  f(bytes, ...) is called once per chunk in consumption order.
+// ------------------------------------------------------------------------------------------------
+// segment W: A1w, rows_w x Kin, for mt, for 64-wide K chunk
+template <class P, class F>
+__host__ __device__ inline void for_seg_w(const P& p, F&& f) {
+#pragma unroll 1
+  for (int r0 = 0; r0 < p.rows_w; r0 += 128) {
+    const int rows = imin(128, p.rows_w - r0);
+#pragma unroll 1
+    for (int k0 = 0; k0 < p.Kin; k0 += 64) f((uint32_t)rows * 128u, r0, rows, k0);
+  }
+}
+// segment U: A1u, rows_u x H, for 128-unit K block (so the MMAs of block kb can start as soon as the epilogue
+// published that block of h), for mt, for the two 64-wide K chunks of the block
+template <class P, class F>
+__host__ __device__ inline void for_seg_u(const P& p, F&& f) {
+#pragma unroll 1
+  for (int kb = 0; kb < p.H / 128; ++kb)
+#pragma unroll 1
+    for (int r0 = 0; r0 < p.rows_u; r0 += 128) {
+      const int rows = imin(128, p.rows_u - r0);
+#pragma unroll 1
+      for (int c2 = 0; c2 < 2; ++c2) f((uint32_t)rows * 128u, kb, r0, rows, kb * 128 + c2 * 64);
+    }
+}
+// segment 2: A2, for unit block ub, for gate g: the t part (K = ru_pad + rw_pad, from the t buffer) in chunks of <= 64,
+// then the x part (layer 0, K = kx, from the input ring) in chunks of <= 64
+template <class P, class F>
+__host__ __device__ inline void for_seg_2(const P& p, F&& f) {
+  const int kt = p.ru_pad + p.rw_pad;
+#pragma unroll 1
+  for (int ub = 0; ub < p.H / 128; ++ub)
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+      for (int k0 = 0; k0 < kt; k0 += 64) {
+        const int kc = imin(64, kt - k0);
+        f((uint32_t)kc * 256u, ub, g, 0, k0, kc);
+      }
+#pragma unroll 1
+      for (int k0 = 0; k0 < p.kx; k0 += 64) {
+        const int kc = imin(64, p.kx - k0);
+        f((uint32_t)kc * 256u, ub, g, 1, k0, kc);
+      }
+    }
+}
+
+#ifdef SVDLSTM_TC_TIMELINE
 #define TC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && t < 64) p.dbg[t * 16 + (slot)] = clock64(); } while (0)
+#define TC_CHUNK_STAMP() do { if (p.dbg != nullptr && blockIdx.x == 0 && dbg_t == 20 && dbg_n < 250) p.dbg[64 * 16 + dbg_n++] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#define TC_CHUNK_STAMP() do { } while (0)
+#endif
 
+template <int NUB>
 __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcSmemPlan sp = tc_plan(p);
@@ -227,31 +353,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int H = p.H, T = p.T;
-  const int nub = H / 128;
+  constexpr int nub = NUB;
   const int nst = p.in_stages;
+  const int ns = p.w_slots;
   const uint32_t in_tile = act_tile_bytes(p.Kin), h_tile = act_tile_bytes(H);
   const uint32_t bar0 = sbase + sp.bars;
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int n_steps = T + (p.n_dense > 0 ? 1 : 0);   // the Dense-top output of step T-1 needs one more S1u pass
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  // zero the activation buffers (h(-1) = 0, padded t rows must be finite)
-  for (uint32_t i = threadIdx.x * 16u; i < sp.inbuf - sp.hbuf; i += kTcThreads * 16u)
+  // zero the activation buffers (h(-1) = 0; padded rows must be finite)
+  for (uint32_t i = threadIdx.x * 16u; i < sp.bars - sp.hbuf; i += kTcThreads * 16u)
     *reinterpret_cast<uint4*>(smem + sp.hbuf + i) = make_uint4(0, 0, 0, 0);
-  for (uint32_t i = threadIdx.x * 16u; i < 2048u; i += kTcThreads * 16u)
-    *reinterpret_cast<uint4*>(smem + sp.total - 2048u + i) = make_uint4(0, 0, 0, 0);
+  if (p.streaming)   // stale bytes behind short chunks feed unused accumulator rows only, but keep them finite
+    for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)ns * kSlotBytes; i += kTcThreads * 16u)
+      *reinterpret_cast<uint4*>(smem + sp.w + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kInStages; ++s) {
+    for (int s = 0; s < kMaxWSlots; ++s) {
+      mbar_init(bar(BAR_W_FULL + s), 1);
+      mbar_init(bar(BAR_W_EMPTY + s), 1);
+    }
+    for (int s = 0; s < kInStagesMax; ++s) {
       mbar_init(bar(BAR_IN_FULL + s), 1);
       mbar_init(bar(BAR_IN_EMPTY + s), 1);
     }
     mbar_init(bar(BAR_S1_FULL), 1);
-    mbar_init(bar(BAR_T_READY), 128);
+    mbar_init(bar(BAR_T_READY), kEpiThreads);
     mbar_init(bar(BAR_S2_FULL0), 1);
     mbar_init(bar(BAR_S2_FULL1), 1);
-    mbar_init(bar(BAR_S2_EMPTY0), 128);
-    mbar_init(bar(BAR_S2_EMPTY1), 128);
-    mbar_init(bar(BAR_H_READY), 128);
-    mbar_init(bar(BAR_H_FREE), 1);
+    mbar_init(bar(BAR_S2_EMPTY0), kEpiThreads);
+    mbar_init(bar(BAR_S2_EMPTY1), kEpiThreads);
+    for (int u = 0; u < kMaxUB; ++u) mbar_init(bar(BAR_H_READY + u), kEpiThreads);
+    mbar_init(bar(BAR_H_DONE), kEpiThreads);
+    mbar_init(bar(BAR_H_STORED), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(sbase + sp.tmem_slot, 512);
@@ -260,270 +394,369 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + sp.tmem_slot);
-  // TMEM columns: [0,32) S1u, [32,64) S1w, [64,192) S2 buffer 0 (4 gates x 32), [192,320) S2 buffer 1
-  const uint32_t tm_s1u = tmem, tm_s1w = tmem + 32, tm_s2 = tmem + 64;
+  // TMEM columns: [0,96) S1u (<= 3 row tiles), [96,160) S1w (<= 2 row tiles), [192,320) S2 buffer 0 (4 gates x 32), [320,448) buffer 1
+  const uint32_t tm_s1u = tmem, tm_s1w = tmem + 96, tm_s2 = tmem + 192;
 
   if (warp == 0) {
-    // ======================= producer: weights once, then the input ring + output stores ==========
+    // ======================= weight streamer ====================================================
     if (lane == 0) {
-      // weights: one transaction barrier (reuse IN_FULL[0] phase 0 would complicate parities; use S2_FULL1's
-      // sibling-free slot instead: H_FREE is idle until the first h store) -> dedicated wait below
-      const uint32_t wbytes = p.a1u_bytes + p.a1w_bytes + p.a2_bytes;
-      mbar_expect_tx(bar(BAR_H_FREE), wbytes);
-      // bulk copies are limited in size per instruction; chunk at 64 KB
-      auto copy_big = [&](uint32_t dst, const uint8_t* src, uint32_t bytes) {
-        for (uint32_t o = 0; o < bytes; o += 65536u) {
-          const uint32_t n = bytes - o < 65536u ? bytes - o : 65536u;
-          bulk_g2s(sbase + dst + o, src + o, n, bar(BAR_H_FREE));
+      const uint32_t wbytes = p.segw_bytes + p.segu_bytes + p.seg2_bytes;
+      if (!p.streaming) {
+        mbar_expect_tx(bar(BAR_W_FULL), wbytes);
+        for (uint32_t o = 0; o < wbytes; o += 65536u) {
+          const uint32_t n = wbytes - o < 65536u ? wbytes - o : 65536u;
+          bulk_g2s(sbase + sp.w + o, p.wimg + o, n, bar(BAR_W_FULL));
         }
-      };
-      copy_big(sp.a1u, p.a1u, p.a1u_bytes);
-      if (p.has_s1w) copy_big(sp.a1w, p.a1w, p.a1w_bytes);
-      copy_big(sp.a2, p.a2, p.a2_bytes);
-      // input ring + output stores
+      } else {
+        int slot = 0;
+        uint32_t use = 0;   // how many times the ring wrapped
+        const uint8_t* src = nullptr;
+        auto push = [&](uint32_t bytes) {
+          if (use > 0) mbar_wait(bar(BAR_W_EMPTY + slot), (use - 1u) & 1u);
+          mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+          bulk_g2s(sbase + sp.w + (uint32_t)slot * kSlotBytes, src, bytes, bar(BAR_W_FULL + slot));
+          src += bytes;
+          if (++slot == ns) { slot = 0; ++use; }
+        };
+        auto seg_w = [&]() { src = p.wimg; for_seg_w(p, [&](uint32_t b, int, int, int) { push(b); }); };
+        auto seg_u = [&]() { src = p.wimg + p.segw_bytes; for_seg_u(p, [&](uint32_t b, int, int, int, int) { push(b); }); };
+        auto seg_2 = [&]() { src = p.wimg + p.segw_bytes + p.segu_bytes; for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { push(b); }); };
+        if (p.has_s1w) seg_w();
+        for (int t = 0; t < n_steps; ++t) {
+          seg_u();
+          if (t == T) break;
+          seg_2();
+          if (p.has_s1w && t + 1 < T) seg_w();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ======================= input ring + hidden-sequence stores ====================================
+    if (lane == 0) {
       const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
-      uint8_t* out = p.out_seq + (size_t)cta * T * h_tile;
-      uint32_t ph_empty = 0;   // per-stage parity bits
+      uint8_t* out = p.store_h ? p.out_seq + (size_t)cta * T * h_tile : nullptr;
       auto load_step = [&](int tl) {
         const int s = tl % nst;
-        if (tl >= nst) {
-          mbar_wait(bar(BAR_IN_EMPTY + s), (ph_empty >> s) & 1u);
-          ph_empty ^= 1u << s;
-        }
+        const uint32_t n = (uint32_t)(tl / nst);
+        if (n > 0) mbar_wait(bar(BAR_IN_EMPTY + s), (n - 1u) & 1u);
         mbar_expect_tx(bar(BAR_IN_FULL + s), in_tile);
         bulk_g2s(sbase + sp.inbuf + s * in_tile, src + (size_t)tl * in_tile, in_tile, bar(BAR_IN_FULL + s));
       };
       for (int tl = 0; tl < nst - 1 && tl < T; ++tl) load_step(tl);
       for (int t = 0; t < T; ++t) {
         if (t + nst - 1 < T) load_step(t + nst - 1);
-        // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
-        mbar_wait(bar(BAR_H_READY), (uint32_t)(t & 1));
-        bulk_s2g(out + (size_t)t * h_tile, sbase + sp.hbuf, h_tile);
-        bulk_commit();
-        bulk_wait_read0();
-        mbar_arrive(bar(BAR_H_FREE));
+        if (p.store_h) {
+          // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
+          mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
+          bulk_s2g(out + (size_t)t * h_tile, sbase + sp.hbuf, h_tile);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(bar(BAR_H_STORED));
+        }
       }
-      bulk_wait_all0();
+      if (p.store_h) bulk_wait_all0();
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer ==========================================================
-    if (lane == 0) {
-      const uint32_t idesc_mn = make_idesc(128, kN, 0, 1);   // A K-major (weights), B MN-major (activations)
-      // weights landed?
-      mbar_wait(bar(BAR_H_FREE), 0);
-      uint32_t ph_in = 0, ph_t = 0, ph_hready = 0, ph_s2e = 0;
-      const int K2 = p.ru_pad + p.rin_pad;
-      // descriptor words: hi = SBO | version, lo = start address | LBO.  K advances by 16 elements per MMA:
-      // +256 B on K-major weight images (lo += 16), +1024 B on MN-major activation tiles (lo += 64).
-      const uint32_t act_hi = desc_hi(kActSBO);
-      const uint32_t a1u_hi = desc_hi((uint32_t)H * 16u), a1u_lo0 = desc_lo(sbase + sp.a1u, 128u);
-      const uint32_t a1w_hi = desc_hi((uint32_t)p.Kin * 16u), a1w_lo0 = desc_lo(sbase + sp.a1w, 128u);
-      const uint32_t a2_hi = desc_hi((uint32_t)K2 * 16u), a2_lo0 = desc_lo(sbase + sp.a2, 128u);
-      const uint32_t a2_tile_lo = (128u * (uint32_t)K2 * 2u) >> 4;
-      const uint32_t h_lo0 = desc_lo(sbase + sp.hbuf, kActLBO), t_lo0 = desc_lo(sbase + sp.tbuf, kActLBO);
-      const uint32_t in_lo0 = desc_lo(sbase + sp.inbuf, kActLBO), in_stage_lo = in_tile >> 4;
-      const int n_s1u = H / 16, n_s1w = p.has_s1w ? p.Kin / 16 : 0;
-      const int n_s2t = p.has_s1w ? K2 / 16 : p.ru_pad / 16;     // K slices of S2 read from the t buffer
-      const int n_s2x = p.has_s1w ? 0 : p.rin_pad / 16;          // K slices of S2 read from the x stage (layer 0)
-      for (int t = 0; t < T; ++t) {
-        const int s = t % nst;
-        if (t > 0) {
-          mbar_wait(bar(BAR_H_READY), ph_hready);
-          ph_hready ^= 1u;
-        }
-        TC_STAMP(0);   // MMA: h(t-1) ready seen
-        mbar_wait(bar(BAR_IN_FULL + s), (ph_in >> s) & 1u);
-        ph_in ^= 1u << s;
+    // ======================= MMA issuer (whole warp, converged; one elected lane issues) =============
+    // This warp runs alone on its scheduler slot, so every instruction's latency is exposed: the issue
+    // loops below are written to cost a handful of uniform-datapath instructions per tcgen05.mma
+    // (descriptor words advanced by immediates inside one asm block per chunk, no per-MMA branches).
+    const uint32_t elected = elect_one();
+    const uint32_t idesc = make_idesc(128, kN);
+    const uint32_t act_hi = desc_hi(kActSBO);
+    const uint32_t h_lo0 = desc_lo(sbase + sp.hbuf, kActLBO), t_lo0 = desc_lo(sbase + sp.tbuf, kActLBO);
+    const uint32_t in_lo0 = desc_lo(sbase + sp.inbuf, kActLBO), in_stage_lo = in_tile >> 4;
+    const uint32_t w_lo0 = desc_lo(sbase + sp.w, 128u);
+    const uint32_t streaming = (uint32_t)p.streaming;
+    const uint32_t a_hi64 = desc_hi(1024u);   // kc = 64 chunks
+    int w_slot = 0;
+    uint32_t w_use = 0;
+    int dbg_n = 0, dbg_t = -1;
+    (void)dbg_n;
+    (void)dbg_t;
+    uint32_t a_lo = w_lo0;   // descriptor word of the next chunk (resident: walks the image; streaming: walks the ring)
+    if (!streaming) mbar_wait(bar(BAR_W_FULL), 0);
+    // one weight chunk = NM <= 4 MMAs (K = 16 each): A = chunk (K-major, SBO = 256*NM), B = activation rows
+    auto chunk = [&](int nm, uint32_t bytes, uint32_t a_hi, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
+      TC_CHUNK_STAMP();
+      if (streaming) {
+        mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
         tc_fence_after();
-        TC_STAMP(1);   // MMA: in(t) ready seen
-        const uint32_t in_lo = in_lo0 + (uint32_t)s * in_stage_lo;
-        // ---- S1u: t_u = A1u . h(t-1)    K = H
-        {
-          uint32_t alo = a1u_lo0, blo = h_lo0;
-#pragma unroll 8
-          for (int kk = 0; kk < n_s1u; ++kk) {
-            umma_lh(tm_s1u, alo, a1u_hi, blo, act_hi, idesc_mn, kk > 0);
-            alo += 16u;
-            blo += 64u;
-          }
-        }
-        // ---- S1w: t_w = A1w . in(t)     K = Kin
-        {
-          uint32_t alo = a1w_lo0, blo = in_lo;
-#pragma unroll 8
-          for (int kk = 0; kk < n_s1w; ++kk) {
-            umma_lh(tm_s1w, alo, a1w_hi, blo, act_hi, idesc_mn, kk > 0);
-            alo += 16u;
-            blo += 64u;
-          }
-        }
-        umma_commit(bar(BAR_S1_FULL));
-        if (p.has_s1w) umma_commit(bar(BAR_IN_EMPTY + s));   // in(t) consumed once S1w completes
-        TC_STAMP(2);   // MMA: S1 issued + committed
-        // ---- S2: z = A2 . [t_u ; t_w | x(t)]
-        mbar_wait(bar(BAR_T_READY), ph_t);
-        ph_t ^= 1u;
-        tc_fence_after();
-        TC_STAMP(3);   // MMA: t operand ready seen
-        uint32_t tile_lo = a2_lo0;
-        for (int ub = 0; ub < nub; ++ub) {
-          const int buf = ub & 1;
-          // wait until the epilogue drained this TMEM buffer (first use of each buffer passes: parity trick)
-          mbar_wait(bar(BAR_S2_EMPTY0 + buf), ((ph_s2e >> buf) & 1u) ^ 1u);
-          ph_s2e ^= 1u << buf;
-          tc_fence_after();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t d = tm_s2 + (uint32_t)buf * 128u + (uint32_t)g * 32u;
-            uint32_t alo = tile_lo, blo = t_lo0;
-#pragma unroll 4
-            for (int kk = 0; kk < n_s2t; ++kk) {
-              umma_lh(d, alo, a2_hi, blo, act_hi, idesc_mn, kk > 0);
-              alo += 16u;
-              blo += 64u;
-            }
-            blo = in_lo;
-            for (int kk = 0; kk < n_s2x; ++kk) {
-              umma_lh(d, alo, a2_hi, blo, act_hi, idesc_mn, 1u);
-              alo += 16u;
-              blo += 64u;
-            }
-            tile_lo += a2_tile_lo;
-          }
-          umma_commit(bar(BAR_S2_FULL0 + buf));
-          TC_STAMP(4 + ub);   // MMA: S2 block ub issued + committed
-        }
-        if (!p.has_s1w) umma_commit(bar(BAR_IN_EMPTY + s));   // layer 0: x(t) is consumed by S2
       }
-    }
-  } else {
-    // ======================= epilogue warps (128 threads; thread = TMEM lane = one row) ==============
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;             // row of every 128-row tile handled by this thread
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float cst[2][kN];                          // cell state of unit (ub*128+row), FP32, all T steps  (H <= 256)
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int n = 0; n < kN; ++n) cst[u][n] = 0.f;
-    float bi[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) bi[u][g] = (u < nub) ? p.bias[(u * 4 + g) * 128 + row] : 0.f;
-    uint32_t ph_s1 = 0, ph_s2f = 0, ph_hfree = 1;   // H_FREE phase 0 was consumed by the weight load
-    for (int t = 0; t < T; ++t) {
-      // ---- epilogue 1: t_u / t_w accumulators -> bf16 rows of the S2 B operand ---------------------
-      mbar_wait(bar(BAR_S1_FULL), ph_s1);
-      ph_s1 ^= 1u;
+      switch (nm) {
+        case 4: umma_f16_x<4>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 3: umma_f16_x<3>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 2: umma_f16_x<2>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        default: umma_f16_x<1>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+      }
+      if (streaming) {
+        umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
+        a_lo += kSlotBytes >> 4;
+        if (++w_slot == ns) { w_slot = 0; ++w_use; a_lo = w_lo0; }
+      } else {
+        a_lo += bytes >> 4;
+      }
+    };
+    auto chunk64 = [&](uint32_t bytes, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {   // the common case, no switch
+      TC_CHUNK_STAMP();
+      if (streaming) {
+        mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
+        tc_fence_after();
+      }
+      umma_f16_x<4>(d_tmem, a_lo, a_hi64, b_lo, act_hi, idesc, first_accumulates, elected);
+      if (streaming) {
+        umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
+        a_lo += kSlotBytes >> 4;
+        if (++w_slot == ns) { w_slot = 0; ++w_use; a_lo = w_lo0; }
+      } else {
+        a_lo += bytes >> 4;
+      }
+    };
+    const int n_in_chunks = p.Kin >> 6;
+    const int kt = p.ru_pad + p.rw_pad;
+    const int kt_full = kt >> 6, kt_rem = (kt & 63) >> 4;
+    const int kx_full = p.kx >> 6, kx_rem = (p.kx & 63) >> 4;
+    int in_s = 0;            // input ring stage of step t (layer 0) / of the next S1w (layers >= 1)
+    uint32_t in_ph = 0;      // its phase bit
+    auto issue_s1w = [&]() {   // t_w(tt) = A1w . in(tt), tt = the step the ring cursor points at
+      mbar_wait(bar(BAR_IN_FULL + in_s), in_ph);
       tc_fence_after();
-      if (threadIdx.x == 64) TC_STAMP(8);   // EPI: S1 accumulators seen
+      const uint32_t in_lo = in_lo0 + (uint32_t)in_s * in_stage_lo;
+      if (!streaming) a_lo = w_lo0;
+      uint32_t d = tm_s1w;
+#pragma unroll 1
+      for (int r0 = 0; r0 < p.rows_w; r0 += 128) {
+        const uint32_t bytes = (uint32_t)imin(128, p.rows_w - r0) * 128u;
+        uint32_t b = in_lo;
+#pragma unroll 1
+        for (int c = 0; c < n_in_chunks; ++c) {
+          chunk64(bytes, d, b, c > 0 ? 1u : 0u);
+          b += 256u;   // 64 K rows of the activation tile
+        }
+        d += 32u;
+      }
+      umma_commit(bar(BAR_IN_EMPTY + in_s), elected);   // in(tt) is consumed once these MMAs complete
+      if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
+    };
+    uint32_t s2_use = 0;   // global count of S2 accumulator-buffer uses (buffers alternate)
+    if (p.has_s1w) issue_s1w();
+#pragma unroll 1
+    for (int t = 0; t < n_steps; ++t) {
+      dbg_t = t;
+      // ---- S1u: [t_u ; y] = A1u . h(t-1), K block by K block as the epilogue publishes h(t-1)
+      if (!streaming) a_lo = w_lo0 + (p.segw_bytes >> 4);
       {
-        const bool do_u = (q * 32) < p.ru_pad;       // warp-uniform: any valid row in this quarter?
-        const bool do_w = p.has_s1w && (q * 32) < p.rin_pad;
-        uint32_t r[16];
-        if (do_u) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            tmem_ld16(tm_s1u + lane_addr + half * 16, r);
-            tmem_ld_wait();
-            if (row < p.ru_pad) {
-              const bool live = row < p.ru;
-              uint4 v0, v1;
-              v0.x = live ? pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
-              v0.y = live ? pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
-              v0.z = live ? pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
-              v0.w = live ? pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
-              v1.x = live ? pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
-              v1.y = live ? pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
-              v1.z = live ? pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
-              v1.w = live ? pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
-              uint8_t* dst = smem + sp.tbuf + act_offset(row, half * 16);
-              *reinterpret_cast<uint4*>(dst) = v0;
-              *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
-            }
+        uint32_t b = h_lo0;
+#pragma unroll 1
+        for (int kb = 0; kb < nub; ++kb) {
+          if (t > 0) {
+            mbar_wait(bar(BAR_H_READY + kb), (uint32_t)(t - 1) & 1u);
+            tc_fence_after();
           }
-        }
-        if (do_w) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            tmem_ld16(tm_s1w + lane_addr + half * 16, r);
-            tmem_ld_wait();
-            if (row < p.rin_pad) {
-              const bool live = row < p.rw;
-              uint4 v0, v1;
-              v0.x = live ? pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
-              v0.y = live ? pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
-              v0.z = live ? pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
-              v0.w = live ? pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
-              v1.x = live ? pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
-              v1.y = live ? pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
-              v1.z = live ? pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
-              v1.w = live ? pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
-              uint8_t* dst = smem + sp.tbuf + act_offset(p.ru_pad + row, half * 16);
-              *reinterpret_cast<uint4*>(dst) = v0;
-              *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
-            }
+          uint32_t d = tm_s1u;
+#pragma unroll 1
+          for (int r0 = 0; r0 < p.rows_u; r0 += 128) {
+            const uint32_t bytes = (uint32_t)imin(128, p.rows_u - r0) * 128u;
+            chunk64(bytes, d, b, kb > 0 ? 1u : 0u);
+            chunk64(bytes, d, b + 256u, 1u);
+            d += 32u;
           }
+          b += 512u;   // next 128 K rows of h
         }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(bar(BAR_T_READY));
-      if (threadIdx.x == 64) TC_STAMP(9);   // EPI: t operand written + arrived
-
-      // ---- epilogue 2: gates + cell update per unit block ------------------------------------------
-      // h(t-1) tile must have been copied out before it is overwritten
-      if (t > 0) {
-        mbar_wait(bar(BAR_H_FREE), ph_hfree);
-        ph_hfree ^= 1u;
+      umma_commit(bar(BAR_S1_FULL), elected);
+      TC_STAMP(2);   // MMA: S1 issued + committed
+      if (t == T) break;
+      // ---- S2: z = A2 . [t_u ; t_w | x(t)]
+      uint32_t in_lo = 0;
+      if (!p.has_s1w) {
+        mbar_wait(bar(BAR_IN_FULL + in_s), in_ph);
+        in_lo = in_lo0 + (uint32_t)in_s * in_stage_lo;
       }
-#pragma unroll
-      for (int ub = 0; ub < 2; ++ub) {
-        if (ub < nub) {
-          const int buf = ub & 1;
-          mbar_wait(bar(BAR_S2_FULL0 + buf), (ph_s2f >> buf) & 1u);
-          ph_s2f ^= 1u << buf;
+      mbar_wait(bar(BAR_T_READY), (uint32_t)t & 1u);
+      tc_fence_after();
+      TC_STAMP(3);   // MMA: t operand ready seen
+      if (!streaming) a_lo = w_lo0 + ((p.segw_bytes + p.segu_bytes) >> 4);
+#pragma unroll 1
+      for (int ub = 0; ub < nub; ++ub) {
+        const uint32_t use = s2_use + (uint32_t)ub;
+        const uint32_t buf = use & 1u;
+        if (use >= 2u) {   // wait until the epilogue drained this TMEM buffer (two uses ago)
+          mbar_wait(bar(BAR_S2_EMPTY0 + buf), ((use >> 1) - 1u) & 1u);
           tc_fence_after();
-          if (threadIdx.x == 64) TC_STAMP(10 + 2 * ub);   // EPI: z block ub seen
-          const uint32_t tb = tm_s2 + (uint32_t)buf * 128u + lane_addr;
-          const int unit = ub * 128 + row;
+        }
+        uint32_t d = tm_s2 + buf * 128u;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t b = t_lo0;
+          uint32_t acc = 0u;
+#pragma unroll 1
+          for (int c = 0; c < kt_full; ++c) {
+            chunk64(16384u, d, b, acc);
+            acc = 1u;
+            b += 256u;
+          }
+          if (kt_rem) {
+            chunk(kt_rem, (uint32_t)kt_rem * 4096u, desc_hi((uint32_t)kt_rem * 256u), d, b, acc);
+            acc = 1u;
+          }
+          b = in_lo;
+#pragma unroll 1
+          for (int c = 0; c < kx_full; ++c) {
+            chunk64(16384u, d, b, 1u);
+            b += 256u;
+          }
+          if (kx_rem) chunk(kx_rem, (uint32_t)kx_rem * 4096u, desc_hi((uint32_t)kx_rem * 256u), d, b, 1u);
+          d += 32u;
+        }
+        umma_commit(bar(BAR_S2_FULL0 + buf), elected);
+        TC_STAMP(4 + (ub & 1));   // MMA: S2 block ub issued + committed
+      }
+      s2_use += (uint32_t)nub;
+      if (!p.has_s1w) {   // layer 0: x(t) is consumed by S2
+        umma_commit(bar(BAR_IN_EMPTY + in_s), elected);
+        if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
+      }
+      // ---- S1w of the NEXT step: no recurrence, so it fills the tensor pipe while the epilogue works on z(t)
+      if (p.has_s1w && t + 1 < T) issue_s1w();
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue warps (256 threads; thread = TMEM lane = one row, 16 of the 32 columns) ==
+    const int ew = warp - 4;
+    const int q = ew & 3;                      // TMEM lane quarter this warp may access (== warp % 4)
+    const int half = ew >> 2;                  // column half
+    const int c0 = half * 16;
+    const int row = q * 32 + lane;             // row of every 128-row tile handled by this thread
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+    float cst[NUB][16];                     // cell state of unit (ub*128+row), 16 sequences, FP32, all T steps
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t zi[16], zf[16], zg[16], zo[16];
-            tmem_ld16(tb + 0 * 32 + half * 16, zi);
-            tmem_ld16(tb + 1 * 32 + half * 16, zf);
-            tmem_ld16(tb + 2 * 32 + half * 16, zg);
-            tmem_ld16(tb + 3 * 32 + half * 16, zo);
-            tmem_ld_wait();
-            float hv[16];
+    for (int u = 0; u < NUB; ++u)
 #pragma unroll
-            for (int n = 0; n < 16; ++n) {
-              const float ig = sigmoid_approx(__uint_as_float(zi[n]) + bi[ub][0]);
-              const float fg = sigmoid_approx(__uint_as_float(zf[n]) + bi[ub][1]);
-              const float gg = tanh_approx(__uint_as_float(zg[n]) + bi[ub][2]);
-              const float og = sigmoid_approx(__uint_as_float(zo[n]) + bi[ub][3]);
-              const float c = fmaf(fg, cst[ub][half * 16 + n], ig * gg);
-              cst[ub][half * 16 + n] = c;
-              hv[n] = og * tanh_approx(c);
-            }
+      for (int n = 0; n < 16; ++n) cst[u][n] = 0.f;
+    float bi[NUB][4];
+#pragma unroll
+    for (int u = 0; u < NUB; ++u)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bi[u][g] = p.bias[(u * 4 + g) * 128 + row];
+    const int b_first = cta * kN + c0;         // global sequence index of this thread's first column
+    const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
+    uint32_t s2_use = 0;
+    for (int t = 0; t < n_steps; ++t) {
+      // ---- epilogue 1: t_u / t_w accumulators -> f16 rows of the S2 B operand; Dense-top rows -> y(t-1) ----
+      mbar_wait(bar(BAR_S1_FULL), (uint32_t)t & 1u);
+      tc_fence_after();
+      if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
+      {
+        uint32_t r[16];
+        for (int r0 = 0; r0 < p.rows_u; r0 += 128) {
+          if (r0 + q * 32 >= e1_rows_u) break;   // warp-uniform: no live row in this quarter (and none above)
+          tmem_ld16(tm_s1u + (uint32_t)(r0 >> 7) * 32u + lane_addr, r);
+          tmem_ld_wait();
+          if (threadIdx.x == 128) TC_STAMP(0);   // EPI: first S1 accumulator tile in registers
+          const int j = r0 + row;
+          if (j < p.ru_pad && t < T) {
+            const bool live = j < p.ru;
             uint4 v0, v1;
-            v0.x = pack_bf16(hv[0], hv[1]);   v0.y = pack_bf16(hv[2], hv[3]);
-            v0.z = pack_bf16(hv[4], hv[5]);   v0.w = pack_bf16(hv[6], hv[7]);
-            v1.x = pack_bf16(hv[8], hv[9]);   v1.y = pack_bf16(hv[10], hv[11]);
-            v1.z = pack_bf16(hv[12], hv[13]); v1.w = pack_bf16(hv[14], hv[15]);
-            uint8_t* dst = smem + sp.hbuf + act_offset(unit, half * 16);
+            v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
+            v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
+            v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
+            v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
+            v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
+            v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
+            v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
+            v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
+            uint8_t* dst = smem + sp.tbuf + act_offset(j, c0);
             *reinterpret_cast<uint4*>(dst) = v0;
             *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
           }
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S2_EMPTY0 + buf));
-          if (threadIdx.x == 64) TC_STAMP(11 + 2 * ub);   // EPI: block ub done
+          if (t > 0 && j >= p.ru && j < e1_rows_u) {
+            const int o = j - p.ru;
+            const float db = p.dense_bias[o];
+#pragma unroll
+            for (int n = 0; n < 16; ++n)
+              if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + o] = __uint_as_float(r[n]) + db;
+          }
+        }
+        if (p.has_s1w && t < T) {
+          for (int r0 = 0; r0 < p.rows_w; r0 += 128) {
+            if (r0 + q * 32 >= p.rw_pad) break;
+            tmem_ld16(tm_s1w + (uint32_t)(r0 >> 7) * 32u + lane_addr, r);
+            tmem_ld_wait();
+            const int j = r0 + row;
+            if (j < p.rw_pad) {
+              const bool live = j < p.rw;
+              uint4 v0, v1;
+              v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
+              v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
+              v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
+              v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
+              v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
+              v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
+              v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
+              v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
+              uint8_t* dst = smem + sp.tbuf + act_offset(p.ru_pad + j, c0);
+              *reinterpret_cast<uint4*>(dst) = v0;
+              *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
+            }
+          }
         }
       }
+      if (t == T) break;
+      if (threadIdx.x == 128) TC_STAMP(1);   // EPI: t rows stored
+      tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar(BAR_H_READY));
-      if (threadIdx.x == 64) TC_STAMP(14);      // EPI: h(t) published
+      if (threadIdx.x == 128) TC_STAMP(6);   // EPI: proxy fence done
+      mbar_arrive(bar(BAR_T_READY));
+      if (threadIdx.x == 128) TC_STAMP(9);   // EPI: t operand written + arrived
+
+      // ---- epilogue 2: gates + cell update per unit block ------------------------------------------
+      // the h(t-1) tile must have been copied out before it is overwritten
+      if (p.store_h && t > 0) mbar_wait(bar(BAR_H_STORED), (uint32_t)(t - 1) & 1u);
+#pragma unroll
+      for (int ub = 0; ub < NUB; ++ub) {
+        {
+          const uint32_t use = s2_use + (uint32_t)ub;
+          const uint32_t buf = use & 1u;
+          mbar_wait(bar(BAR_S2_FULL0 + buf), (use >> 1) & 1u);
+          tc_fence_after();
+          if (threadIdx.x == 128) TC_STAMP(10 + 2 * (ub & 1));   // EPI: z block ub seen
+          const uint32_t tb = tm_s2 + buf * 128u + lane_addr;
+          uint32_t zi[16], zf[16], zg[16], zo[16];
+          tmem_ld16(tb + 0 * 32, zi);
+          tmem_ld16(tb + 1 * 32, zf);
+          tmem_ld16(tb + 2 * 32, zg);
+          tmem_ld16(tb + 3 * 32, zo);
+          tmem_ld_wait();
+          // the accumulators are in registers: hand the TMEM buffer back to the MMA warp right away
+          tc_fence_before();
+          mbar_arrive(bar(BAR_S2_EMPTY0 + buf));
+          float hv[16];
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const float ig = fmaf(0.5f, tanh_approx(__uint_as_float(zi[n]) + bi[ub][0]), 0.5f);
+            const float fg = fmaf(0.5f, tanh_approx(__uint_as_float(zf[n]) + bi[ub][1]), 0.5f);
+            const float gg = tanh_approx(__uint_as_float(zg[n]) + bi[ub][2]);
+            const float og = fmaf(0.5f, tanh_approx(__uint_as_float(zo[n]) + bi[ub][3]), 0.5f);
+            const float c = fmaf(fg, cst[ub][n], ig * gg);
+            cst[ub][n] = c;
+            hv[n] = og * tanh_approx(c);
+          }
+          uint4 v0, v1;
+          v0.x = pack_f16(hv[0], hv[1]);   v0.y = pack_f16(hv[2], hv[3]);
+          v0.z = pack_f16(hv[4], hv[5]);   v0.w = pack_f16(hv[6], hv[7]);
+          v1.x = pack_f16(hv[8], hv[9]);   v1.y = pack_f16(hv[10], hv[11]);
+          v1.z = pack_f16(hv[12], hv[13]); v1.w = pack_f16(hv[14], hv[15]);
+          uint8_t* dst = smem + sp.hbuf + act_offset(ub * 128 + row, c0);
+          *reinterpret_cast<uint4*>(dst) = v0;
+          *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
+          fence_proxy_async();
+          mbar_arrive(bar(BAR_H_READY + ub));
+          if (threadIdx.x == 128) TC_STAMP(11 + 2 * (ub & 1));   // EPI: block ub done
+        }
+      }
+      s2_use += (uint32_t)nub;
+      if (p.store_h) mbar_arrive(bar(BAR_H_DONE));
+      if (threadIdx.x == 128) TC_STAMP(14);      // EPI: h(t) published
     }
   }
 
@@ -536,22 +769,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 // ------------------------------------------------------------------------------------------------
 // packing / layout kernels (run once per weight update, or once per forward for the sequences)
 // ------------------------------------------------------------------------------------------------
-// K-major weight image: elem(row,k) at (row/8)*(K*16) + (k/8)*128 + (row%8)*16 + (k%8)*2
-__device__ __forceinline__ size_t kmaj_off(int row, int k, int K) {
-  return (size_t)(row / 8) * ((size_t)K * 16) + (size_t)(k / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)(k % 8) * 2;
-}
-
-// A1 image: rows = rank index j (padded to 8), K = kin: value = left[k*ld + j] * scale[j]
-__global__ void pack_a1_kernel(const float* __restrict__ left, int ld, const float* __restrict__ scale, int r, int r_pad8, int K,
-                               __nv_bfloat16* __restrict__ img) {
-  const int total = r_pad8 * K;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int row = idx / K, k = idx - row * K;
-    float v = 0.f;
-    if (row < r) v = left[(size_t)k * ld + row] * (scale ? scale[row] : 1.f);
-    img[kmaj_off(row, k, K) / 2] = __float2bfloat16_rn(v);
-  }
-}
+struct PackChunk {
+  uint32_t byte_off;   // offset of the chunk inside the weight stream image
+  int16_t seg;         // 0 = W (A1w), 1 = U (A1u), 2 = A2
+  int16_t rows, kc;    // chunk extent (rows multiple of 8, kc multiple of 16)
+  int16_t r0, k0;      // seg 0/1: first row / first K;  seg 2: k0 = first K of the part
+  int16_t ub, g, part; // seg 2
+};
 
 // effective right-factor element of a block: row kk of the (rank x 4H) matrix, gate column n
 __device__ __forceinline__ float block_right(const Block& b, int kk, int n) {
@@ -564,63 +788,89 @@ __device__ __forceinline__ float block_right(const Block& b, int kk, int n) {
   if (rel >= b.ncols) return 0.f;
   return b.right[(size_t)kk * b.right_ld + rel];
 }
+__device__ __forceinline__ float block_left(const Block& b, int k, int j) {   // (L sigma)[k][j]
+  return b.left[(size_t)k * b.left_ld + j] * (b.scale ? b.scale[j] : 1.f);
+}
 
-// A2 image: tile tl = ub*4+g holds gate columns n = g*H + ub*128 + i, i<128; K = ru_pad + rin_pad:
-//   k <  ru_pad            : R_u[k][n]                        (0 beyond r_u)
-//   k >= ru_pad (layer>=1) : R_w[k-ru_pad][n]                 (0 beyond r_w)
-//   k >= ru_pad (layer 0)  : W0[d][n] = sum_j L_w[d][j] s_w[j] R_w[j][n],  d = k-ru_pad < D
-__global__ void pack_a2_kernel(Block bw, Block bu, int H, int ru_pad, int rin_pad, int dense_input, int D,
-                               __nv_bfloat16* __restrict__ img, float* __restrict__ bias_img, const float* __restrict__ bias) {
-  const int K2 = ru_pad + rin_pad;
-  const int total = 4 * H * K2;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int rowg = idx / K2, k = idx - rowg * K2;
-    const int tl = rowg / 128, i = rowg - tl * 128;
-    const int ub = tl / 4, g = tl - ub * 4;
-    const int n = g * H + ub * 128 + i;
+__global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, int H, int D, int ru_pad,
+                                    const float* __restrict__ dense_k, int n_dense, int n_out, __half* __restrict__ img) {
+  const PackChunk c = chunks[blockIdx.x];
+  __half* out = img + c.byte_off / 2;
+  const int total = c.rows * c.kc;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int row = idx / c.kc, k = idx - row * c.kc;
     float v = 0.f;
-    if (k < ru_pad) {
-      if (k < bu.rank) v = block_right(bu, k, n);
+    if (c.seg == 0) {
+      const int j = c.r0 + row, kk = c.k0 + k;
+      if (j < bw.rank) v = block_left(bw, kk, j);
+    } else if (c.seg == 1) {
+      const int j = c.r0 + row, kk = c.k0 + k;
+      if (j < bu.rank) v = block_left(bu, kk, j);
+      else if (j - bu.rank < n_dense) v = dense_k[(size_t)kk * n_out + (j - bu.rank)];
     } else {
-      const int kk = k - ru_pad;
-      if (dense_input) {
-        if (kk < D) {
-          float acc = 0.f;
-          for (int j = 0; j < bw.rank; ++j) {
-            const float l = bw.left ? bw.left[(size_t)kk * bw.left_ld + j] * (bw.scale ? bw.scale[j] : 1.f) : (kk == j ? 1.f : 0.f);
-            acc = fmaf(l, block_right(bw, j, n), acc);
-          }
-          v = acc;
+      const int n = c.g * H + c.ub * 128 + row;
+      const int kk = c.k0 + k;
+      if (c.part == 0) {
+        if (kk < ru_pad) {
+          if (kk < bu.rank) v = block_right(bu, kk, n);
+        } else if (kk - ru_pad < bw.rank) {
+          v = block_right(bw, kk - ru_pad, n);
         }
-      } else if (kk < bw.rank) {
-        v = block_right(bw, kk, n);
+      } else if (kk < D) {
+        float acc = 0.f;
+        for (int j = 0; j < bw.rank; ++j) acc = fmaf(block_left(bw, kk, j), block_right(bw, j, n), acc);
+        v = acc;
       }
+      if (c.g != 2) v *= 0.5f;   // sigmoid gates: tanh(z/2) form
     }
-    img[((size_t)tl * 128 * K2 * 2 + kmaj_off(i, k, K2)) / 2] = __float2bfloat16_rn(v);
-    if (k == 0) bias_img[rowg] = bias[n];
+    const size_t off = (size_t)(row / 8) * ((size_t)c.kc * 16) + (size_t)(k / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)(k % 8) * 2;
+    out[off / 2] = __float2half_rn(v);
   }
 }
 
-// x (B,T,D) fp32 -> bf16 activation tile images [cta][t] (K = Dpad16)
-__global__ void pack_x_kernel(const float* __restrict__ x, int B, int T, int D, int Dpad, uint8_t* __restrict__ img) {
-  const size_t total = (size_t)gridDim.y * T * Dpad * kN;   // gridDim.y = number of CTAs (batch tiles)
+__global__ void pack_bias_kernel(const float* __restrict__ bias, int H, float* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // [ub][g][128]
+  if (idx >= 4 * H) return;
+  const int ub = idx / 512, g = (idx / 128) & 3, i = idx & 127;
+  img[idx] = bias[g * H + ub * 128 + i] * (g != 2 ? 0.5f : 1.f);
+}
+
+// x (B,T,D) fp32 -> f16 activation tile images [cta][t] (K = Dpad16).  One block = one batch tile x TT steps:
+// coalesced reads of each sequence's TT*D contiguous floats into smem, then contiguous 16-byte tile writes.
+__global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x, int B, int T, int D, int Dpad, int TT,
+                                                     uint8_t* __restrict__ img) {
+  extern __shared__ float xs[];   // [kN][TT*D]
   const uint32_t tile = act_tile_bytes(Dpad);
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)T * Dpad * kN; idx += (size_t)gridDim.x * blockDim.x) {
-    const int cta = blockIdx.y;
-    const int t = idx / (Dpad * kN);
-    const int rem = idx - (size_t)t * Dpad * kN;
-    const int n = rem / Dpad, k = rem - n * Dpad;
+  const int cta = blockIdx.y;
+  const int t0 = blockIdx.x * TT;
+  const int nt = imin(TT, T - t0);
+  const int row = nt * D;   // contiguous floats per sequence
+  for (int idx = threadIdx.x; idx < kN * row; idx += blockDim.x) {
+    const int n = idx / row, o = idx - n * row;
     const int b = cta * kN + n;
-    float v = 0.f;
-    if (b < B && k < D) v = x[((size_t)b * T + t) * D + k];
-    *reinterpret_cast<__nv_bfloat16*>(img + ((size_t)cta * T + t) * tile + act_offset(k, n)) = __float2bfloat16_rn(v);
+    xs[n * (TT * D) + o] = (b < B) ? x[((size_t)b * T + t0) * D + o] : 0.f;
   }
-  (void)total;
+  __syncthreads();
+  // one 16-byte store = 8 consecutive sequences of one (t, k)
+  const int per_t = Dpad * (kN / 8);
+  for (int idx = threadIdx.x; idx < nt * per_t; idx += blockDim.x) {
+    const int tt = idx / per_t, rem = idx - tt * per_t;
+    const int kg = rem / 32, w = rem - kg * 32;   // within a k-group of 8: [n-group (4)][k%8 (8)] 16-byte words
+    const int ng = w / 8, k = kg * 8 + (w & 7);
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = ng * 8 + 2 * i;
+      const float a = k < D ? xs[n * (TT * D) + tt * D + k] : 0.f;
+      const float c = k < D ? xs[(n + 1) * (TT * D) + tt * D + k] : 0.f;
+      v[i] = pack_f16(a, c);
+    }
+    *reinterpret_cast<uint4*>(img + ((size_t)cta * T + t0 + tt) * tile + act_offset(k, ng * 8)) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
 }
 
-// last layer h tiles -> y (B,T,n_out) = h . dense + bias   (or h itself as fp32 when n_out == 0)
-__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int H, const float* __restrict__ dk,
-                                  const float* __restrict__ db, int n_out, float* __restrict__ y) {
+// last layer h tiles -> y (B,T,H) fp32 (only when the model has no Dense top; the Dense top is fused otherwise)
+__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int H, float* __restrict__ y) {
   const uint32_t tile = act_tile_bytes(H);
   const int cta = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -629,23 +879,9 @@ __global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T,
     const int b = cta * kN + n;
     if (b >= B) continue;
     const uint8_t* tp = img + ((size_t)cta * T + t) * tile;
-    if (n_out > 0) {
-      for (int o = 0; o < n_out; ++o) {
-        float acc = 0.f;
-        for (int k = lane; k < H; k += 32)
-          acc = fmaf(__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tp + act_offset(k, n))), dk[(size_t)k * n_out + o], acc);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        if (lane == 0) y[((size_t)b * T + t) * n_out + o] = acc + db[o];
-      }
-    } else {
-      for (int k = lane; k < H; k += 32)
-        y[((size_t)b * T + t) * H + k] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tp + act_offset(k, n)));
-    }
+    for (int k = lane; k < H; k += 32) y[((size_t)b * T + t) * H + k] = __half2float(*reinterpret_cast<const __half*>(tp + act_offset(k, n)));
   }
 }
-
-inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
@@ -653,7 +889,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcLayerImg {
-  uint8_t *a1u = nullptr, *a1w = nullptr, *a2 = nullptr;
+  uint8_t* wimg = nullptr;
   float* bias = nullptr;
   TcLayerParams prm;
 };
@@ -665,19 +901,20 @@ struct TcState {
   size_t seq_bytes[2] = {0, 0};
   uint8_t* xseq = nullptr;
   size_t xseq_bytes = 0;
+  PackChunk* chunk_buf = nullptr;
+  size_t chunk_cap = 0;
 };
 
 void tc_free(TcState* s) {
   if (!s) return;
   for (int l = 0; l < kMaxLayers; ++l) {
-    if (s->layers[l].a1u) cudaFree(s->layers[l].a1u);
-    if (s->layers[l].a1w) cudaFree(s->layers[l].a1w);
-    if (s->layers[l].a2) cudaFree(s->layers[l].a2);
+    if (s->layers[l].wimg) cudaFree(s->layers[l].wimg);
     if (s->layers[l].bias) cudaFree(s->layers[l].bias);
   }
   for (int i = 0; i < 2; ++i)
     if (s->seq[i]) cudaFree(s->seq[i]);
   if (s->xseq) cudaFree(s->xseq);
+  if (s->chunk_buf) cudaFree(s->chunk_buf);
   delete s;
 }
 
@@ -688,34 +925,47 @@ static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const 
   const Block& bu = L.blocks[1];
   if (bu.left == nullptr || bw.left == nullptr) { *why = "full (unfactored) cells are not low-rank: use the FP32 engines"; return false; }
   const int H = L.units;
-  if (H % 128 != 0 || H > 256) { *why = "tensor-core engine needs units in {128, 256}"; return false; }
-  if (bu.rank > 128 || bw.rank > 128) { *why = "ranks above 128 are not supported by the tensor-core engine yet"; return false; }
+  if (H % 128 != 0 || H > 128 * kMaxUB) { *why = "tensor-core engine needs units in {128, 256, 384, 512}"; return false; }
+  if (bu.rank > 256 || bw.rank > 256) { *why = "ranks above 256 are not supported by the tensor-core engine"; return false; }
+  const bool last = (l == md.n_layers - 1);
+  p = TcLayerParams{};
   p.H = H;
   p.ru = bu.rank;
   p.rw = bw.rank;
   p.ru_pad = round_up(bu.rank, 16);
   p.has_s1w = l > 0;
+  p.n_dense = (last && md.n_out > 0) ? md.n_out : 0;
+  p.store_h = p.n_dense > 0 ? 0 : 1;
+  p.rows_u = round_up(p.ru + p.n_dense, 8);
+  if (p.rows_u > 384) { *why = "rank + Dense-top outputs exceed three 128-row MMA tiles"; return false; }
   if (l == 0) {
     if (L.d_in > 64) { *why = "layer-0 input_dim above 64 is not supported by the tensor-core engine yet"; return false; }
     p.Kin = round_up(L.d_in, 16);
-    p.rin_pad = p.Kin;
+    p.kx = p.Kin;
+    p.rw_pad = 0;
+    p.rows_w = 0;
   } else {
     p.Kin = md.layers[l - 1].units;
-    p.rin_pad = round_up(bw.rank, 16);
+    p.kx = 0;
+    p.rw_pad = round_up(bw.rank, 16);
+    p.rows_w = round_up(bw.rank, 8);
   }
-  p.a1u_bytes = (uint32_t)round_up(p.ru, 8) * H * 2;
-  p.a1w_bytes = p.has_s1w ? (uint32_t)round_up(p.rw, 8) * p.Kin * 2 : 0;
-  p.a2_bytes = (uint32_t)4 * H * (p.ru_pad + p.rin_pad) * 2;
-  p.a1u = p.a1w = p.a2 = nullptr;
-  p.bias = nullptr;
-  p.dbg = nullptr;
-  p.in_seq = nullptr;
-  p.out_seq = nullptr;
-  p.T = 0;
+  p.segw_bytes = p.segu_bytes = p.seg2_bytes = 0;
+  if (p.has_s1w) for_seg_w(p, [&](uint32_t b, int, int, int) { p.segw_bytes += b; });
+  for_seg_u(p, [&](uint32_t b, int, int, int, int) { p.segu_bytes += b; });
+  for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { p.seg2_bytes += b; });
+  // resident if the whole stream fits next to the activation buffers, else a ring of 16 KB slots
+  p.streaming = 0;
+  p.w_slots = 1;
   p.in_stages = 3;
-  if (tc_plan(p).total > 227 * 1024) p.in_stages = 2;
-  const TcSmemPlan sp = tc_plan(p);
-  if (sp.total > 227 * 1024) { *why = "factor matrices of this rank do not fit the shared memory of one SM (single-CTA engine)"; return false; }
+  if (tc_plan(p).total > kSmemCap) p.in_stages = 2;
+  if (tc_plan(p).total > kSmemCap) {
+    p.streaming = 1;
+    p.in_stages = 2;
+    p.w_slots = kMaxWSlots;
+    while (p.w_slots > 3 && tc_plan(p).total > kSmemCap) --p.w_slots;
+    if (tc_plan(p).total > kSmemCap) { *why = "activation buffers of this layer do not fit shared memory next to a weight ring"; return false; }
+  }
   return true;
 }
 
@@ -744,30 +994,48 @@ int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const 
       TcLayerImg& li = st->layers[l];
       TcLayerParams p;
       SVD_REQUIRE(tc_layer_params(md, l, p, &why), "tensor-core engine: %s", why);
-      if (li.a1u) cudaFree(li.a1u);
-      if (li.a1w) cudaFree(li.a1w);
-      if (li.a2) cudaFree(li.a2);
+      if (li.wimg) cudaFree(li.wimg);
       if (li.bias) cudaFree(li.bias);
-      li.a1u = li.a1w = li.a2 = nullptr;
+      li.wimg = nullptr;
       li.bias = nullptr;
-      SVD_CUDA_TRY(cudaMalloc(&li.a1u, p.a1u_bytes));
-      if (p.has_s1w) SVD_CUDA_TRY(cudaMalloc(&li.a1w, p.a1w_bytes));
-      SVD_CUDA_TRY(cudaMalloc(&li.a2, p.a2_bytes));
+      const uint32_t wbytes = p.segw_bytes + p.segu_bytes + p.seg2_bytes;
+      SVD_CUDA_TRY(cudaMalloc(&li.wimg, wbytes));
       SVD_CUDA_TRY(cudaMalloc(&li.bias, sizeof(float) * 4 * p.H));
-      const LayerDesc& Ld = md.layers[l];
-      const Block& bw = Ld.blocks[0];
-      const Block& bu = Ld.blocks[1];
-      pack_a1_kernel<<<64, 256, 0, stream>>>(bu.left, bu.left_ld, bu.scale, bu.rank, round_up(bu.rank, 8), p.H,
-                                             reinterpret_cast<__nv_bfloat16*>(li.a1u));
+      // chunk table: the SAME iteration the kernel uses defines where every chunk lives
+      std::vector<PackChunk> chunks;
+      uint32_t off = 0;
       if (p.has_s1w)
-        pack_a1_kernel<<<64, 256, 0, stream>>>(bw.left, bw.left_ld, bw.scale, bw.rank, round_up(bw.rank, 8), p.Kin,
-                                               reinterpret_cast<__nv_bfloat16*>(li.a1w));
-      pack_a2_kernel<<<296, 256, 0, stream>>>(bw, bu, p.H, p.ru_pad, p.rin_pad, l == 0 ? 1 : 0, Ld.d_in,
-                                              reinterpret_cast<__nv_bfloat16*>(li.a2), li.bias, Ld.bias);
-      nl += p.has_s1w ? 3 : 2;
-      p.a1u = li.a1u;
-      p.a1w = li.a1w;
-      p.a2 = li.a2;
+        for_seg_w(p, [&](uint32_t b, int r0, int rows, int k0) {
+          chunks.push_back(PackChunk{off, 0, (int16_t)rows, 64, (int16_t)r0, (int16_t)k0, 0, 0, 0});
+          off += b;
+        });
+      for_seg_u(p, [&](uint32_t b, int, int r0, int rows, int k0) {
+        chunks.push_back(PackChunk{off, 1, (int16_t)rows, 64, (int16_t)r0, (int16_t)k0, 0, 0, 0});
+        off += b;
+      });
+      for_seg_2(p, [&](uint32_t b, int ub, int g, int part, int k0, int kc) {
+        chunks.push_back(PackChunk{off, 2, 128, (int16_t)kc, 0, (int16_t)k0, (int16_t)ub, (int16_t)g, (int16_t)part});
+        off += b;
+      });
+      if (st->chunk_cap < chunks.size()) {
+        if (st->chunk_buf) {
+          SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+          cudaFree(st->chunk_buf);
+        }
+        SVD_CUDA_TRY(cudaMalloc(&st->chunk_buf, sizeof(PackChunk) * chunks.size()));
+        st->chunk_cap = chunks.size();
+      }
+      // pageable source: the copy is staged before the call returns, so `chunks` may die afterwards;
+      // the sync keeps the shared table buffer from being overwritten while a previous layer's packer reads it
+      SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+      SVD_CUDA_TRY(cudaMemcpyAsync(st->chunk_buf, chunks.data(), sizeof(PackChunk) * chunks.size(), cudaMemcpyHostToDevice, stream));
+      const LayerDesc& Ld = md.layers[l];
+      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(st->chunk_buf, Ld.blocks[0], Ld.blocks[1], p.H, Ld.d_in, p.ru_pad,
+                                                                       md.dense_kernel, p.n_dense, md.n_out,
+                                                                       reinterpret_cast<__half*>(li.wimg));
+      pack_bias_kernel<<<(4 * p.H + 255) / 256, 256, 0, stream>>>(Ld.bias, p.H, li.bias);
+      nl += 2;
+      p.wimg = li.wimg;
       p.bias = li.bias;
       li.prm = p;
     }
@@ -785,6 +1053,7 @@ int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const 
     st->xseq_bytes = xbytes;
   }
   for (int l = 0; l < L; ++l) {
+    if (!st->layers[l].prm.store_h) continue;
     const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H);
     const int slot = l & 1;
     if (st->seq_bytes[slot] < hb) {
@@ -793,37 +1062,67 @@ int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const 
       st->seq_bytes[slot] = hb;
     }
   }
-  pack_x_kernel<<<dim3(64, n_cta), 256, 0, stream>>>(a.x, B, T, md.input_dim, Dpad, st->xseq);
+  {
+    const int D = md.input_dim;
+    const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
+    pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * kN * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, st->xseq);
+  }
   ++nl;
   static long long* dbg_buf = nullptr;
   const char* dbg_env = getenv("SVDLSTM_TC_TIMELINE");
-  if (dbg_env && !dbg_buf) SVD_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * 64 * 16 * kMaxLayers));
+  if (dbg_env && !dbg_buf) {
+    SVD_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * kDbgPerLayer * kMaxLayers));
+    SVD_CUDA_TRY(cudaMemset(dbg_buf, 0, sizeof(long long) * kDbgPerLayer * kMaxLayers));
+  }
   for (int l = 0; l < L; ++l) {
     TcLayerParams p = st->layers[l].prm;
     p.T = T;
-    p.dbg = dbg_env ? dbg_buf + (size_t)l * 64 * 16 : nullptr;
+    p.B = B;
+    p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
     p.in_seq = (l == 0) ? st->xseq : st->seq[(l - 1) & 1];
-    p.out_seq = st->seq[l & 1];
+    p.out_seq = p.store_h ? st->seq[l & 1] : nullptr;
+    p.y = a.y;
+    p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
-    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
-    lstm_tc_layer_kernel<<<n_cta, kTcThreads, sp.total, stream>>>(p);
+    switch (p.H / 128) {
+#define SVD_TC_LAUNCH(NUB_)                                                                                                          \
+  case NUB_:                                                                                                                         \
+    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));      \
+    lstm_tc_layer_kernel<NUB_><<<n_cta, kTcThreads, sp.total, stream>>>(p);                                                          \
+    break;
+      SVD_TC_LAUNCH(1)
+      SVD_TC_LAUNCH(2)
+      SVD_TC_LAUNCH(3)
+      SVD_TC_LAUNCH(4)
+#undef SVD_TC_LAUNCH
+      default:
+        set_error("tensor-core engine: unsupported units %d", p.H);
+        return -1;
+    }
     ++nl;
   }
-  unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(st->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, md.dense_kernel,
-                                                          md.dense_bias, md.n_out, a.y);
-  ++nl;
+  if (st->layers[L - 1].prm.store_h) {   // no Dense top: the output is the last hidden sequence itself
+    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(st->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, a.y);
+    ++nl;
+  }
   SVD_CUDA_TRY(cudaGetLastError());
   if (dbg_env) {   // debugging aid: dump the per-step timeline of CTA 0 (cycles relative to the step's first stamp)
-    static long long host[64 * 16 * kMaxLayers];
+    static long long host[kDbgPerLayer * kMaxLayers];
     SVD_CUDA_TRY(cudaStreamSynchronize(stream));
-    SVD_CUDA_TRY(cudaMemcpy(host, dbg_buf, sizeof(long long) * 64 * 16 * L, cudaMemcpyDeviceToHost));
+    SVD_CUDA_TRY(cudaMemcpy(host, dbg_buf, sizeof(long long) * kDbgPerLayer * L, cudaMemcpyDeviceToHost));
     for (int l = 0; l < L; ++l)
       for (int t = 20; t < 24 && t < T; ++t) {
-        const long long* r = host + ((size_t)l * 64 + t) * 16;
-        fprintf(stderr, "[tc timeline] layer %d step %d:", l, t);
-        for (int i = 0; i < 15; ++i) fprintf(stderr, " %lld", r[i] ? r[i] - r[0] : -1);
-        fprintf(stderr, "  | step period %lld\n", r[0] - (r - 16)[0]);
+        const long long* r = host + (size_t)l * kDbgPerLayer + (size_t)t * 16;
+        fprintf(stderr, "[tc timeline] layer %d step %d (stream=%d slots=%d):", l, t, st->layers[l].prm.streaming, st->layers[l].prm.w_slots);
+        for (int i = 0; i < 15; ++i) fprintf(stderr, " %lld", r[i] ? r[i] - r[2] : -1);
+        fprintf(stderr, "  | step period %lld\n", r[2] - (r - 16)[2]);
       }
+    for (int l = 0; l < L; ++l) {   // issue time of every weight chunk of step 20, relative to that step's S1 commit
+      const long long* r = host + (size_t)l * kDbgPerLayer;
+      fprintf(stderr, "[tc chunks] layer %d step 20:", l);
+      for (int i = 0; i < 250 && r[64 * 16 + i]; ++i) fprintf(stderr, " %lld", r[64 * 16 + i] - r[20 * 16 + 2]);
+      fprintf(stderr, "\n");
+    }
   }
   *launches = nl;
   return 0;
