@@ -2,12 +2,14 @@
 """bench.py -- headline benchmark of the SVD-factored LSTM hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--rank R] [--engine auto|general|tc_bf16] [--batch B] [--seq-len T] [--quick]
+                    [--rank R] [--engine tc|general|auto] [--batch B] [--seq-len T] [--quick]
 
 Workload (BASELINE.json configs[2], the config the metric "low-rank LSTM timesteps/sec (batch 4096)" is
 quoted on): synthetic 2-layer SVD-LSTM, D=16, H=256, seq_len=1024, batch=4096 per GPU, 3-factor form
-truncated to rank R (default 128), Dense(1) top.  One "step" = one forward pass of the whole batch
-through all T timesteps, all layers and the Dense top.  value = sequence-timesteps/s over all GPUs
+truncated to rank R (default 128), Dense(1) top, run on the tcgen05 tensor-core engine (FP16 operands,
+FP32 accumulation and cell state; its RMSE delta against the FP32 parity engine is measured in the same run
+and reported under "rmse_delta").  One "step" = one forward pass of the whole batch through all T
+timesteps, all layers and the Dense top; "rank_sweep" repeats the measurement for ranks 8..256.  value = sequence-timesteps/s over all GPUs
 (weak scaling: every GPU runs its own 4096 sequences; the path shards by independent sequences with
 no data-path collective).  The batch-1 half of the metric (us/step vs rank on the shipped DROPBEAR
 model, configs[1]) is measured in the same run and reported under "batch1_us_per_step".
@@ -36,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rank", type=int, default=128)
-    ap.add_argument("--engine", default=None)
+    ap.add_argument("--engine", default="tc")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--seq-len", type=int, default=1024)
     ap.add_argument("--hidden", type=int, default=256)
@@ -45,6 +47,7 @@ def parse():
     ap.add_argument("--no-batch1", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     a = ap.parse_args()
     if a.quick:
         a.batch, a.seq_len = 512, 64
@@ -124,22 +127,35 @@ def build_workload(a, svdlstm):
     full = svdlstm.full_model_from_weights(layers, dense, return_sequences=True)
     sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
     model = svdlstm.truncate_singular_model(sm, a.rank)
+    model._singular_parent = sm
     return layers, dense, model
 
 
-def cpu_forward_sample(layers, dense, rank, Bs, Ts, seed=0):
-    """Reference maths (oracle port, float32, batched numpy => multithreaded BLAS) on a bounded sample."""
+def cpu_oracle_model(layers, dense, rank):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import svdlstm_oracle as O
     ofull = O.model_from_weights(layers, dense, dtype=np.float32)
     osm = O.make_LSTM_singular_model(ofull, merged_kernel=True, return_sequences=True, svd_dtype=np.float32, dtype=np.float32)
-    om = O.truncate_singular_model(osm, rank, dtype=np.float32)
+    return O.truncate_singular_model(osm, rank, dtype=np.float32)
+
+
+def cpu_forward_sample(om, Bs, Ts, seed=0):
+    """Reference maths (oracle port, float32, batched numpy => multithreaded BLAS) on a bounded sample."""
     x = np.random.default_rng(seed).standard_normal((Bs, Ts, 16)).astype(np.float32)
-    om.predict(x[:, :2])                      # warm-up
     t0 = time.perf_counter()
     om.predict(x)
     dt = time.perf_counter() - t0
     return Bs * Ts / dt, dt
+
+
+def cpu_sample_shape(om, a, target_s):
+    """Sample = the full batch (same per-step matrix shapes as the GPU workload) for as many timesteps as fit
+    `target_s` seconds of host time, found by timing 2 steps first."""
+    Bs = a.batch if not a.quick else 64
+    om.predict(np.zeros((Bs, 1, 16), np.float32))          # warm-up (BLAS threads, page faults)
+    _, dt = cpu_forward_sample(om, Bs, 2)
+    Ts = int(max(2, min(a.seq_len, target_s / max(dt / 2, 1e-6))))
+    return Bs, Ts
 
 
 def reference_arm(a):
@@ -148,20 +164,20 @@ def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    layers, dense = None, None
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import svdlstm_oracle as O
     layers, dense = O.synthetic_layers(16, a.hidden, a.layers, seed=0)
-    Bs, Ts = (256, 8) if not a.quick else (64, 4)
+    om = cpu_oracle_model(layers, dense, a.rank)
     cores = os.cpu_count() or 1
+    Bs, Ts = cpu_sample_shape(om, a, target_s=6.0 if not a.quick else 0.5)
     vals = []
     for i in range(a.warmup + a.steps):
-        v, dt = cpu_forward_sample(layers, dense, a.rank, Bs, Ts, seed=i)
+        v, dt = cpu_forward_sample(om, Bs, Ts, seed=i)
         if i >= a.warmup:
             vals.append((v, dt))
     v = float(np.mean([x[0] for x in vals]))
     ms = float(np.mean([x[1] for x in vals])) * 1e3
-    sample = "B=%d of %d sequences x T=%d of %d steps per step, float32 numpy (multithreaded BLAS)" % (Bs, a.batch, Ts, a.seq_len)
+    sample = "B=%d of %d sequences x T=%d of %d steps per step, float32 numpy oracle (multithreaded BLAS)" % (Bs, a.batch, Ts, a.seq_len)
     line = {"impl": "reference", "metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": v, "unit": "sequence-timesteps/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -174,7 +190,7 @@ def reference_arm(a):
 def workload_config(a):
     return {"workload": "synthetic %d-layer SVD-LSTM (3-factor, merged) D=16 H=%d seq_len=%d batch=%d/GPU rank=%d + Dense(1)"
                         % (a.layers, a.hidden, a.seq_len, a.batch, a.rank),
-            "rank": a.rank, "form": "singular", "batch_per_gpu": a.batch, "seq_len": a.seq_len, "hidden": a.hidden, "layers": a.layers,
+            "rank": a.rank, "form": "singular (3-factor)", "batch_per_gpu": a.batch, "seq_len": a.seq_len, "hidden": a.hidden, "layers": a.layers,
             "l2": "inputs larger than L2 (x is %.0f MB per GPU)" % (a.batch * a.seq_len * 16 * 4 / 1e6),
             "parallelism": "independent sequences per GPU, no data-path collective"}
 
@@ -234,6 +250,7 @@ def main():
     dev = torch.device("cuda", local)
 
     layers, dense, model = build_workload(a, svdlstm)
+    smodel = model._singular_parent
     B, T, D = a.batch, a.seq_len, 16
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(B, T, D, generator=gen).pin_memory()
@@ -305,21 +322,57 @@ def main():
     fl = flops_per_seq_step(D, a.hidden, a.layers, a.rank) * B * T
     achieved = fl / (kern_ms * 1e-3) / 1e12
     eng_id = model.last_engine()
-    eng_name = {0: "auto", 1: "general(fp32 cuda cores)", 2: "wavefront(fp32)", 3: "tc_bf16(tcgen05)"}.get(eng_id, str(eng_id))
+    eng_name = {0: "auto", 1: "general(fp32 cuda cores)", 2: "wavefront(fp32)", 3: "tc(tcgen05 f16 operands, fp32 accumulate)"}.get(eng_id, str(eng_id))
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes of one forward, from the committed ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("rank_%d" % a.rank)
+        except Exception:
+            traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
-                "kernel": eng_name, "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms}
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + " (cuBLAS bf16 sustained; f16 runs at the same tensor rate)",
+                "kernel": "lstm_tc_layer_kernel x%d layers (one forward = one 'launch' here; pack_x included in the time)" % a.layers
+                          if eng_id == 3 else eng_name,
+                "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms,
+                "hbm_bytes_algorithmic": int(B * T * (D * 4 + 4) + (a.layers - 1) * 2 * B * T * a.hidden * 2 + B * T * D * 2 * 2)}
     line = {"metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": value, "unit": "sequence-timesteps/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if eng_id == 3 else "f32", "data": "synthetic", "config": workload_config(a),
+            "vs_baseline": None, "dtype": "f16" if eng_id == 3 else "f32", "data": "synthetic", "config": workload_config(a),
             "engine": eng_name, "roofline": roofline, "clocks": clocks, "gpu_launches": launches}
+    if eng_id == 3:
+        # reduced-precision report (north_star): RMSE of the tensor-core output against the FP32 parity engine, same weights/inputs
+        xs = x[:256, :128].contiguous()
+        y32 = model(xs, engine="general")
+        ytc = model(xs, engine=engine)
+        line["rmse_delta"] = {"rmse_tc_vs_fp32": float(((ytc - y32) ** 2).mean().sqrt()), "max_abs": float((ytc - y32).abs().max()),
+                              "output_rms": float((y32 ** 2).mean().sqrt()), "sample": "first 256 sequences x 128 steps"}
+    if not a.no_sweep and world == 1 and eng_id == 3:
+        sweep = {}
+        for r in (8, 16, 32, 64, 128, 256):
+            m = svdlstm.truncate_singular_model(smodel, r)
+            m(x, engine=engine)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                m(x, engine=engine)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            tf = flops_per_seq_step(D, a.hidden, a.layers, r) * B * T / (ms * 1e-3) / 1e12
+            sweep["r%d" % r] = {"ms": round(ms, 3), "Mseqsteps_per_s": round(B * T / ms / 1e3, 1), "tflops": round(tf, 1),
+                                "frac_of_peak": round(tf / pk["bf16_tflops_sustained"], 4)}
+        line["rank_sweep"] = sweep
     if e2e is not None:
         line["e2e"] = e2e
     if not a.no_batch1 and world == 1:
         line["batch1_us_per_step"] = batch1_table(svdlstm, torch)
     if not a.no_cpu_baseline and world == 1:
-        Bs, Ts = (256, 8) if not a.quick else (64, 4)
-        v, dt = cpu_forward_sample(layers, dense, a.rank, Bs, Ts)
+        om = cpu_oracle_model(layers, dense, a.rank)
+        Bs, Ts = cpu_sample_shape(om, a, target_s=12.0 if not a.quick else 0.5)
+        v, dt = cpu_forward_sample(om, Bs, Ts)
         line["cpu_baseline"] = {"value": v, "unit": "sequence-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "B=%d of %d sequences x T=%d of %d steps, float32 numpy oracle (multithreaded BLAS), %.1f s"
                                           % (Bs, B, Ts, T, dt)}

@@ -5,7 +5,7 @@ Drop-in for the reference's layer / builder API (code/svd_classes_v3.py) and dri
 (code/svd_acceleration_v3.py), Python host -> C-ABI (include/svdlstm.h) -> hand-written CUDA.
 There is no CPU fallback: the numpy oracle under oracle/ is test infrastructure only.
 """
-from ._cabi import (ENGINE_AUTO, ENGINE_GENERAL, ENGINE_TC_BF16, ENGINE_WAVEFRONT, EXPORTS, LIB_PATH, lib,
+from ._cabi import (ENGINE_AUTO, ENGINE_GENERAL, ENGINE_TC, ENGINE_TC_BF16, ENGINE_WAVEFRONT, EXPORTS, LIB_PATH, lib,
                     require_cuda)
 from . import _cabi
 from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell, OrthogonalRegularizer,

@@ -24,8 +24,9 @@ ZERO_OUTPUT_FOR_MASK = 8
 ENGINE_AUTO = 0
 ENGINE_GENERAL = 1
 ENGINE_WAVEFRONT = 2
-ENGINE_TC_BF16 = 3
-ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc_bf16": 3, None: 0}
+ENGINE_TC = 3          # tcgen05 tensor-core engine: FP16 operands, FP32 accumulation / cell state (reduced precision)
+ENGINE_TC_BF16 = ENGINE_TC   # name of the first (BF16-operand) version of that engine; kept as an alias
+ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc": 3, "tc_f16": 3, "tc_bf16": 3, None: 0}
 
 EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",

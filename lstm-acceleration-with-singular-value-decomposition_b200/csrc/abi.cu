@@ -248,13 +248,13 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
       SVD_REQUIRE(wavefront_supported(h->md, a), "svdlstm_forward: wavefront engine needs units,input_dim,ranks <= 32, <= %d layers, n_out <= 1, no mask, and factors within the register budget", 6);
       rc = run_wavefront(h->md, h->dev_md, a, stream, &launches);
       break;
-    case SVDLSTM_ENGINE_TC_BF16: {
+    case SVDLSTM_ENGINE_TC: {
       const char* why = "";
       if (!tc_supported(h->md, a, &why)) {
         set_error("svdlstm_forward: tensor-core engine unsupported for this model/call: %s", why);
         return -3;
       }
-      rc = run_tc_bf16(h->md, &h->tc, h->tc_dirty, a, stream, &launches);
+      rc = run_tc(h->md, &h->tc, h->tc_dirty, a, stream, &launches);
       if (rc == 0) h->tc_dirty = false;
       break;
     }

@@ -84,7 +84,7 @@ int run_wavefront(const ModelDesc& host_md, const ModelDesc* dev_md, const Forwa
                   cudaStream_t stream, int* launches);
 bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why);
 struct TcState;  // packed bf16 weights owned by the handle
-int run_tc_bf16(const ModelDesc& host_md, TcState** state, bool weights_dirty, const ForwardArgs& a,
+int run_tc(const ModelDesc& host_md, TcState** state, bool weights_dirty, const ForwardArgs& a,
                 cudaStream_t stream, int* launches);
 void tc_free(TcState* s);
 

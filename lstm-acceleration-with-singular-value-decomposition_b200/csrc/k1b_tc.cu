@@ -227,6 +227,21 @@ __host__ __device__ inline uint32_t act_offset(int k, int n) {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
+// 16 fp32 accumulator columns of one row -> f16, two 16-byte stores into an MN-major activation tile
+__device__ __forceinline__ void store_t_row(uint8_t* dst, const uint32_t* r, bool live) {
+  uint4 v0, v1;
+  v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
+  v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
+  v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
+  v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
+  v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
+  v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
+  v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
+  v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
+  *reinterpret_cast<uint4*>(dst) = v0;
+  *reinterpret_cast<uint4*>(dst + 128) = v1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-layer launch parameters
 // ------------------------------------------------------------------------------------------------
@@ -647,58 +662,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       tc_fence_after();
       if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
       {
-        uint32_t r[16];
-        for (int r0 = 0; r0 < p.rows_u; r0 += 128) {
-          if (r0 + q * 32 >= e1_rows_u) break;   // warp-uniform: no live row in this quarter (and none above)
-          tmem_ld16(tm_s1u + (uint32_t)(r0 >> 7) * 32u + lane_addr, r);
+        // both accumulator sets are fetched before the single wait: a TMEM load costs ~500 cycles of latency here
+        uint32_t au[16], aw[16];
+        const int rows_max = p.rows_u > p.rows_w ? p.rows_u : p.rows_w;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_max; r0 += 128) {
+          const bool do_u = r0 + q * 32 < e1_rows_u;                              // warp-uniform: a live row in this quarter
+          const bool do_w = p.has_s1w && t < T && r0 + q * 32 < p.rw_pad;
+          if (!do_u && !do_w) break;
+          if (do_u) tmem_ld16(tm_s1u + (uint32_t)(r0 >> 7) * 32u + lane_addr, au);
+          if (do_w) tmem_ld16(tm_s1w + (uint32_t)(r0 >> 7) * 32u + lane_addr, aw);
           tmem_ld_wait();
-          if (threadIdx.x == 128) TC_STAMP(0);   // EPI: first S1 accumulator tile in registers
+          if (threadIdx.x == 128) TC_STAMP(0);   // EPI: S1 accumulator tiles in registers
           const int j = r0 + row;
-          if (j < p.ru_pad && t < T) {
-            const bool live = j < p.ru;
-            uint4 v0, v1;
-            v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
-            v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
-            v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
-            v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
-            v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
-            v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
-            v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
-            v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
-            uint8_t* dst = smem + sp.tbuf + act_offset(j, c0);
-            *reinterpret_cast<uint4*>(dst) = v0;
-            *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
-          }
-          if (t > 0 && j >= p.ru && j < e1_rows_u) {
-            const int o = j - p.ru;
-            const float db = p.dense_bias[o];
+          if (do_u) {
+            if (j < p.ru_pad && t < T) store_t_row(smem + sp.tbuf + act_offset(j, c0), au, j < p.ru);
+            if (t > 0 && j >= p.ru && j < e1_rows_u) {
+              const int o = j - p.ru;
+              const float db = p.dense_bias[o];
 #pragma unroll
-            for (int n = 0; n < 16; ++n)
-              if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + o] = __uint_as_float(r[n]) + db;
-          }
-        }
-        if (p.has_s1w && t < T) {
-          for (int r0 = 0; r0 < p.rows_w; r0 += 128) {
-            if (r0 + q * 32 >= p.rw_pad) break;
-            tmem_ld16(tm_s1w + (uint32_t)(r0 >> 7) * 32u + lane_addr, r);
-            tmem_ld_wait();
-            const int j = r0 + row;
-            if (j < p.rw_pad) {
-              const bool live = j < p.rw;
-              uint4 v0, v1;
-              v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
-              v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
-              v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
-              v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
-              v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
-              v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
-              v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
-              v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
-              uint8_t* dst = smem + sp.tbuf + act_offset(p.ru_pad + j, c0);
-              *reinterpret_cast<uint4*>(dst) = v0;
-              *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
+              for (int n = 0; n < 16; ++n)
+                if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + o] = __uint_as_float(au[n]) + db;
             }
           }
+          if (do_w && j < p.rw_pad) store_t_row(smem + sp.tbuf + act_offset(p.ru_pad + j, c0), aw, j < p.rw);
         }
       }
       if (t == T) break;
@@ -980,7 +967,7 @@ bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why) {
   return true;
 }
 
-int run_tc_bf16(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
+int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
   const char* why = "";
   int nl = 0;
   if (*state == nullptr) {

@@ -28,7 +28,7 @@ _default_engine = "auto"
 
 
 def set_default_engine(name: str) -> None:
-    """'auto' | 'general' | 'wavefront' | 'tc_bf16' -- engine used when a call does not name one."""
+    """'auto' | 'general' | 'wavefront' | 'tc' -- engine used when a call does not name one."""
     global _default_engine
     if name not in C.ENGINE_NAMES:
         raise ValueError("unknown engine %r" % (name,))
