@@ -245,8 +245,18 @@ __device__ __forceinline__ void store_t_row(uint8_t* dst, const uint32_t* r, boo
 // ------------------------------------------------------------------------------------------------
 // per-layer launch parameters
 // ------------------------------------------------------------------------------------------------
+struct PackChunk {
+  uint32_t byte_off;   // offset of the chunk inside the weight stream image
+  int16_t seg;         // 0 = W (A1w), 1 = U (A1u), 2 = A2
+  int16_t rows, kc;    // chunk extent (rows multiple of 8, kc multiple of 16)
+  int16_t r0, k0;      // seg 0/1: first row / first K;  seg 2: k0 = first K of the part
+  int16_t ub, g, part; // seg 2
+};
+
 struct TcLayerParams {
   const uint8_t* wimg;      // weight stream image: [segment W][segment U][segment 2]
+  const PackChunk* chunks;  // the same stream as a chunk table (offset, extent) in consumption order: [W | U | 2]
+  int n_chunks_w, n_chunks_u, n_chunks_2;
   const float* bias;        // [nub][4][128]; gates i,f,o pre-scaled by 0.5 (sigmoid(x) = 0.5 tanh(x/2) + 0.5)
   const uint8_t* in_seq;    // activation tile images [cta][t], K = Kin
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
@@ -267,7 +277,7 @@ struct TcLayerParams {
 };
 
 struct TcSmemPlan {
-  uint32_t w, hbuf, tbuf, inbuf, bars, tmem_slot, total;
+  uint32_t w, hbuf, tbuf, inbuf, bars, tmem_slot, ctab, total;
 };
 
 __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
@@ -280,6 +290,8 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin);
   s.bars = off; off += 512;
   s.tmem_slot = off; off += 16;
+  // streaming: the chunk table (offset, bytes in 256-byte units) lives in smem -- with a 227 KB carve-out there is no L1 to cache it
+  s.ctab = off; off += p.streaming ? (uint32_t)(((p.n_chunks_w + p.n_chunks_u + p.n_chunks_2) * 4 + 15) & ~15) : 0u;
   s.total = off;
   return s;
 }
@@ -360,7 +372,7 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 #define TC_CHUNK_STAMP() do { } while (0)
 #endif
 
-template <int NUB>
+template <int NUB, bool STREAM>
 __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcSmemPlan sp = tc_plan(p);
@@ -383,6 +395,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   if (p.streaming)   // stale bytes behind short chunks feed unused accumulator rows only, but keep them finite
     for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)ns * kSlotBytes; i += kTcThreads * 16u)
       *reinterpret_cast<uint4*>(smem + sp.w + i) = make_uint4(0, 0, 0, 0);
+  if (STREAM) {
+    const int nc = p.n_chunks_w + p.n_chunks_u + p.n_chunks_2;
+    uint32_t* ctab = reinterpret_cast<uint32_t*>(smem + sp.ctab);
+    for (int i = threadIdx.x; i < nc; i += kTcThreads) {
+      const PackChunk c = p.chunks[i];
+      ctab[i] = (c.byte_off >> 8) | (((uint32_t)c.rows * (uint32_t)c.kc * 2u) >> 8) << 16;
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxWSlots; ++s) {
       mbar_init(bar(BAR_W_FULL + s), 1);
@@ -415,33 +435,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   if (warp == 0) {
     // ======================= weight streamer ====================================================
     if (lane == 0) {
-      const uint32_t wbytes = p.segw_bytes + p.segu_bytes + p.seg2_bytes;
-      if (!p.streaming) {
+      if (!STREAM) {
+        const uint32_t wbytes = p.segw_bytes + p.segu_bytes + p.seg2_bytes;
         mbar_expect_tx(bar(BAR_W_FULL), wbytes);
+#pragma unroll 1
         for (uint32_t o = 0; o < wbytes; o += 65536u) {
           const uint32_t n = wbytes - o < 65536u ? wbytes - o : 65536u;
           bulk_g2s(sbase + sp.w + o, p.wimg + o, n, bar(BAR_W_FULL));
         }
       } else {
+        // walk the chunk table in consumption order: [W] then per step [U][2][W of the next step], finally [U] (Dense flush)
         int slot = 0;
         uint32_t use = 0;   // how many times the ring wrapped
-        const uint8_t* src = nullptr;
-        auto push = [&](uint32_t bytes) {
-          if (use > 0) mbar_wait(bar(BAR_W_EMPTY + slot), (use - 1u) & 1u);
-          mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
-          bulk_g2s(sbase + sp.w + (uint32_t)slot * kSlotBytes, src, bytes, bar(BAR_W_FULL + slot));
-          src += bytes;
-          if (++slot == ns) { slot = 0; ++use; }
-        };
-        auto seg_w = [&]() { src = p.wimg; for_seg_w(p, [&](uint32_t b, int, int, int) { push(b); }); };
-        auto seg_u = [&]() { src = p.wimg + p.segw_bytes; for_seg_u(p, [&](uint32_t b, int, int, int, int) { push(b); }); };
-        auto seg_2 = [&]() { src = p.wimg + p.segw_bytes + p.segu_bytes; for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { push(b); }); };
-        if (p.has_s1w) seg_w();
-        for (int t = 0; t < n_steps; ++t) {
-          seg_u();
-          if (t == T) break;
-          seg_2();
-          if (p.has_s1w && t + 1 < T) seg_w();
+        const int nw = p.n_chunks_w, nu = p.n_chunks_u, n2 = p.n_chunks_2;
+        int t = 0, ph = p.has_s1w ? 0 : 1;   // ph 0: W of step 0; then per step 1: U, 2: segment 2, 3: W of step t+1
+#pragma unroll 1
+        while (true) {
+          int i0, n;
+          if (ph == 0) { i0 = 0; n = nw; }
+          else if (ph == 1) { i0 = nw; n = nu; }
+          else if (ph == 2) { i0 = nw + nu; n = n2; }
+          else { i0 = 0; n = (p.has_s1w && t + 1 < T) ? nw : 0; }
+#pragma unroll 1
+          for (int i = i0; i < i0 + n; ++i) {
+            const uint32_t e = reinterpret_cast<const volatile uint32_t*>(smem + sp.ctab)[i];
+            const uint32_t bytes = (e >> 16) << 8;
+            if (use > 0) mbar_wait(bar(BAR_W_EMPTY + slot), (use - 1u) & 1u);
+            mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
+            bulk_g2s(sbase + sp.w + (uint32_t)slot * kSlotBytes, p.wimg + ((size_t)(e & 0xFFFFu) << 8), bytes, bar(BAR_W_FULL + slot));
+            if (++slot == ns) { slot = 0; ++use; }
+          }
+          if (ph == 0) ph = 1;
+          else if (ph == 1) { if (t == T) break; ph = 2; }
+          else if (ph == 2) ph = 3;
+          else { if (++t >= n_steps) break; ph = 1; }
         }
       }
     }
@@ -450,16 +477,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     if (lane == 0) {
       const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
       uint8_t* out = p.store_h ? p.out_seq + (size_t)cta * T * h_tile : nullptr;
-      auto load_step = [&](int tl) {
-        const int s = tl % nst;
-        const uint32_t n = (uint32_t)(tl / nst);
-        if (n > 0) mbar_wait(bar(BAR_IN_EMPTY + s), (n - 1u) & 1u);
-        mbar_expect_tx(bar(BAR_IN_FULL + s), in_tile);
-        bulk_g2s(sbase + sp.inbuf + s * in_tile, src + (size_t)tl * in_tile, in_tile, bar(BAR_IN_FULL + s));
+      int ld_s = 0;          // ring stage of the next tile to load
+      uint32_t ld_n = 0;     // how many times that stage has been used
+      int ld_t = 0;          // step index of the next tile to load
+      auto load_next = [&]() {
+        if (ld_n > 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
+        mbar_expect_tx(bar(BAR_IN_FULL + ld_s), in_tile);
+        bulk_g2s(sbase + sp.inbuf + ld_s * in_tile, src + (size_t)ld_t * in_tile, in_tile, bar(BAR_IN_FULL + ld_s));
+        ++ld_t;
+        if (++ld_s == nst) { ld_s = 0; ++ld_n; }
       };
-      for (int tl = 0; tl < nst - 1 && tl < T; ++tl) load_step(tl);
+#pragma unroll 1
+      for (int tl = 0; tl < nst - 1 && tl < T; ++tl) load_next();
+#pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        if (t + nst - 1 < T) load_step(t + nst - 1);
+        if (ld_t < T) load_next();
         if (p.store_h) {
           // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
           mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     const uint32_t h_lo0 = desc_lo(sbase + sp.hbuf, kActLBO), t_lo0 = desc_lo(sbase + sp.tbuf, kActLBO);
     const uint32_t in_lo0 = desc_lo(sbase + sp.inbuf, kActLBO), in_stage_lo = in_tile >> 4;
     const uint32_t w_lo0 = desc_lo(sbase + sp.w, 128u);
-    const uint32_t streaming = (uint32_t)p.streaming;
+    constexpr bool streaming = STREAM;
     const uint32_t a_hi64 = desc_hi(1024u);   // kc = 64 chunks
     int w_slot = 0;
     uint32_t w_use = 0;
@@ -492,18 +524,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     uint32_t a_lo = w_lo0;   // descriptor word of the next chunk (resident: walks the image; streaming: walks the ring)
     if (!streaming) mbar_wait(bar(BAR_W_FULL), 0);
     // one weight chunk = NM <= 4 MMAs (K = 16 each): A = chunk (K-major, SBO = 256*NM), B = activation rows
+    // remainder chunk (K extent not a multiple of 64): nm < 4 single MMAs
     auto chunk = [&](int nm, uint32_t bytes, uint32_t a_hi, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
       TC_CHUNK_STAMP();
       if (streaming) {
         mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
         tc_fence_after();
       }
-      switch (nm) {
-        case 4: umma_f16_x<4>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        case 3: umma_f16_x<3>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        case 2: umma_f16_x<2>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        default: umma_f16_x<1>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-      }
+#pragma unroll 1
+      for (int k = 0; k < nm; ++k)
+        umma_f16_x<1>(d_tmem, a_lo + 16u * (uint32_t)k, a_hi, b_lo + 64u * (uint32_t)k, act_hi, idesc, k > 0 ? 1u : first_accumulates, elected);
       if (streaming) {
         umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
         a_lo += kSlotBytes >> 4;
@@ -655,12 +685,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       for (int g = 0; g < 4; ++g) bi[u][g] = p.bias[(u * 4 + g) * 128 + row];
     const int b_first = cta * kN + c0;         // global sequence index of this thread's first column
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
+    // Dense-top row owned by this thread (if any): its S1u row index is ru + o
+    int y_r0 = -1, y_o = 0;
+    float y_bias = 0.f;
+    for (int o = 0; o < p.n_dense; ++o)
+      if (((p.ru + o) & 127) == row) { y_r0 = (p.ru + o) & ~127; y_o = o; y_bias = p.dense_bias[o]; }
     uint32_t s2_use = 0;
     for (int t = 0; t < n_steps; ++t) {
       // ---- epilogue 1: t_u / t_w accumulators -> f16 rows of the S2 B operand; Dense-top rows -> y(t-1) ----
       mbar_wait(bar(BAR_S1_FULL), (uint32_t)t & 1u);
       tc_fence_after();
       if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
+      float yv[16];
       {
         // both accumulator sets are fetched before the single wait: a TMEM load costs ~500 cycles of latency here
         uint32_t au[16], aw[16];
@@ -677,24 +713,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           const int j = r0 + row;
           if (do_u) {
             if (j < p.ru_pad && t < T) store_t_row(smem + sp.tbuf + act_offset(j, c0), au, j < p.ru);
-            if (t > 0 && j >= p.ru && j < e1_rows_u) {
-              const int o = j - p.ru;
-              const float db = p.dense_bias[o];
+            if (r0 == y_r0) {   // keep the Dense-top row; it is written out after the t operand has been published
 #pragma unroll
-              for (int n = 0; n < 16; ++n)
-                if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + o] = __uint_as_float(au[n]) + db;
+              for (int n = 0; n < 16; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
             }
           }
           if (do_w && j < p.rw_pad) store_t_row(smem + sp.tbuf + act_offset(p.ru_pad + j, c0), aw, j < p.rw);
         }
       }
+      if (t < T) {
+        if (threadIdx.x == 128) TC_STAMP(1);   // EPI: t rows stored
+        tc_fence_before();
+        fence_proxy_async();
+        if (threadIdx.x == 128) TC_STAMP(6);   // EPI: proxy fence done
+        mbar_arrive(bar(BAR_T_READY));
+        if (threadIdx.x == 128) TC_STAMP(9);   // EPI: t operand written + arrived
+      }
+      if (t > 0 && y_r0 >= 0) {   // Dense top of step t-1 (off the critical path: after the arrive)
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+          if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + y_o] = yv[n];
+      }
       if (t == T) break;
-      if (threadIdx.x == 128) TC_STAMP(1);   // EPI: t rows stored
-      tc_fence_before();
-      fence_proxy_async();
-      if (threadIdx.x == 128) TC_STAMP(6);   // EPI: proxy fence done
-      mbar_arrive(bar(BAR_T_READY));
-      if (threadIdx.x == 128) TC_STAMP(9);   // EPI: t operand written + arrived
 
       // ---- epilogue 2: gates + cell update per unit block ------------------------------------------
       // the h(t-1) tile must have been copied out before it is overwritten
@@ -756,13 +796,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 // ------------------------------------------------------------------------------------------------
 // packing / layout kernels (run once per weight update, or once per forward for the sequences)
 // ------------------------------------------------------------------------------------------------
-struct PackChunk {
-  uint32_t byte_off;   // offset of the chunk inside the weight stream image
-  int16_t seg;         // 0 = W (A1w), 1 = U (A1u), 2 = A2
-  int16_t rows, kc;    // chunk extent (rows multiple of 8, kc multiple of 16)
-  int16_t r0, k0;      // seg 0/1: first row / first K;  seg 2: k0 = first K of the part
-  int16_t ub, g, part; // seg 2
-};
 
 // effective right-factor element of a block: row kk of the (rank x 4H) matrix, gate column n
 __device__ __forceinline__ float block_right(const Block& b, int kk, int n) {
@@ -876,6 +909,7 @@ __global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T,
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcLayerImg {
+  PackChunk* chunks = nullptr;
   uint8_t* wimg = nullptr;
   float* bias = nullptr;
   TcLayerParams prm;
@@ -888,20 +922,18 @@ struct TcState {
   size_t seq_bytes[2] = {0, 0};
   uint8_t* xseq = nullptr;
   size_t xseq_bytes = 0;
-  PackChunk* chunk_buf = nullptr;
-  size_t chunk_cap = 0;
 };
 
 void tc_free(TcState* s) {
   if (!s) return;
   for (int l = 0; l < kMaxLayers; ++l) {
     if (s->layers[l].wimg) cudaFree(s->layers[l].wimg);
+    if (s->layers[l].chunks) cudaFree(s->layers[l].chunks);
     if (s->layers[l].bias) cudaFree(s->layers[l].bias);
   }
   for (int i = 0; i < 2; ++i)
     if (s->seq[i]) cudaFree(s->seq[i]);
   if (s->xseq) cudaFree(s->xseq);
-  if (s->chunk_buf) cudaFree(s->chunk_buf);
   delete s;
 }
 
@@ -938,9 +970,10 @@ static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const 
     p.rows_w = round_up(bw.rank, 8);
   }
   p.segw_bytes = p.segu_bytes = p.seg2_bytes = 0;
-  if (p.has_s1w) for_seg_w(p, [&](uint32_t b, int, int, int) { p.segw_bytes += b; });
-  for_seg_u(p, [&](uint32_t b, int, int, int, int) { p.segu_bytes += b; });
-  for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { p.seg2_bytes += b; });
+  p.n_chunks_w = p.n_chunks_u = p.n_chunks_2 = 0;
+  if (p.has_s1w) for_seg_w(p, [&](uint32_t b, int, int, int) { p.segw_bytes += b; ++p.n_chunks_w; });
+  for_seg_u(p, [&](uint32_t b, int, int, int, int) { p.segu_bytes += b; ++p.n_chunks_u; });
+  for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { p.seg2_bytes += b; ++p.n_chunks_2; });
   // resident if the whole stream fits next to the activation buffers, else a ring of 16 KB slots
   p.streaming = 0;
   p.w_slots = 1;
@@ -1004,20 +1037,18 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
         chunks.push_back(PackChunk{off, 2, 128, (int16_t)kc, 0, (int16_t)k0, (int16_t)ub, (int16_t)g, (int16_t)part});
         off += b;
       });
-      if (st->chunk_cap < chunks.size()) {
-        if (st->chunk_buf) {
-          SVD_CUDA_TRY(cudaStreamSynchronize(stream));
-          cudaFree(st->chunk_buf);
-        }
-        SVD_CUDA_TRY(cudaMalloc(&st->chunk_buf, sizeof(PackChunk) * chunks.size()));
-        st->chunk_cap = chunks.size();
+      if (li.chunks) {
+        SVD_CUDA_TRY(cudaStreamSynchronize(stream));   // a previous forward may still be streaming from the old table
+        cudaFree(li.chunks);
+        li.chunks = nullptr;
       }
-      // pageable source: the copy is staged before the call returns, so `chunks` may die afterwards;
-      // the sync keeps the shared table buffer from being overwritten while a previous layer's packer reads it
-      SVD_CUDA_TRY(cudaStreamSynchronize(stream));
-      SVD_CUDA_TRY(cudaMemcpyAsync(st->chunk_buf, chunks.data(), sizeof(PackChunk) * chunks.size(), cudaMemcpyHostToDevice, stream));
+      SVD_CUDA_TRY(cudaMalloc(&li.chunks, sizeof(PackChunk) * chunks.size()));
+      // pageable source: the copy is staged before the call returns, so `chunks` may die afterwards
+      SVD_CUDA_TRY(cudaMemcpyAsync(li.chunks, chunks.data(), sizeof(PackChunk) * chunks.size(), cudaMemcpyHostToDevice, stream));
+      p.chunks = li.chunks;
+      SVD_REQUIRE((int)chunks.size() == p.n_chunks_w + p.n_chunks_u + p.n_chunks_2, "tensor-core engine: chunk table mismatch");
       const LayerDesc& Ld = md.layers[l];
-      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(st->chunk_buf, Ld.blocks[0], Ld.blocks[1], p.H, Ld.d_in, p.ru_pad,
+      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, Ld.blocks[0], Ld.blocks[1], p.H, Ld.d_in, p.ru_pad,
                                                                        md.dense_kernel, p.n_dense, md.n_out,
                                                                        reinterpret_cast<__half*>(li.wimg));
       pack_bias_kernel<<<(4 * p.H + 255) / 256, 256, 0, stream>>>(Ld.bias, p.H, li.bias);
@@ -1071,20 +1102,27 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     p.y = a.y;
     p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
-    switch (p.H / 128) {
-#define SVD_TC_LAUNCH(NUB_)                                                                                                          \
-  case NUB_:                                                                                                                         \
-    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));      \
-    lstm_tc_layer_kernel<NUB_><<<n_cta, kTcThreads, sp.total, stream>>>(p);                                                          \
-    break;
-      SVD_TC_LAUNCH(1)
-      SVD_TC_LAUNCH(2)
-      SVD_TC_LAUNCH(3)
-      SVD_TC_LAUNCH(4)
+    bool launched = true;
+#define SVD_TC_LAUNCH(NUB_, STREAM_)                                                                                               \
+  do {                                                                                                                              \
+    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB_, STREAM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
+    lstm_tc_layer_kernel<NUB_, STREAM_><<<n_cta, kTcThreads, sp.total, stream>>>(p);                                                \
+  } while (0)
+    switch ((p.H / 128) * 2 + (p.streaming ? 1 : 0)) {
+      case 2: SVD_TC_LAUNCH(1, false); break;
+      case 3: SVD_TC_LAUNCH(1, true); break;
+      case 4: SVD_TC_LAUNCH(2, false); break;
+      case 5: SVD_TC_LAUNCH(2, true); break;
+      case 6: SVD_TC_LAUNCH(3, false); break;
+      case 7: SVD_TC_LAUNCH(3, true); break;
+      case 8: SVD_TC_LAUNCH(4, false); break;
+      case 9: SVD_TC_LAUNCH(4, true); break;
+      default: launched = false;
+    }
 #undef SVD_TC_LAUNCH
-      default:
-        set_error("tensor-core engine: unsupported units %d", p.H);
-        return -1;
+    if (!launched) {
+      set_error("tensor-core engine: unsupported units %d", p.H);
+      return -1;
     }
     ++nl;
   }
