@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rank", type=int, default=128)
@@ -78,48 +78,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe):
+    one background `nvidia-smi -lms 50` process, started before and killed after the timed loops."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
+        self.t_start = None
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)    # let the first sample land before the timed region starts
+        except Exception:
+            self.proc = None
+
+    def mark(self):
+        """Call right before the timed region: samples taken earlier are dropped."""
+        self.t_start = time.time()
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        lines = []
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
             try:
-                sm.append(float(s[0]))
-                mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[3:7]):
+                out, _ = self.proc.communicate(timeout=5)
+                lines = [l for l in out.splitlines() if l.strip()]
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons, pw = [], 0.0, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                pw.append(float(f[2]))
+                for n, v in zip(names, f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        # the GPU is idle before mark(): keep the samples taken under load (upper half by power draw) for the median
+        if len(sm) >= 4:
+            order = np.argsort(pw)[len(pw) // 2:]
+            sm_load = [sm[i] for i in order]
+        else:
+            sm_load = sm
+        return {"sm_mhz": float(np.median(sm_load)) if sm_load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def build_workload(a, svdlstm):
@@ -282,7 +293,6 @@ def main():
     t1.record()
     barrier()
     launches = svdlstm.launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = t0.elapsed_time(t1)
     kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))
     tt = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
@@ -313,6 +323,7 @@ def main():
         e2e = {"value": world * B * T / (e2e_ms * 1e-3), "unit": "sequence-timesteps/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4)}
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

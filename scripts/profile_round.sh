@@ -1,0 +1,19 @@
+#!/bin/bash
+# Profiling pass of one round (run on the GPU box through gpurun):  bash scripts/profile_round.sh r01
+# 1) launch list of the default bench command (shares of the step), 2) ncu --set full of the tensor-core layer kernel at
+# rank 128 (streamed) and rank 32 (resident), 3) ncu --set full of the batch-1 wavefront kernel.
+# Every ncu run is preceded by the identical plain command (B200_PROFILING.md rule).
+R=${1:-r01}
+O=gpurun_out
+BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep"
+$BENCH > $O/plain_bench_$R.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 12000 --csv --log-file $O/launches_$R.csv $BENCH > $O/ncu_bench_$R.log 2>&1
+for rk in 128 32; do
+  CMD="python scripts/tc_time.py $rk 4096 128"
+  $CMD > $O/plain_tc_$rk.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:lstm_tc_layer_kernel -s 2 -c 2 -f -o $O/tc_layer_rank${rk}_$R $CMD > $O/ncu_tc_$rk.log 2>&1
+done
+CMD="python scripts/prof_batch1.py"
+$CMD > $O/plain_b1.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:lstm_wavefront_kernel -s 1 -c 1 -f -o $O/b1_wavefront_$R $CMD > $O/ncu_b1.log 2>&1
+for f in $O/plain_tc_128.log $O/plain_tc_32.log $O/plain_b1.log; do tail -n 2 $f; done
