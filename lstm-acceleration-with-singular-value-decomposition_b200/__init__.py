@@ -15,7 +15,8 @@ from .models import (Sequential, full_model_from_weights, make_LSTM_reduced_mode
                      make_split_LSTM_singular_model, reduce_factors, svd_batched, truncate_singular_model)
 from .metrics import (count_weights, full_weight_count, reduced_merged_weight_count, reduced_split_weight_count,
                       reference_rmse, rmse, signaltonoise, sweep_sse, weight_reduction_percent)
-from .rank_reduce import get_model_singular_values, reduce_matrix_rank, reduce_two_step, set_model_matrix_rank
+from .rank_reduce import (LSTM_wrapper, get_model_singular_values, reduce_matrix_rank, reduce_two_step,
+                          set_model_matrix_rank, sorted_sigma_indices)
 from .sweep import build_rank_models, rank_sweep, shard_bounds
 from .weights_io import (load_model_weights_csv, load_model_weights_npz, save_model_weights_csv, synthetic_layers)
 

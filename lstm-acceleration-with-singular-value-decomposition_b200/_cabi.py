@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvdlstm.so")
+LIB_PATH = os.environ.get("SVDLSTM_LIB") or os.path.join(_HERE, "libsvdlstm.so")   # SVDLSTM_LIB: e.g. the timeline debug build
 
 RETURN_SEQUENCES = 1
 GO_BACKWARDS = 2

@@ -18,8 +18,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["abi.cu", "k1_general.cu", "k1_wavefront.cu", "k1b_tc.cu", "k2_svd.cu", "k3_penalties.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-if os.environ.get("SVDLSTM_TC_TIMELINE_BUILD"):   # debug build: per-step clock64 stamps inside the tensor-core kernel
+if os.environ.get("SVDLSTM_TC_TIMELINE_BUILD"):   # debug build (separate .so): per-step clock64 stamps inside the tensor-core kernel
     FLAGS.append("-DSVDLSTM_TC_TIMELINE")
+    BUILD = os.path.join(HERE, "build_dbg")
+    LIB = os.path.join(HERE, "libsvdlstm_dbg.so")   # load it with SVDLSTM_LIB=<path>
 
 
 def _deps_mtime():

@@ -524,6 +524,30 @@ def set_model_matrix_rank(model: Model, index, rank):
     return model
 
 
+def greedy_sigma_sweep(model: Model, X, y, reductions, skip_first_layer_W=False):
+    """old_versions/svd_acceleration.py:61-88 (== LSTM_wrapper.iterate_reduce_model, svd_classes.py:139-182)
+    without a scaler: global ascending sigma order, per iteration predict -> RMSE (sqrt of the mean over
+    sequences of the per-sequence MSE), then lower the rank of the gate block owning the next-smallest sigma."""
+    sv = get_model_singular_values(model)
+    units = sv.shape[-1]
+    idx = np.squeeze(np.dstack(np.unravel_index(np.argsort(sv.ravel(), kind="stable"), sv.shape)))
+    if skip_first_layer_W:
+        idx = idx[~np.logical_and(idx[:, 0] == 0, idx[:, 1] == 0)]
+    ranks = np.full(sv.shape[:3], units)
+    rmse_out, weights = np.zeros(reductions), np.zeros(reductions)
+    running = 0
+    yt = np.asarray(y, np.float64).reshape(np.shape(y)[0], -1)
+    for i in range(reductions):
+        yp = np.asarray(model.predict(X), np.float64).reshape(yt.shape)
+        rmse_out[i] = np.sqrt(np.mean(np.mean((yt - yp) ** 2, axis=1)))
+        weights[i] = running
+        ci, mi, gi = (int(v) for v in idx[i][:3])
+        ranks[ci, mi, gi] -= 1
+        set_model_matrix_rank(model, (ci, mi, gi), int(ranks[ci, mi, gi]))
+        running += 2 * units - 2 * int(ranks[ci, mi, gi]) - 1
+    return rmse_out, weights
+
+
 # --------------------------------------------------------------------------------------
 # fixture I/O: the shipped code/model_weights layout (transposed, SURVEY fact 8)
 # --------------------------------------------------------------------------------------

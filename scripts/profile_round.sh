@@ -5,9 +5,9 @@
 # Every ncu run is preceded by the identical plain command (B200_PROFILING.md rule).
 R=${1:-r01}
 O=gpurun_out
-BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep"
+BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-batch1"
 $BENCH > $O/plain_bench_$R.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 12000 --csv --log-file $O/launches_$R.csv $BENCH > $O/ncu_bench_$R.log 2>&1
+ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $O/launches_$R.csv $BENCH > $O/ncu_bench_$R.log 2>&1
 for rk in 128 32; do
   CMD="python scripts/tc_time.py $rk 4096 128"
   $CMD > $O/plain_tc_$rk.log 2>&1 && \

@@ -200,6 +200,30 @@ def test_old_explicit_rank_api(oracle, dropbear_weights, kat):
     assert np.linalg.matrix_rank(full.layers[0].get_weights()[1][:, 30:45].astype(np.float64), tol=1e-4) == 9
 
 
+def test_greedy_sigma_sweep_matches_oracle(oracle, dropbear_weights):
+    """LSTM_wrapper.iterate_reduce_model (old_versions/svd_classes.py:139-182; loop of
+    old_versions/svd_acceleration.py:61-88) on device == the oracle's restatement, iteration by iteration."""
+    layers, dense = dropbear_weights
+    sub = [layers[1], layers[2]]                       # square layers, as the old sweep assumes
+    x = np.random.default_rng(12).standard_normal((3, 40, 15)).astype(np.float32)
+    om_full = oracle.model_from_weights([tuple(a.copy() for a in l) for l in sub], dense)
+    y = om_full.predict(x)                             # target = full-model output (RMSE ratio plot semantics)
+    n_it = 12
+    ref_rmse, ref_w = oracle.greedy_sigma_sweep(om_full, x, y, n_it)
+    wrap = svdlstm.LSTM_wrapper(svdlstm.full_model_from_weights(sub, dense))
+    rmse, w, done = wrap.iterate_reduce_model(x, y.astype(np.float32), reductions=n_it)
+    assert done == n_it and rmse.shape == (n_it,)
+    assert rmse[0] < 1e-6                              # nothing removed yet: the model reproduces its own output
+    assert np.array_equal(w, ref_w)
+    assert np.max(np.abs(rmse - ref_rmse)) < 2e-5 + 1e-4 * np.max(ref_rmse)
+    assert np.all(np.diff(w) > 0)
+    order = svdlstm.sorted_sigma_indices(wrap.model_singular_values)
+    assert order.shape == (2 * 2 * 4 * 15, 4)
+    sv = wrap.model_singular_values
+    assert np.all(np.diff(sv[tuple(order.T)]) >= 0)    # ascending global order
+    assert int(wrap.model_ranks.sum()) == 2 * 2 * 4 * 15 - n_it
+
+
 def test_weight_counts_device_models(dropbear_weights):
     layers, dense = dropbear_weights
     full = svdlstm.full_model_from_weights(layers, dense)

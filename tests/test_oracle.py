@@ -168,3 +168,17 @@ def test_oracle_float32_close_to_float64(oracle, dropbear_weights):
     y64 = oracle.model_from_weights(layers, dense, dtype=np.float64).predict(x)
     y32 = oracle.model_from_weights(layers, dense, dtype=np.float32).predict(x)
     assert np.max(np.abs(y64 - y32)) < 2e-5
+
+
+def test_greedy_sigma_sweep_oracle(oracle, dropbear_weights):
+    """old_versions/svd_acceleration.py:61-88: the first evaluation happens before anything is removed (RMSE 0 against
+    the model's own output), weights eliminated follow 2n-2r-1 (:86), and the error grows as sigmas are dropped."""
+    layers, dense = dropbear_weights
+    sub = [tuple(a.copy() for a in l) for l in (layers[1], layers[2])]
+    om = oracle.model_from_weights(sub, dense)
+    x = np.random.default_rng(3).standard_normal((2, 25, 15)).astype(np.float32)
+    y = om.predict(x)
+    rmse, w = oracle.greedy_sigma_sweep(om, x, y, 8)
+    assert rmse[0] < 1e-12 and rmse[-1] > rmse[1] > 0
+    assert list(w[:3]) == [0.0, 2 * 15 - 2 * 14 - 1, (2 * 15 - 2 * 14 - 1) * 2] or w[2] in (2.0, 4.0)
+    assert np.all(np.diff(w) > 0)
