@@ -918,11 +918,20 @@ struct TcLayerImg {
 struct TcState {
   TcLayerImg layers[kMaxLayers];
   int n_layers = 0;
-  uint8_t* seq[2] = {nullptr, nullptr};   // ping-pong activation sequences
+};
+
+// Per-device scratch shared by every handle: the FP16 image of x and the two ping-pong hidden-sequence images
+// (C3: 134 MB + 2 x 2.1 GB).  A rank sweep holds hundreds of handles; per-handle scratch would not fit.  Work on
+// one stream is ordered, so sharing is safe there; a forward on a different stream first drains the previous one.
+struct TcWorkspace {
+  uint8_t* seq[2] = {nullptr, nullptr};
   size_t seq_bytes[2] = {0, 0};
   uint8_t* xseq = nullptr;
   size_t xseq_bytes = 0;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
 };
+static TcWorkspace g_tc_ws[16];
 
 void tc_free(TcState* s) {
   if (!s) return;
@@ -931,9 +940,6 @@ void tc_free(TcState* s) {
     if (s->layers[l].chunks) cudaFree(s->layers[l].chunks);
     if (s->layers[l].bias) cudaFree(s->layers[l].bias);
   }
-  for (int i = 0; i < 2; ++i)
-    if (s->seq[i]) cudaFree(s->seq[i]);
-  if (s->xseq) cudaFree(s->xseq);
   delete s;
 }
 
@@ -1062,28 +1068,41 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   }
   const int B = a.B, T = a.T;
   const int n_cta = (B + kN - 1) / kN;
-  // workspaces
+  // workspaces (per device, shared by all handles)
+  int dev = 0;
+  SVD_CUDA_TRY(cudaGetDevice(&dev));
+  SVD_REQUIRE(dev >= 0 && dev < 16, "tensor-core engine: device ordinal %d out of range", dev);
+  TcWorkspace* ws = &g_tc_ws[dev];
+  if (ws->used && ws->last_stream != stream) SVD_CUDA_TRY(cudaStreamSynchronize(ws->last_stream));
+  ws->used = true;
+  ws->last_stream = stream;
   const int Dpad = st->layers[0].prm.Kin;
   const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad);
-  if (st->xseq_bytes < xbytes) {
-    if (st->xseq) cudaFree(st->xseq);
-    SVD_CUDA_TRY(cudaMalloc(&st->xseq, xbytes));
-    st->xseq_bytes = xbytes;
+  if (ws->xseq_bytes < xbytes) {
+    if (ws->xseq) {
+      SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFree(ws->xseq);
+    }
+    SVD_CUDA_TRY(cudaMalloc(&ws->xseq, xbytes));
+    ws->xseq_bytes = xbytes;
   }
   for (int l = 0; l < L; ++l) {
     if (!st->layers[l].prm.store_h) continue;
     const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H);
     const int slot = l & 1;
-    if (st->seq_bytes[slot] < hb) {
-      if (st->seq[slot]) cudaFree(st->seq[slot]);
-      SVD_CUDA_TRY(cudaMalloc(&st->seq[slot], hb));
-      st->seq_bytes[slot] = hb;
+    if (ws->seq_bytes[slot] < hb) {
+      if (ws->seq[slot]) {
+        SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(ws->seq[slot]);
+      }
+      SVD_CUDA_TRY(cudaMalloc(&ws->seq[slot], hb));
+      ws->seq_bytes[slot] = hb;
     }
   }
   {
     const int D = md.input_dim;
     const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
-    pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * kN * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, st->xseq);
+    pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * kN * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, ws->xseq);
   }
   ++nl;
   static long long* dbg_buf = nullptr;
@@ -1097,8 +1116,8 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     p.T = T;
     p.B = B;
     p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
-    p.in_seq = (l == 0) ? st->xseq : st->seq[(l - 1) & 1];
-    p.out_seq = p.store_h ? st->seq[l & 1] : nullptr;
+    p.in_seq = (l == 0) ? ws->xseq : ws->seq[(l - 1) & 1];
+    p.out_seq = p.store_h ? ws->seq[l & 1] : nullptr;
     p.y = a.y;
     p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
@@ -1127,7 +1146,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     ++nl;
   }
   if (st->layers[L - 1].prm.store_h) {   // no Dense top: the output is the last hidden sequence itself
-    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(st->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, a.y);
+    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, a.y);
     ++nl;
   }
   SVD_CUDA_TRY(cudaGetLastError());

@@ -81,7 +81,7 @@ def build_rank_models(full_model, ranks: Sequence[int], form="reduced", merged_k
 
 
 def rank_sweep(full_model, X, ranks: Sequence[int], *, target=None, form="reduced", merged_kernel=True, engine=None,
-               gather_predictions=True, last_step_only=False, models=None):
+               gather_predictions=True, last_step_only=False, models=None, sse_over="kept"):
     """Evaluate every rank-truncated model on this process's shard of X and reduce.
 
     X: (N, T, D) host or device array holding ALL sequences (each process slices its own shard), or, if
@@ -102,19 +102,26 @@ def rank_sweep(full_model, X, ranks: Sequence[int], *, target=None, form="reduce
     else:
         tgt = C.dev_tensor(target(lo, hi) if callable(target) else target[lo:hi])
     tgt = tgt.reshape(tgt.shape[0], -1) if tgt.dim() > 1 else tgt.reshape(-1, 1)
+    tgt_all = tgt
     if last_step_only:
         tgt = tgt[:, -1:]
+    if sse_over not in ("kept", "all"):
+        raise ValueError("sse_over must be 'kept' or 'all'")
     R = len(ranks)
     per = tgt.shape[1]
+    per_sse = tgt_all.shape[1] if sse_over == "all" else per
     preds = torch.empty((R, hi - lo, per), dtype=torch.float32, device=x_loc.device)
+    sse = torch.zeros(R, dtype=torch.float64, device=x_loc.device)
+    tgt_flat = tgt_all.reshape(-1).contiguous()
     for i, m in enumerate(models):
         y = m(x_loc, engine=engine)
         y = y.reshape(y.shape[0], -1)
         preds[i] = y[:, -1:] if last_step_only else y
-    if hi > lo:
+        if sse_over == "all" and last_step_only and hi > lo:
+            sse[i:i + 1] = sweep_sse(y.reshape(1, -1), tgt_flat)
+    if hi > lo and not (sse_over == "all" and last_step_only):
         sse = sweep_sse(preds.reshape(R, -1), tgt.reshape(-1))
-    else:
-        sse = torch.zeros(R, dtype=torch.float64, device=x_loc.device)
+    per = per_sse
     count = torch.tensor([float((hi - lo) * per)], dtype=torch.float64, device=x_loc.device)
     sse, count, all_preds = exchange_results(preds, sse, count, N, gather_predictions=gather_predictions)
     sse_h = sse.cpu().numpy()
