@@ -227,19 +227,16 @@ __host__ __device__ inline uint32_t act_offset(int k, int n) {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
-// 16 fp32 accumulator columns of one row -> f16, two 16-byte stores into an MN-major activation tile
-__device__ __forceinline__ void store_t_row(uint8_t* dst, const uint32_t* r, bool live) {
-  uint4 v0, v1;
-  v0.x = live ? pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) : 0u;
-  v0.y = live ? pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) : 0u;
-  v0.z = live ? pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) : 0u;
-  v0.w = live ? pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) : 0u;
-  v1.x = live ? pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) : 0u;
-  v1.y = live ? pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) : 0u;
-  v1.z = live ? pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) : 0u;
-  v1.w = live ? pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) : 0u;
-  *reinterpret_cast<uint4*>(dst) = v0;
-  *reinterpret_cast<uint4*>(dst + 128) = v1;
+// 16 fp32 accumulator columns of one row -> f16, two 16-byte stores into an MN-major activation tile (shared-space address)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void store_t_row(uint32_t saddr, const uint32_t* r, bool live) {
+  const uint32_t m = live ? 0xFFFFFFFFu : 0u;   // padding rows (rank..rank_pad) must hold zeros
+  sts128(saddr, pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) & m, pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) & m,
+         pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) & m, pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) & m);
+  sts128(saddr + 128u, pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) & m, pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) & m,
+         pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) & m, pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) & m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,12 +681,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 #pragma unroll
       for (int g = 0; g < 4; ++g) bi[u][g] = p.bias[(u * 4 + g) * 128 + row];
     const int b_first = cta * kN + c0;         // global sequence index of this thread's first column
+    // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
+    uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0;
+    int e1_tiles = 0;
+    for (int mt = 0; mt < 3; ++mt) {
+      const int r0 = mt * 128, j = r0 + row;
+      if (r0 < p.rows_u && r0 + q * 32 < e1_rows_u) { u_ld |= 1u << mt; e1_tiles = mt + 1; }   // warp-uniform
+      if (j < p.ru_pad) u_st |= 1u << mt;
+      if (j < p.ru) u_live |= 1u << mt;
+      if (p.has_s1w && r0 < p.rows_w && r0 + q * 32 < p.rw_pad) { w_ld |= 1u << mt; e1_tiles = mt + 1; }
+      if (j < p.rw_pad) w_st |= 1u << mt;
+      if (j < p.rw) w_live |= 1u << mt;
+    }
+    const uint32_t tb_u = sbase + sp.tbuf + act_offset(row, c0);                  // + 8192 per 128-row tile
+    const uint32_t tb_w = tb_u + (uint32_t)(p.ru_pad >> 3) * 512u;
+    const uint32_t tm_u = tm_s1u + lane_addr, tm_w = tm_s1w + lane_addr;          // + 32 columns per tile
+    const uint32_t hb_addr = sbase + sp.hbuf + act_offset(row, c0);               // + 8192 per 128-unit block
     // Dense-top row owned by this thread (if any): its S1u row index is ru + o
-    int y_r0 = -1, y_o = 0;
+    int y_mt = -1, y_o = 0;
     float y_bias = 0.f;
     for (int o = 0; o < p.n_dense; ++o)
-      if (((p.ru + o) & 127) == row) { y_r0 = (p.ru + o) & ~127; y_o = o; y_bias = p.dense_bias[o]; }
+      if (((p.ru + o) & 127) == row) { y_mt = (p.ru + o) >> 7; y_o = o; y_bias = p.dense_bias[o]; }
+    float* y_ptr = (p.n_dense > 0 && y_mt >= 0) ? p.y + (size_t)b_first * T * p.n_dense + y_o : nullptr;   // + t*n_dense, + n*T*n_dense
+    const int y_valid = p.B - b_first < 16 ? (p.B - b_first < 0 ? 0 : p.B - b_first) : 16;
+    const size_t y_seq_stride = (size_t)T * p.n_dense;
     uint32_t s2_use = 0;
     for (int t = 0; t < n_steps; ++t) {
       // ---- epilogue 1: t_u / t_w accumulators -> f16 rows of the S2 B operand; Dense-top rows -> y(t-1) ----
@@ -698,27 +714,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
       float yv[16];
       {
-        // both accumulator sets are fetched before the single wait: a TMEM load costs ~500 cycles of latency here
+        // both accumulator sets are fetched before the single wait: a TMEM load has a few hundred cycles of latency here
         uint32_t au[16], aw[16];
-        const int rows_max = p.rows_u > p.rows_w ? p.rows_u : p.rows_w;
+        const bool step_live = t < T;   // the flush pass (t == T) only extracts the Dense-top row
 #pragma unroll 1
-        for (int r0 = 0; r0 < rows_max; r0 += 128) {
-          const bool do_u = r0 + q * 32 < e1_rows_u;                              // warp-uniform: a live row in this quarter
-          const bool do_w = p.has_s1w && t < T && r0 + q * 32 < p.rw_pad;
-          if (!do_u && !do_w) break;
-          if (do_u) tmem_ld16(tm_s1u + (uint32_t)(r0 >> 7) * 32u + lane_addr, au);
-          if (do_w) tmem_ld16(tm_s1w + (uint32_t)(r0 >> 7) * 32u + lane_addr, aw);
+        for (int mt = 0; mt < e1_tiles; ++mt) {
+          const bool do_u = (u_ld >> mt) & 1u, do_w = ((w_ld >> mt) & 1u) && step_live;
+          if (do_u) tmem_ld16(tm_u + (uint32_t)mt * 32u, au);
+          if (do_w) tmem_ld16(tm_w + (uint32_t)mt * 32u, aw);
           tmem_ld_wait();
           if (threadIdx.x == 128) TC_STAMP(0);   // EPI: S1 accumulator tiles in registers
-          const int j = r0 + row;
           if (do_u) {
-            if (j < p.ru_pad && t < T) store_t_row(smem + sp.tbuf + act_offset(j, c0), au, j < p.ru);
-            if (r0 == y_r0) {   // keep the Dense-top row; it is written out after the t operand has been published
+            if (((u_st >> mt) & 1u) && step_live) store_t_row(tb_u + (uint32_t)mt * 8192u, au, (u_live >> mt) & 1u);
+            if (mt == y_mt) {   // keep the Dense-top row; it is written out after the t operand has been published
 #pragma unroll
               for (int n = 0; n < 16; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
             }
           }
-          if (do_w && j < p.rw_pad) store_t_row(smem + sp.tbuf + act_offset(p.ru_pad + j, c0), aw, j < p.rw);
+          if (do_w && ((w_st >> mt) & 1u)) store_t_row(tb_w + (uint32_t)mt * 8192u, aw, (w_live >> mt) & 1u);
         }
       }
       if (t < T) {
@@ -729,10 +742,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
         mbar_arrive(bar(BAR_T_READY));
         if (threadIdx.x == 128) TC_STAMP(9);   // EPI: t operand written + arrived
       }
-      if (t > 0 && y_r0 >= 0) {   // Dense top of step t-1 (off the critical path: after the arrive)
+      if (t > 0 && y_ptr != nullptr) {   // Dense top of step t-1 (off the critical path: after the arrive)
+        float* yp = y_ptr + (size_t)(t - 1) * p.n_dense;
 #pragma unroll
         for (int n = 0; n < 16; ++n)
-          if (b_first + n < p.B) p.y[((size_t)(b_first + n) * T + (t - 1)) * p.n_dense + y_o] = yv[n];
+          if (n < y_valid) yp[(size_t)n * y_seq_stride] = yv[n];
       }
       if (t == T) break;
 
@@ -768,14 +782,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
             cst[ub][n] = c;
             hv[n] = og * tanh_approx(c);
           }
-          uint4 v0, v1;
-          v0.x = pack_f16(hv[0], hv[1]);   v0.y = pack_f16(hv[2], hv[3]);
-          v0.z = pack_f16(hv[4], hv[5]);   v0.w = pack_f16(hv[6], hv[7]);
-          v1.x = pack_f16(hv[8], hv[9]);   v1.y = pack_f16(hv[10], hv[11]);
-          v1.z = pack_f16(hv[12], hv[13]); v1.w = pack_f16(hv[14], hv[15]);
-          uint8_t* dst = smem + sp.hbuf + act_offset(ub * 128 + row, c0);
-          *reinterpret_cast<uint4*>(dst) = v0;
-          *reinterpret_cast<uint4*>(dst + kActSBO) = v1;
+          sts128(hb_addr + (uint32_t)ub * 8192u, pack_f16(hv[0], hv[1]), pack_f16(hv[2], hv[3]), pack_f16(hv[4], hv[5]), pack_f16(hv[6], hv[7]));
+          sts128(hb_addr + (uint32_t)ub * 8192u + 128u, pack_f16(hv[8], hv[9]), pack_f16(hv[10], hv[11]), pack_f16(hv[12], hv[13]),
+                 pack_f16(hv[14], hv[15]));
           fence_proxy_async();
           mbar_arrive(bar(BAR_H_READY + ub));
           if (threadIdx.x == 128) TC_STAMP(11 + 2 * (ub & 1));   // EPI: block ub done
