@@ -10,7 +10,8 @@
 //   S1w: t_w[r_w x N]  = (L_w sigma_w)^T [r_w x Hin] . in(t)  [Hin x N]    (layers >= 1; issued one
 //                                                                           step early: no recurrence)
 //   S2 : z [4H x N]    = [R_u ; R_w]^T   [4H x K2]   . [t_u ; t_w | x(t)]  (layer 0: x enters S2 directly
-//                                                                           through the dense 16x4H W)
+//                                                                           through the dense 16x4H W);
+//        issued in two passes: the input part (t_w | x) BEFORE t_u is ready, the recurrent part after
 // Accumulators live in TMEM (S1: <= 5 x 32 columns; S2: two buffers of 4 gates x 32 columns, so the
 // gate/cell epilogue of one 128-unit block overlaps the MMAs of the next).  The weight factors are one
 // "weight stream": a fixed sequence of K-major 128-row chunks (<= 16 KB, <= 4 MMAs each) consumed in
@@ -172,6 +173,51 @@ __device__ __forceinline__ void umma_f16_x(uint32_t d_tmem, uint32_t alo, uint32
   if constexpr (NM == 4)
     asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) SVD_UMMA_NEXT(48, 192) "}\n" SVD_UMMA_OPERANDS);
 }
+// The 4 gate tiles of one unit block in ONE asm block (resident mode, one K chunk of NM MMAs per tile): gate g's
+// accumulator is D + 32 g columns, its weight chunk follows gate g-1's (+NM*4096 bytes), the B operand is shared.
+// All steps are immediates, so the 4*NM MMAs cost a few uniform instructions each and no branches.
+#define SVD_UMMA_G(goff_a, goff_d, koff_a, koff_b, PRED)                \
+  "add.u32 ta, %1, " #goff_a "+" #koff_a ";\n\t"                        \
+  "add.u32 tb, %3, " #koff_b ";\n\t"                                    \
+  "add.u32 td, %0, " #goff_d ";\n\t"                                    \
+  "mov.b64 da, {ta, %2};\n\t"                                           \
+  "mov.b64 db, {tb, %4};\n\t"                                           \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %5, " PRED ";\n\t"
+#define SVD_UMMA_G_HEAD                                                 \
+  "{\n\t"                                                               \
+  ".reg .pred p, q, one;\n\t"                                           \
+  ".reg .b64 da, db;\n\t"                                               \
+  ".reg .b32 ta, tb, td;\n\t"                                           \
+  "setp.ne.b32 q, %7, 0;\n\t"                                           \
+  "setp.ne.b32 p, %6, 0;\n\t"                                           \
+  "setp.eq.b32 one, 0, 0;\n\t"
+template <int NM>
+__device__ __forceinline__ void umma_f16_gates(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                               uint32_t first_accumulates, uint32_t elected) {
+  static_assert(NM >= 1 && NM <= 4, "1..4 MMAs per gate tile");
+  if constexpr (NM == 1)
+    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(256, 32, 0, 0, "p") SVD_UMMA_G(512, 64, 0, 0, "p")
+                 SVD_UMMA_G(768, 96, 0, 0, "p") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2)
+    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one")
+                 SVD_UMMA_G(512, 32, 0, 0, "p") SVD_UMMA_G(512, 32, 16, 64, "one")
+                 SVD_UMMA_G(1024, 64, 0, 0, "p") SVD_UMMA_G(1024, 64, 16, 64, "one")
+                 SVD_UMMA_G(1536, 96, 0, 0, "p") SVD_UMMA_G(1536, 96, 16, 64, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3)
+    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one")
+                 SVD_UMMA_G(768, 32, 0, 0, "p") SVD_UMMA_G(768, 32, 16, 64, "one") SVD_UMMA_G(768, 32, 32, 128, "one")
+                 SVD_UMMA_G(1536, 64, 0, 0, "p") SVD_UMMA_G(1536, 64, 16, 64, "one") SVD_UMMA_G(1536, 64, 32, 128, "one")
+                 SVD_UMMA_G(2304, 96, 0, 0, "p") SVD_UMMA_G(2304, 96, 16, 64, "one") SVD_UMMA_G(2304, 96, 32, 128, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4)
+    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one")
+                 SVD_UMMA_G(0, 0, 48, 192, "one")
+                 SVD_UMMA_G(1024, 32, 0, 0, "p") SVD_UMMA_G(1024, 32, 16, 64, "one") SVD_UMMA_G(1024, 32, 32, 128, "one")
+                 SVD_UMMA_G(1024, 32, 48, 192, "one")
+                 SVD_UMMA_G(2048, 64, 0, 0, "p") SVD_UMMA_G(2048, 64, 16, 64, "one") SVD_UMMA_G(2048, 64, 32, 128, "one")
+                 SVD_UMMA_G(2048, 64, 48, 192, "one")
+                 SVD_UMMA_G(3072, 96, 0, 0, "p") SVD_UMMA_G(3072, 96, 16, 64, "one") SVD_UMMA_G(3072, 96, 32, 128, "one")
+                 SVD_UMMA_G(3072, 96, 48, 192, "one") "}\n" SVD_UMMA_OPERANDS);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t elected) {
   asm volatile(
       "{\n\t"
@@ -301,6 +347,8 @@ enum {
   BAR_IN_EMPTY = BAR_IN_FULL + kInStagesMax,
   BAR_S1_FULL = BAR_IN_EMPTY + kInStagesMax,
   BAR_T_READY,
+  BAR_S1W_FULL,                       // layers >= 1: t_w(t) accumulators complete (committed one step early)
+  BAR_TW_READY,                       // ... and converted into the B operand
   BAR_S2_FULL0,
   BAR_S2_FULL1,
   BAR_S2_EMPTY0,
@@ -339,26 +387,52 @@ __host__ __device__ inline void for_seg_u(const P& p, F&& f) {
       for (int c2 = 0; c2 < 2; ++c2) f((uint32_t)rows * 128u, kb, r0, rows, kb * 128 + c2 * 64);
     }
 }
-// segment 2: A2, for unit block ub, for gate g: the t part (K = ru_pad + rw_pad, from the t buffer) in chunks of <= 64,
-// then the x part (layer 0, K = kx, from the input ring) in chunks of <= 64
+// segment 2: A2 in TWO passes over the (unit block, gate) tiles.  Early pass = the part of the gate contraction that
+// does not depend on h(t-1): K = rw_pad rows of t_w (layers >= 1, part 2) or K = kx rows of x(t) (layer 0, part 1);
+// for the first unit block it is issued while the epilogue is still converting t_u.  Late pass = the recurrent part,
+// K = ru_pad rows of t_u (part 0), accumulating on top.  Resident stream: per unit block, early pass of its 4 gate
+// tiles, then late pass (each pass is one asm block).  Streamed: tile by tile, early chunks then late chunks (the E2
+// epilogue of block 0 can then start after half of the step's chunks, and one tile's early chunks cover E1).
+// Chunks of <= 64 K each.
 template <class P, class F>
 __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
-  const int kt = p.ru_pad + p.rw_pad;
+  const int ke = p.has_s1w ? p.rw_pad : p.kx;
+  const int part_e = p.has_s1w ? 2 : 1;
+  if (p.streaming) {   // streamed: tile by tile (early chunks, then late chunks of the same tile)
 #pragma unroll 1
-  for (int ub = 0; ub < p.H / 128; ++ub)
+    for (int ub = 0; ub < p.H / 128; ++ub)
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 4; ++g) {
 #pragma unroll 1
-      for (int k0 = 0; k0 < kt; k0 += 64) {
-        const int kc = imin(64, kt - k0);
+        for (int k0 = 0; k0 < ke; k0 += 64) {
+          const int kc = imin(64, ke - k0);
+          f((uint32_t)kc * 256u, ub, g, part_e, k0, kc);
+        }
+#pragma unroll 1
+        for (int k0 = 0; k0 < p.ru_pad; k0 += 64) {
+          const int kc = imin(64, p.ru_pad - k0);
+          f((uint32_t)kc * 256u, ub, g, 0, k0, kc);
+        }
+      }
+    return;
+  }
+#pragma unroll 1
+  for (int ub = 0; ub < p.H / 128; ++ub) {
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g)
+#pragma unroll 1
+      for (int k0 = 0; k0 < ke; k0 += 64) {
+        const int kc = imin(64, ke - k0);
+        f((uint32_t)kc * 256u, ub, g, part_e, k0, kc);
+      }
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g)
+#pragma unroll 1
+      for (int k0 = 0; k0 < p.ru_pad; k0 += 64) {
+        const int kc = imin(64, p.ru_pad - k0);
         f((uint32_t)kc * 256u, ub, g, 0, k0, kc);
       }
-#pragma unroll 1
-      for (int k0 = 0; k0 < p.kx; k0 += 64) {
-        const int kc = imin(64, p.kx - k0);
-        f((uint32_t)kc * 256u, ub, g, 1, k0, kc);
-      }
-    }
+  }
 }
 
 #ifdef SVDLSTM_TC_TIMELINE
@@ -411,6 +485,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     }
     mbar_init(bar(BAR_S1_FULL), 1);
     mbar_init(bar(BAR_T_READY), kEpiThreads);
+    mbar_init(bar(BAR_S1W_FULL), 1);
+    mbar_init(bar(BAR_TW_READY), kEpiThreads);
     mbar_init(bar(BAR_S2_FULL0), 1);
     mbar_init(bar(BAR_S2_FULL1), 1);
     mbar_init(bar(BAR_S2_EMPTY0), kEpiThreads);
@@ -554,10 +630,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
         a_lo += bytes >> 4;
       }
     };
+    // resident mode, one K chunk of nm MMAs per gate tile: the whole unit block (4 gates) goes out as one asm block
+    auto gates_block = [&](int nm, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
+      const uint32_t a_hi = desc_hi((uint32_t)nm * 256u);
+      switch (nm) {
+        case 4: umma_f16_gates<4>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 3: umma_f16_gates<3>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 2: umma_f16_gates<2>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        default: umma_f16_gates<1>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+      }
+      a_lo += (uint32_t)nm * 1024u;   // 4 chunks of nm * 4096 bytes
+    };
     const int n_in_chunks = p.Kin >> 6;
-    const int kt = p.ru_pad + p.rw_pad;
-    const int kt_full = kt >> 6, kt_rem = (kt & 63) >> 4;
-    const int kx_full = p.kx >> 6, kx_rem = (p.kx & 63) >> 4;
+    const int ke = p.has_s1w ? p.rw_pad : p.kx;                 // early (input) part of S2
+    const int ke_full = ke >> 6, ke_rem = (ke & 63) >> 4;
+    const int ku_full = p.ru_pad >> 6, ku_rem = (p.ru_pad & 63) >> 4;   // late (recurrent) part
+    const uint32_t tw_lo0 = t_lo0 + (uint32_t)(p.ru_pad >> 3) * 32u;    // t_w rows follow the t_u rows in the t buffer
+    const int ke_one = ke <= 64 ? ke >> 4 : 0, ku_one = p.ru_pad <= 64 ? p.ru_pad >> 4 : 0;   // MMAs per tile if it is ONE chunk
     int in_s = 0;            // input ring stage of step t (layer 0) / of the next S1w (layers >= 1)
     uint32_t in_ph = 0;      // its phase bit
     auto issue_s1w = [&]() {   // t_w(tt) = A1w . in(tt), tt = the step the ring cursor points at
@@ -578,6 +667,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
         d += 32u;
       }
       umma_commit(bar(BAR_IN_EMPTY + in_s), elected);   // in(tt) is consumed once these MMAs complete
+      umma_commit(bar(BAR_S1W_FULL), elected);
       if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
     };
     uint32_t s2_use = 0;   // global count of S2 accumulator-buffer uses (buffers alternate)
@@ -609,16 +699,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       umma_commit(bar(BAR_S1_FULL), elected);
       TC_STAMP(2);   // MMA: S1 issued + committed
       if (t == T) break;
-      // ---- S2: z = A2 . [t_u ; t_w | x(t)]
-      uint32_t in_lo = 0;
-      if (!p.has_s1w) {
+      // ---- S2 early pass: z = A2in . (t_w(t) | x(t)) -- nothing here depends on h(t-1)
+      uint32_t be0;
+      if (p.has_s1w) {
+        mbar_wait(bar(BAR_TW_READY), (uint32_t)t & 1u);
+        be0 = tw_lo0;
+      } else {
         mbar_wait(bar(BAR_IN_FULL + in_s), in_ph);
-        in_lo = in_lo0 + (uint32_t)in_s * in_stage_lo;
+        be0 = in_lo0 + (uint32_t)in_s * in_stage_lo;
       }
-      mbar_wait(bar(BAR_T_READY), (uint32_t)t & 1u);
       tc_fence_after();
-      TC_STAMP(3);   // MMA: t operand ready seen
-      if (!streaming) a_lo = w_lo0 + ((p.segw_bytes + p.segu_bytes) >> 4);
 #pragma unroll 1
       for (int ub = 0; ub < nub; ++ub) {
         const uint32_t use = s2_use + (uint32_t)ub;
@@ -627,38 +717,90 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           mbar_wait(bar(BAR_S2_EMPTY0 + buf), ((use >> 1) - 1u) & 1u);
           tc_fence_after();
         }
-        uint32_t d = tm_s2 + buf * 128u;
+        const uint32_t d0 = tm_s2 + buf * 128u;
+        if (streaming) {
+          // tile by tile: early chunks (input part), then late chunks (recurrent part; the first one waits for t_u)
+          uint32_t d = d0;
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t b = t_lo0;
-          uint32_t acc = 0u;
+          for (int g = 0; g < 4; ++g) {
+            uint32_t b = be0;
+            uint32_t acc = 0u;
 #pragma unroll 1
-          for (int c = 0; c < kt_full; ++c) {
-            chunk64(16384u, d, b, acc);
-            acc = 1u;
-            b += 256u;
-          }
-          if (kt_rem) {
-            chunk(kt_rem, (uint32_t)kt_rem * 4096u, desc_hi((uint32_t)kt_rem * 256u), d, b, acc);
-            acc = 1u;
-          }
-          b = in_lo;
+            for (int c = 0; c < ke_full; ++c) {
+              chunk64(16384u, d, b, acc);
+              acc = 1u;
+              b += 256u;
+            }
+            if (ke_rem) chunk(ke_rem, (uint32_t)ke_rem * 4096u, desc_hi((uint32_t)ke_rem * 256u), d, b, acc);
+            if (ub == nub - 1 && g == 3 && !p.has_s1w) {   // layer 0: x(t) fully consumed
+              umma_commit(bar(BAR_IN_EMPTY + in_s), elected);
+              if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
+            }
+            if (ub == 0 && g == 0) {
+              mbar_wait(bar(BAR_T_READY), (uint32_t)t & 1u);
+              tc_fence_after();
+              TC_STAMP(3);   // MMA: t operand ready seen
+            }
+            b = t_lo0;
 #pragma unroll 1
-          for (int c = 0; c < kx_full; ++c) {
-            chunk64(16384u, d, b, 1u);
-            b += 256u;
+            for (int c = 0; c < ku_full; ++c) {
+              chunk64(16384u, d, b, 1u);
+              b += 256u;
+            }
+            if (ku_rem) chunk(ku_rem, (uint32_t)ku_rem * 4096u, desc_hi((uint32_t)ku_rem * 256u), d, b, 1u);
+            d += 32u;
           }
-          if (kx_rem) chunk(kx_rem, (uint32_t)kx_rem * 4096u, desc_hi((uint32_t)kx_rem * 256u), d, b, 1u);
-          d += 32u;
+        } else {
+          // early pass of this unit block
+          if (ke_one > 0) {
+            gates_block(ke_one, d0, be0, 0u);
+          } else {
+            uint32_t d = d0;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+              uint32_t b = be0;
+              uint32_t acc = 0u;
+#pragma unroll 1
+              for (int c = 0; c < ke_full; ++c) {
+                chunk64(16384u, d, b, acc);
+                acc = 1u;
+                b += 256u;
+              }
+              if (ke_rem) chunk(ke_rem, (uint32_t)ke_rem * 4096u, desc_hi((uint32_t)ke_rem * 256u), d, b, acc);
+              d += 32u;
+            }
+          }
+          if (ub == nub - 1 && !p.has_s1w) {   // layer 0: x(t) is consumed by the early passes
+            umma_commit(bar(BAR_IN_EMPTY + in_s), elected);
+            if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
+          }
+          if (ub == 0) {   // ---- the recurrent part needs t_u(t)
+            mbar_wait(bar(BAR_T_READY), (uint32_t)t & 1u);
+            tc_fence_after();
+            TC_STAMP(3);   // MMA: t operand ready seen
+          }
+          // late pass: z += A2u . t_u(t)
+          if (ku_one > 0) {
+            gates_block(ku_one, d0, t_lo0, 1u);
+          } else {
+            uint32_t d = d0;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+              uint32_t b = t_lo0;
+#pragma unroll 1
+              for (int c = 0; c < ku_full; ++c) {
+                chunk64(16384u, d, b, 1u);
+                b += 256u;
+              }
+              if (ku_rem) chunk(ku_rem, (uint32_t)ku_rem * 4096u, desc_hi((uint32_t)ku_rem * 256u), d, b, 1u);
+              d += 32u;
+            }
+          }
         }
         umma_commit(bar(BAR_S2_FULL0 + buf), elected);
         TC_STAMP(4 + (ub & 1));   // MMA: S2 block ub issued + committed
       }
       s2_use += (uint32_t)nub;
-      if (!p.has_s1w) {   // layer 0: x(t) is consumed by S2
-        umma_commit(bar(BAR_IN_EMPTY + in_s), elected);
-        if (++in_s == nst) { in_s = 0; in_ph ^= 1u; }
-      }
       // ---- S1w of the NEXT step: no recurrence, so it fills the tensor pipe while the epilogue works on z(t)
       if (p.has_s1w && t + 1 < T) issue_s1w();
     }
@@ -684,13 +826,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
     uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0;
-    int e1_tiles = 0;
+    int e1u_tiles = 0, e1w_tiles = 0;
     for (int mt = 0; mt < 3; ++mt) {
       const int r0 = mt * 128, j = r0 + row;
-      if (r0 < p.rows_u && r0 + q * 32 < e1_rows_u) { u_ld |= 1u << mt; e1_tiles = mt + 1; }   // warp-uniform
+      if (r0 < p.rows_u && r0 + q * 32 < e1_rows_u) { u_ld |= 1u << mt; e1u_tiles = mt + 1; }   // warp-uniform
       if (j < p.ru_pad) u_st |= 1u << mt;
       if (j < p.ru) u_live |= 1u << mt;
-      if (p.has_s1w && r0 < p.rows_w && r0 + q * 32 < p.rw_pad) { w_ld |= 1u << mt; e1_tiles = mt + 1; }
+      if (p.has_s1w && r0 < p.rows_w && r0 + q * 32 < p.rw_pad) { w_ld |= 1u << mt; e1w_tiles = mt + 1; }
       if (j < p.rw_pad) w_st |= 1u << mt;
       if (j < p.rw) w_live |= 1u << mt;
     }
@@ -706,6 +848,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     float* y_ptr = (p.n_dense > 0 && y_mt >= 0) ? p.y + (size_t)b_first * T * p.n_dense + y_o : nullptr;   // + t*n_dense, + n*T*n_dense
     const int y_valid = p.B - b_first < 16 ? (p.B - b_first < 0 ? 0 : p.B - b_first) : 16;
     const size_t y_seq_stride = (size_t)T * p.n_dense;
+    // t_w(tt) accumulators -> f16 rows [ru_pad, ru_pad + rw_pad) of the S2 B operand.  Runs one step ahead of its use
+    // (S1w has no recurrence), at the tail of the previous step's epilogue, so it is never on the critical path.
+    auto e1w = [&](uint32_t parity) {
+      mbar_wait(bar(BAR_S1W_FULL), parity);
+      tc_fence_after();
+      uint32_t aw[16];
+#pragma unroll 1
+      for (int mt = 0; mt < e1w_tiles; ++mt) {
+        tmem_ld16(tm_w + (uint32_t)mt * 32u, aw);
+        tmem_ld_wait();
+        if ((w_st >> mt) & 1u) store_t_row(tb_w + (uint32_t)mt * 8192u, aw, (w_live >> mt) & 1u);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar(BAR_TW_READY));
+    };
+    if (p.has_s1w) e1w(0u);
     uint32_t s2_use = 0;
     for (int t = 0; t < n_steps; ++t) {
       // ---- epilogue 1: t_u / t_w accumulators -> f16 rows of the S2 B operand; Dense-top rows -> y(t-1) ----
@@ -714,24 +873,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
       float yv[16];
       {
-        // both accumulator sets are fetched before the single wait: a TMEM load has a few hundred cycles of latency here
-        uint32_t au[16], aw[16];
+        uint32_t au[16];
         const bool step_live = t < T;   // the flush pass (t == T) only extracts the Dense-top row
 #pragma unroll 1
-        for (int mt = 0; mt < e1_tiles; ++mt) {
-          const bool do_u = (u_ld >> mt) & 1u, do_w = ((w_ld >> mt) & 1u) && step_live;
-          if (do_u) tmem_ld16(tm_u + (uint32_t)mt * 32u, au);
-          if (do_w) tmem_ld16(tm_w + (uint32_t)mt * 32u, aw);
+        for (int mt = 0; mt < e1u_tiles; ++mt) {
+          tmem_ld16(tm_u + (uint32_t)mt * 32u, au);
           tmem_ld_wait();
-          if (threadIdx.x == 128) TC_STAMP(0);   // EPI: S1 accumulator tiles in registers
-          if (do_u) {
-            if (((u_st >> mt) & 1u) && step_live) store_t_row(tb_u + (uint32_t)mt * 8192u, au, (u_live >> mt) & 1u);
-            if (mt == y_mt) {   // keep the Dense-top row; it is written out after the t operand has been published
+          if (threadIdx.x == 128) TC_STAMP(0);   // EPI: S1 accumulator tile in registers
+          if (((u_st >> mt) & 1u) && step_live) store_t_row(tb_u + (uint32_t)mt * 8192u, au, (u_live >> mt) & 1u);
+          if (mt == y_mt) {   // keep the Dense-top row; it is written out after the t operand has been published
 #pragma unroll
-              for (int n = 0; n < 16; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
-            }
+            for (int n = 0; n < 16; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
           }
-          if (do_w && ((w_st >> mt) & 1u)) store_t_row(tb_w + (uint32_t)mt * 8192u, aw, (w_live >> mt) & 1u);
         }
       }
       if (t < T) {
@@ -792,6 +945,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       }
       s2_use += (uint32_t)nub;
       if (p.store_h) mbar_arrive(bar(BAR_H_DONE));
+      if (p.has_s1w && t + 1 < T) e1w((uint32_t)(t + 1) & 1u);
       if (threadIdx.x == 128) TC_STAMP(14);      // EPI: h(t) published
     }
   }
@@ -839,13 +993,11 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
     } else {
       const int n = c.g * H + c.ub * 128 + row;
       const int kk = c.k0 + k;
-      if (c.part == 0) {
-        if (kk < ru_pad) {
-          if (kk < bu.rank) v = block_right(bu, kk, n);
-        } else if (kk - ru_pad < bw.rank) {
-          v = block_right(bw, kk - ru_pad, n);
-        }
-      } else if (kk < D) {
+      if (c.part == 0) {            // recurrent part: row kk of R_u
+        if (kk < bu.rank) v = block_right(bu, kk, n);
+      } else if (c.part == 2) {     // input part, layers >= 1: row kk of R_w
+        if (kk < bw.rank) v = block_right(bw, kk, n);
+      } else if (kk < D) {          // input part, layer 0: the dense D x 4H product W0 = (L_w sigma_w) R_w
         float acc = 0.f;
         for (int j = 0; j < bw.rank; ++j) acc = fmaf(block_left(bw, kk, j), block_right(bw, j, n), acc);
         v = acc;
