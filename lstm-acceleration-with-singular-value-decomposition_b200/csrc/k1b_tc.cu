@@ -39,7 +39,6 @@ namespace svdlstm {
 
 namespace {
 
-constexpr int kN = 32;               // sequences per CTA (MMA N)
 constexpr int kInStagesMax = 3;      // max input prefetch ring depth
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
@@ -125,25 +124,11 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
-// D[tmem] (+)= A[smem desc] . B[smem desc]   (kind::f16: f16 x f16 -> fp32).  Executed by the whole (converged)
-// warp; only the elected lane issues.  Descriptors are given as (lo, hi) words: stepping K is one add on lo.
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
-                                         uint32_t accumulate, uint32_t elected) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(elected)
-      : "memory");
-}
+// tcgen05.mma (kind::f16: f16 x f16 -> fp32) is executed by the whole (converged) warp; only the elected lane issues.
+// Descriptors are given as (lo, hi) words: stepping K is one add on lo.
 // NM (1..4) back-to-back MMAs of one weight chunk in ONE asm block: the K step of both descriptors is an
-// immediate add on the lo word (A +256 B, B +1024 B per K=16) and the predicates are set up once per chunk.
+// immediate add on the lo word (A +256 B; B +2 k-groups = NS*32 B per K=16) and the predicates are set up once per
+// chunk.  NS = sequences per tile (MMA N): 32 or 64.
 #define SVD_UMMA_HEAD                                                   \
   "{\n\t"                                                               \
   ".reg .pred p, q, one;\n\t"                                           \
@@ -163,18 +148,21 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t alo, uint32_t
   "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, one;\n\t"
 #define SVD_UMMA_OPERANDS                                                                                              \
   ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(first_accumulates), "r"(elected) : "memory"
-template <int NM>
+template <int NM, int NS>
 __device__ __forceinline__ void umma_f16_x(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
                                            uint32_t first_accumulates, uint32_t elected) {
-  static_assert(NM >= 1 && NM <= 4, "1..4 MMAs per chunk");
-  if constexpr (NM == 1) asm volatile(SVD_UMMA_HEAD "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 2) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 3) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 4)
-    asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) SVD_UMMA_NEXT(48, 192) "}\n" SVD_UMMA_OPERANDS);
+  static_assert(NM >= 1 && NM <= 4 && (NS == 32 || NS == 64), "1..4 MMAs per chunk, 32 or 64 sequences");
+  if constexpr (NM == 1 && NS == 32) asm volatile(SVD_UMMA_HEAD "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2 && NS == 32) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3 && NS == 32) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4 && NS == 32) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 64) SVD_UMMA_NEXT(32, 128) SVD_UMMA_NEXT(48, 192) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 1 && NS == 64) asm volatile(SVD_UMMA_HEAD "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2 && NS == 64) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 128) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3 && NS == 64) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 128) SVD_UMMA_NEXT(32, 256) "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4 && NS == 64) asm volatile(SVD_UMMA_HEAD SVD_UMMA_NEXT(16, 128) SVD_UMMA_NEXT(32, 256) SVD_UMMA_NEXT(48, 384) "}\n" SVD_UMMA_OPERANDS);
 }
 // The 4 gate tiles of one unit block in ONE asm block (resident mode, one K chunk of NM MMAs per tile): gate g's
-// accumulator is D + 32 g columns, its weight chunk follows gate g-1's (+NM*4096 bytes), the B operand is shared.
+// accumulator is D + NS g columns, its weight chunk follows gate g-1's (+NM*4096 bytes), the B operand is shared.
 // All steps are immediates, so the 4*NM MMAs cost a few uniform instructions each and no branches.
 #define SVD_UMMA_G(goff_a, goff_d, koff_a, koff_b, PRED)                \
   "add.u32 ta, %1, " #goff_a "+" #koff_a ";\n\t"                        \
@@ -191,32 +179,18 @@ __device__ __forceinline__ void umma_f16_x(uint32_t d_tmem, uint32_t alo, uint32
   "setp.ne.b32 q, %7, 0;\n\t"                                           \
   "setp.ne.b32 p, %6, 0;\n\t"                                           \
   "setp.eq.b32 one, 0, 0;\n\t"
-template <int NM>
+template <int NM, int NS>
 __device__ __forceinline__ void umma_f16_gates(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
                                                uint32_t first_accumulates, uint32_t elected) {
-  static_assert(NM >= 1 && NM <= 4, "1..4 MMAs per gate tile");
-  if constexpr (NM == 1)
-    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(256, 32, 0, 0, "p") SVD_UMMA_G(512, 64, 0, 0, "p")
-                 SVD_UMMA_G(768, 96, 0, 0, "p") "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 2)
-    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one")
-                 SVD_UMMA_G(512, 32, 0, 0, "p") SVD_UMMA_G(512, 32, 16, 64, "one")
-                 SVD_UMMA_G(1024, 64, 0, 0, "p") SVD_UMMA_G(1024, 64, 16, 64, "one")
-                 SVD_UMMA_G(1536, 96, 0, 0, "p") SVD_UMMA_G(1536, 96, 16, 64, "one") "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 3)
-    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one")
-                 SVD_UMMA_G(768, 32, 0, 0, "p") SVD_UMMA_G(768, 32, 16, 64, "one") SVD_UMMA_G(768, 32, 32, 128, "one")
-                 SVD_UMMA_G(1536, 64, 0, 0, "p") SVD_UMMA_G(1536, 64, 16, 64, "one") SVD_UMMA_G(1536, 64, 32, 128, "one")
-                 SVD_UMMA_G(2304, 96, 0, 0, "p") SVD_UMMA_G(2304, 96, 16, 64, "one") SVD_UMMA_G(2304, 96, 32, 128, "one") "}\n" SVD_UMMA_OPERANDS);
-  if constexpr (NM == 4)
-    asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one")
-                 SVD_UMMA_G(0, 0, 48, 192, "one")
-                 SVD_UMMA_G(1024, 32, 0, 0, "p") SVD_UMMA_G(1024, 32, 16, 64, "one") SVD_UMMA_G(1024, 32, 32, 128, "one")
-                 SVD_UMMA_G(1024, 32, 48, 192, "one")
-                 SVD_UMMA_G(2048, 64, 0, 0, "p") SVD_UMMA_G(2048, 64, 16, 64, "one") SVD_UMMA_G(2048, 64, 32, 128, "one")
-                 SVD_UMMA_G(2048, 64, 48, 192, "one")
-                 SVD_UMMA_G(3072, 96, 0, 0, "p") SVD_UMMA_G(3072, 96, 16, 64, "one") SVD_UMMA_G(3072, 96, 32, 128, "one")
-                 SVD_UMMA_G(3072, 96, 48, 192, "one") "}\n" SVD_UMMA_OPERANDS);
+  static_assert(NM >= 1 && NM <= 4 && (NS == 32 || NS == 64), "1..4 MMAs per gate tile, 32 or 64 sequences");
+  if constexpr (NM == 1 && NS == 32) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(256, 32, 0, 0, "p") SVD_UMMA_G(512, 64, 0, 0, "p") SVD_UMMA_G(768, 96, 0, 0, "p") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2 && NS == 32) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(512, 32, 0, 0, "p") SVD_UMMA_G(512, 32, 16, 64, "one") SVD_UMMA_G(1024, 64, 0, 0, "p") SVD_UMMA_G(1024, 64, 16, 64, "one") SVD_UMMA_G(1536, 96, 0, 0, "p") SVD_UMMA_G(1536, 96, 16, 64, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3 && NS == 32) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one") SVD_UMMA_G(768, 32, 0, 0, "p") SVD_UMMA_G(768, 32, 16, 64, "one") SVD_UMMA_G(768, 32, 32, 128, "one") SVD_UMMA_G(1536, 64, 0, 0, "p") SVD_UMMA_G(1536, 64, 16, 64, "one") SVD_UMMA_G(1536, 64, 32, 128, "one") SVD_UMMA_G(2304, 96, 0, 0, "p") SVD_UMMA_G(2304, 96, 16, 64, "one") SVD_UMMA_G(2304, 96, 32, 128, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4 && NS == 32) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 64, "one") SVD_UMMA_G(0, 0, 32, 128, "one") SVD_UMMA_G(0, 0, 48, 192, "one") SVD_UMMA_G(1024, 32, 0, 0, "p") SVD_UMMA_G(1024, 32, 16, 64, "one") SVD_UMMA_G(1024, 32, 32, 128, "one") SVD_UMMA_G(1024, 32, 48, 192, "one") SVD_UMMA_G(2048, 64, 0, 0, "p") SVD_UMMA_G(2048, 64, 16, 64, "one") SVD_UMMA_G(2048, 64, 32, 128, "one") SVD_UMMA_G(2048, 64, 48, 192, "one") SVD_UMMA_G(3072, 96, 0, 0, "p") SVD_UMMA_G(3072, 96, 16, 64, "one") SVD_UMMA_G(3072, 96, 32, 128, "one") SVD_UMMA_G(3072, 96, 48, 192, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 1 && NS == 64) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(256, 64, 0, 0, "p") SVD_UMMA_G(512, 128, 0, 0, "p") SVD_UMMA_G(768, 192, 0, 0, "p") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 2 && NS == 64) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 128, "one") SVD_UMMA_G(512, 64, 0, 0, "p") SVD_UMMA_G(512, 64, 16, 128, "one") SVD_UMMA_G(1024, 128, 0, 0, "p") SVD_UMMA_G(1024, 128, 16, 128, "one") SVD_UMMA_G(1536, 192, 0, 0, "p") SVD_UMMA_G(1536, 192, 16, 128, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 3 && NS == 64) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 128, "one") SVD_UMMA_G(0, 0, 32, 256, "one") SVD_UMMA_G(768, 64, 0, 0, "p") SVD_UMMA_G(768, 64, 16, 128, "one") SVD_UMMA_G(768, 64, 32, 256, "one") SVD_UMMA_G(1536, 128, 0, 0, "p") SVD_UMMA_G(1536, 128, 16, 128, "one") SVD_UMMA_G(1536, 128, 32, 256, "one") SVD_UMMA_G(2304, 192, 0, 0, "p") SVD_UMMA_G(2304, 192, 16, 128, "one") SVD_UMMA_G(2304, 192, 32, 256, "one") "}\n" SVD_UMMA_OPERANDS);
+  if constexpr (NM == 4 && NS == 64) asm volatile(SVD_UMMA_G_HEAD SVD_UMMA_G(0, 0, 0, 0, "p") SVD_UMMA_G(0, 0, 16, 128, "one") SVD_UMMA_G(0, 0, 32, 256, "one") SVD_UMMA_G(0, 0, 48, 384, "one") SVD_UMMA_G(1024, 64, 0, 0, "p") SVD_UMMA_G(1024, 64, 16, 128, "one") SVD_UMMA_G(1024, 64, 32, 256, "one") SVD_UMMA_G(1024, 64, 48, 384, "one") SVD_UMMA_G(2048, 128, 0, 0, "p") SVD_UMMA_G(2048, 128, 16, 128, "one") SVD_UMMA_G(2048, 128, 32, 256, "one") SVD_UMMA_G(2048, 128, 48, 384, "one") SVD_UMMA_G(3072, 192, 0, 0, "p") SVD_UMMA_G(3072, 192, 16, 128, "one") SVD_UMMA_G(3072, 192, 32, 256, "one") SVD_UMMA_G(3072, 192, 48, 384, "one") "}\n" SVD_UMMA_OPERANDS);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t elected) {
   asm volatile(
@@ -256,7 +230,7 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 //   K-major  A chunk [rows x kc]: elem(row,k) at (row/8)*(kc*16) + (k/8)*128 + (row%8)*16 + (k%8)*2     LBO=128, SBO=kc*16
 //   MN-major B tile  [K x N=32] : elem(k,n)   at (k/8)*512 + (n/8)*128 + (k%8)*16 + (n%8)*2             LBO=512, SBO=128
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {   // N = sequences per tile
   return (1u << 4)                      // c_format  F32
          | (0u << 7)                    // a_format  F16
          | (0u << 10)                   // b_format  F16
@@ -265,24 +239,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)   // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
-constexpr uint32_t kActLBO = 512, kActSBO = 128;
-__host__ __device__ inline uint32_t act_tile_bytes(int K) { return (uint32_t)(K / 8) * 512u; }
-__host__ __device__ inline uint32_t act_offset(int k, int n) {
-  return (uint32_t)(k / 8) * 512u + (uint32_t)(n / 8) * 128u + (uint32_t)(k % 8) * 16u + (uint32_t)(n % 8) * 2u;
+//   MN-major B tile [K x NS]: elem(k,n) at (k/8)*(NS*16) + (n/8)*128 + (k%8)*16 + (n%8)*2        LBO = NS*16, SBO = 128
+constexpr uint32_t kActSBO = 128;
+__host__ __device__ inline uint32_t act_tile_bytes(int K, int ns) { return (uint32_t)(K / 8) * (uint32_t)ns * 16u; }
+__host__ __device__ inline uint32_t act_offset(int k, int n, int ns) {
+  return (uint32_t)(k / 8) * (uint32_t)ns * 16u + (uint32_t)(n / 8) * 128u + (uint32_t)(k % 8) * 16u + (uint32_t)(n % 8) * 2u;
 }
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
-// 16 fp32 accumulator columns of one row -> f16, two 16-byte stores into an MN-major activation tile (shared-space address)
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void store_t_row(uint32_t saddr, const uint32_t* r, bool live) {
-  const uint32_t m = live ? 0xFFFFFFFFu : 0u;   // padding rows (rank..rank_pad) must hold zeros
-  sts128(saddr, pack_f16(__uint_as_float(r[0]), __uint_as_float(r[1])) & m, pack_f16(__uint_as_float(r[2]), __uint_as_float(r[3])) & m,
-         pack_f16(__uint_as_float(r[4]), __uint_as_float(r[5])) & m, pack_f16(__uint_as_float(r[6]), __uint_as_float(r[7])) & m);
-  sts128(saddr + 128u, pack_f16(__uint_as_float(r[8]), __uint_as_float(r[9])) & m, pack_f16(__uint_as_float(r[10]), __uint_as_float(r[11])) & m,
-         pack_f16(__uint_as_float(r[12]), __uint_as_float(r[13])) & m, pack_f16(__uint_as_float(r[14]), __uint_as_float(r[15])) & m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -306,6 +273,7 @@ struct TcLayerParams {
   float* y;                 // (B, T, n_dense) fused Dense-top output            (n_dense > 0)
   const float* dense_bias;
   int H, Kin, T, B;
+  int ns;                   // sequences per CTA tile (MMA N): 32 or 64
   int ru, rw;               // true ranks
   int ru_pad, rw_pad;       // multiples of 16: K extents of t_u / t_w inside the S2 contraction (rw_pad = 0 on layer 0)
   int kx;                   // layer 0: K extent of the x part of S2 (= Kin); else 0
@@ -328,9 +296,9 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   uint32_t off = 0;
   s.w = off;
   off += p.streaming ? (uint32_t)p.w_slots * kSlotBytes : ((p.segw_bytes + p.segu_bytes + p.seg2_bytes + 1023u) & ~1023u);
-  s.hbuf = off; off += act_tile_bytes(p.H);
-  s.tbuf = off; off += act_tile_bytes(p.ru_pad + p.rw_pad);
-  s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin);
+  s.hbuf = off; off += act_tile_bytes(p.H, p.ns);
+  s.tbuf = off; off += act_tile_bytes(p.ru_pad + p.rw_pad, p.ns);
+  s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin, p.ns);
   s.bars = off; off += 512;
   s.tmem_slot = off; off += 16;
   // streaming: the chunk table (offset, bytes in 256-byte units) lives in smem -- with a 227 KB carve-out there is no L1 to cache it
@@ -443,8 +411,12 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 #define TC_CHUNK_STAMP() do { } while (0)
 #endif
 
-template <int NUB, bool STREAM>
+template <int NUB, bool STREAM, int NS>
 __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
+  constexpr int CPT = NS / 2;                 // accumulator columns per epilogue thread (two warps per TMEM lane quarter)
+  constexpr uint32_t kRowBlk = (uint32_t)NS * 256u;   // bytes of 128 K-rows of an activation tile (16 k-groups)
+  constexpr uint32_t kK64 = (uint32_t)NS * 8u;        // descriptor-lo step of 64 K-rows (8 k-groups of NS*16 bytes)
+  constexpr int kS2Bufs = NS == 32 ? 2 : 1;   // S2 accumulator buffers that fit TMEM (4 gates x NS columns each)
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcSmemPlan sp = tc_plan(p);
   const uint32_t sbase = smem_u32(smem);
@@ -454,7 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   constexpr int nub = NUB;
   const int nst = p.in_stages;
   const int ns = p.w_slots;
-  const uint32_t in_tile = act_tile_bytes(p.Kin), h_tile = act_tile_bytes(H);
+  const uint32_t in_tile = act_tile_bytes(p.Kin, NS), h_tile = act_tile_bytes(H, NS);
   const uint32_t bar0 = sbase + sp.bars;
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int n_steps = T + (p.n_dense > 0 ? 1 : 0);   // the Dense-top output of step T-1 needs one more S1u pass
@@ -502,8 +474,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + sp.tmem_slot);
-  // TMEM columns: [0,96) S1u (<= 3 row tiles), [96,160) S1w (<= 2 row tiles), [192,320) S2 buffer 0 (4 gates x 32), [320,448) buffer 1
-  const uint32_t tm_s1u = tmem, tm_s1w = tmem + 96, tm_s2 = tmem + 192;
+  // TMEM columns (NS=32): [0,96) S1u (<= 3 row tiles), [96,160) S1w (<= 2), [192,320) S2 buffer 0 (4 gates x 32), [320,448) buffer 1
+  //              (NS=64): [0,128) S1u (<= 2 row tiles), [128,256) S1w (<= 2), [256,512) the one S2 buffer (4 gates x 64)
+  const uint32_t tm_s1u = tmem, tm_s1w = tmem + (NS == 32 ? 96u : 128u), tm_s2 = tmem + (NS == 32 ? 192u : 256u);
 
   if (warp == 0) {
     // ======================= weight streamer ====================================================
@@ -582,8 +555,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     // loops below are written to cost a handful of uniform-datapath instructions per tcgen05.mma
     // (descriptor words advanced by immediates inside one asm block per chunk, no per-MMA branches).
     const uint32_t elected = elect_one();
-    const uint32_t idesc = make_idesc(128, kN);
+    const uint32_t idesc = make_idesc(128, NS);
     const uint32_t act_hi = desc_hi(kActSBO);
+    constexpr uint32_t kActLBO = (uint32_t)NS * 16u;
     const uint32_t h_lo0 = desc_lo(sbase + sp.hbuf, kActLBO), t_lo0 = desc_lo(sbase + sp.tbuf, kActLBO);
     const uint32_t in_lo0 = desc_lo(sbase + sp.inbuf, kActLBO), in_stage_lo = in_tile >> 4;
     const uint32_t w_lo0 = desc_lo(sbase + sp.w, 128u);
@@ -606,7 +580,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       }
 #pragma unroll 1
       for (int k = 0; k < nm; ++k)
-        umma_f16_x<1>(d_tmem, a_lo + 16u * (uint32_t)k, a_hi, b_lo + 64u * (uint32_t)k, act_hi, idesc, k > 0 ? 1u : first_accumulates, elected);
+        umma_f16_x<1, NS>(d_tmem, a_lo + 16u * (uint32_t)k, a_hi, b_lo + (uint32_t)(2 * NS) * (uint32_t)k, act_hi, idesc, k > 0 ? 1u : first_accumulates,
+                          elected);
       if (streaming) {
         umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
         a_lo += kSlotBytes >> 4;
@@ -621,7 +596,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
         mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
         tc_fence_after();
       }
-      umma_f16_x<4>(d_tmem, a_lo, a_hi64, b_lo, act_hi, idesc, first_accumulates, elected);
+      umma_f16_x<4, NS>(d_tmem, a_lo, a_hi64, b_lo, act_hi, idesc, first_accumulates, elected);
       if (streaming) {
         umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
         a_lo += kSlotBytes >> 4;
@@ -634,10 +609,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     auto gates_block = [&](int nm, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
       const uint32_t a_hi = desc_hi((uint32_t)nm * 256u);
       switch (nm) {
-        case 4: umma_f16_gates<4>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        case 3: umma_f16_gates<3>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        case 2: umma_f16_gates<2>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
-        default: umma_f16_gates<1>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 4: umma_f16_gates<4, NS>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 3: umma_f16_gates<3, NS>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        case 2: umma_f16_gates<2, NS>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
+        default: umma_f16_gates<1, NS>(d_tmem, a_lo, a_hi, b_lo, act_hi, idesc, first_accumulates, elected); break;
       }
       a_lo += (uint32_t)nm * 1024u;   // 4 chunks of nm * 4096 bytes
     };
@@ -645,7 +620,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     const int ke = p.has_s1w ? p.rw_pad : p.kx;                 // early (input) part of S2
     const int ke_full = ke >> 6, ke_rem = (ke & 63) >> 4;
     const int ku_full = p.ru_pad >> 6, ku_rem = (p.ru_pad & 63) >> 4;   // late (recurrent) part
-    const uint32_t tw_lo0 = t_lo0 + (uint32_t)(p.ru_pad >> 3) * 32u;    // t_w rows follow the t_u rows in the t buffer
+    const uint32_t tw_lo0 = t_lo0 + (uint32_t)(p.ru_pad >> 3) * (uint32_t)NS;    // t_w rows follow the t_u rows in the t buffer
     const int ke_one = ke <= 64 ? ke >> 4 : 0, ku_one = p.ru_pad <= 64 ? p.ru_pad >> 4 : 0;   // MMAs per tile if it is ONE chunk
     int in_s = 0;            // input ring stage of step t (layer 0) / of the next S1w (layers >= 1)
     uint32_t in_ph = 0;      // its phase bit
@@ -662,9 +637,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 #pragma unroll 1
         for (int c = 0; c < n_in_chunks; ++c) {
           chunk64(bytes, d, b, c > 0 ? 1u : 0u);
-          b += 256u;   // 64 K rows of the activation tile
+          b += kK64;   // 64 K rows of the activation tile
         }
-        d += 32u;
+        d += (uint32_t)NS;
       }
       umma_commit(bar(BAR_IN_EMPTY + in_s), elected);   // in(tt) is consumed once these MMAs complete
       umma_commit(bar(BAR_S1W_FULL), elected);
@@ -690,10 +665,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           for (int r0 = 0; r0 < p.rows_u; r0 += 128) {
             const uint32_t bytes = (uint32_t)imin(128, p.rows_u - r0) * 128u;
             chunk64(bytes, d, b, kb > 0 ? 1u : 0u);
-            chunk64(bytes, d, b + 256u, 1u);
-            d += 32u;
+            chunk64(bytes, d, b + kK64, 1u);
+            d += (uint32_t)NS;
           }
-          b += 512u;   // next 128 K rows of h
+          b += 2u * kK64;   // next 128 K rows of h
         }
       }
       umma_commit(bar(BAR_S1_FULL), elected);
@@ -711,25 +686,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       tc_fence_after();
 #pragma unroll 1
       for (int ub = 0; ub < nub; ++ub) {
+        // NS=32: two whole-block buffers (4 gate tiles each), used alternately.  NS=64: ONE block of TMEM, split into
+        // half-buffers A = tiles (i, g) and B = tiles (f, o) that the epilogue drains -- and hands back -- separately.
         const uint32_t use = s2_use + (uint32_t)ub;
-        const uint32_t buf = use & 1u;
-        if (use >= 2u) {   // wait until the epilogue drained this TMEM buffer (two uses ago)
-          mbar_wait(bar(BAR_S2_EMPTY0 + buf), ((use >> 1) - 1u) & 1u);
+        const uint32_t buf = kS2Bufs == 2 ? (use & 1u) : 0u, turn = kS2Bufs == 2 ? (use >> 1) : use;
+        if (turn >= 1u) {   // wait until the epilogue drained this TMEM buffer (its previous use)
+          mbar_wait(bar(BAR_S2_EMPTY0 + buf), (turn - 1u) & 1u);
+          if (kS2Bufs == 1 && !streaming) mbar_wait(bar(BAR_S2_EMPTY1), (turn - 1u) & 1u);   // resident passes touch all 4 tiles
           tc_fence_after();
         }
-        const uint32_t d0 = tm_s2 + buf * 128u;
+        const uint32_t d0 = tm_s2 + buf * (uint32_t)(4 * NS);
         if (streaming) {
           // tile by tile: early chunks (input part), then late chunks (recurrent part; the first one waits for t_u)
           uint32_t d = d0;
 #pragma unroll 1
           for (int g = 0; g < 4; ++g) {
+            if (kS2Bufs == 1 && g == 2 && turn >= 1u) {   // half-buffer B (tiles f, o) of the previous block drained?
+              mbar_wait(bar(BAR_S2_EMPTY1), (turn - 1u) & 1u);
+              tc_fence_after();
+            }
             uint32_t b = be0;
             uint32_t acc = 0u;
 #pragma unroll 1
             for (int c = 0; c < ke_full; ++c) {
               chunk64(16384u, d, b, acc);
               acc = 1u;
-              b += 256u;
+              b += kK64;
             }
             if (ke_rem) chunk(ke_rem, (uint32_t)ke_rem * 4096u, desc_hi((uint32_t)ke_rem * 256u), d, b, acc);
             if (ub == nub - 1 && g == 3 && !p.has_s1w) {   // layer 0: x(t) fully consumed
@@ -745,10 +727,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 #pragma unroll 1
             for (int c = 0; c < ku_full; ++c) {
               chunk64(16384u, d, b, 1u);
-              b += 256u;
+              b += kK64;
             }
             if (ku_rem) chunk(ku_rem, (uint32_t)ku_rem * 4096u, desc_hi((uint32_t)ku_rem * 256u), d, b, 1u);
-            d += 32u;
+            if (kS2Bufs == 1 && g == 1) umma_commit(bar(BAR_S2_FULL0), elected);   // half-buffer A (tiles i, g) complete
+            d += (uint32_t)NS;
           }
         } else {
           // early pass of this unit block
@@ -764,10 +747,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
               for (int c = 0; c < ke_full; ++c) {
                 chunk64(16384u, d, b, acc);
                 acc = 1u;
-                b += 256u;
+                b += kK64;
               }
               if (ke_rem) chunk(ke_rem, (uint32_t)ke_rem * 4096u, desc_hi((uint32_t)ke_rem * 256u), d, b, acc);
-              d += 32u;
+              d += (uint32_t)NS;
             }
           }
           if (ub == nub - 1 && !p.has_s1w) {   // layer 0: x(t) is consumed by the early passes
@@ -790,14 +773,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
 #pragma unroll 1
               for (int c = 0; c < ku_full; ++c) {
                 chunk64(16384u, d, b, 1u);
-                b += 256u;
+                b += kK64;
               }
               if (ku_rem) chunk(ku_rem, (uint32_t)ku_rem * 4096u, desc_hi((uint32_t)ku_rem * 256u), d, b, 1u);
-              d += 32u;
+              d += (uint32_t)NS;
             }
           }
         }
-        umma_commit(bar(BAR_S2_FULL0 + buf), elected);
+        if (kS2Bufs == 1) {
+          if (!streaming) umma_commit(bar(BAR_S2_FULL0), elected);
+          umma_commit(bar(BAR_S2_FULL1), elected);   // half-buffer B (and, resident, A) complete
+        } else {
+          umma_commit(bar(BAR_S2_FULL0 + buf), elected);
+        }
         TC_STAMP(4 + (ub & 1));   // MMA: S2 block ub issued + committed
       }
       s2_use += (uint32_t)nub;
@@ -805,24 +793,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (p.has_s1w && t + 1 < T) issue_s1w();
     }
   } else if (warp >= 4) {
-    // ======================= epilogue warps (256 threads; thread = TMEM lane = one row, 16 of the 32 columns) ==
+    // ======================= epilogue warps (256 threads; thread = TMEM lane = one row, CPT = NS/2 of the columns) ==
     const int ew = warp - 4;
     const int q = ew & 3;                      // TMEM lane quarter this warp may access (== warp % 4)
     const int half = ew >> 2;                  // column half
-    const int c0 = half * 16;
+    const int c0 = half * CPT;
     const int row = q * 32 + lane;             // row of every 128-row tile handled by this thread
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-    float cst[NUB][16];                     // cell state of unit (ub*128+row), 16 sequences, FP32, all T steps
+    float cst[NUB][CPT];                       // cell state of unit (ub*128+row), CPT sequences, FP32, all T steps
 #pragma unroll
     for (int u = 0; u < NUB; ++u)
 #pragma unroll
-      for (int n = 0; n < 16; ++n) cst[u][n] = 0.f;
+      for (int n = 0; n < CPT; ++n) cst[u][n] = 0.f;
     float bi[NUB][4];
 #pragma unroll
     for (int u = 0; u < NUB; ++u)
 #pragma unroll
       for (int g = 0; g < 4; ++g) bi[u][g] = p.bias[(u * 4 + g) * 128 + row];
-    const int b_first = cta * kN + c0;         // global sequence index of this thread's first column
+    const int b_first = cta * NS + c0;         // global sequence index of this thread's first column
     // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
     uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0;
@@ -836,29 +824,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (j < p.rw_pad) w_st |= 1u << mt;
       if (j < p.rw) w_live |= 1u << mt;
     }
-    const uint32_t tb_u = sbase + sp.tbuf + act_offset(row, c0);                  // + 8192 per 128-row tile
-    const uint32_t tb_w = tb_u + (uint32_t)(p.ru_pad >> 3) * 512u;
-    const uint32_t tm_u = tm_s1u + lane_addr, tm_w = tm_s1w + lane_addr;          // + 32 columns per tile
-    const uint32_t hb_addr = sbase + sp.hbuf + act_offset(row, c0);               // + 8192 per 128-unit block
+    const uint32_t tb_u = sbase + sp.tbuf + act_offset(row, c0, NS);              // + kRowBlk per 128-row tile
+    const uint32_t tb_w = tb_u + (uint32_t)(p.ru_pad >> 3) * (uint32_t)NS * 16u;
+    const uint32_t tm_u = tm_s1u + lane_addr, tm_w = tm_s1w + lane_addr;          // + NS columns per tile
+    const uint32_t hb_addr = sbase + sp.hbuf + act_offset(row, c0, NS);           // + kRowBlk per 128-unit block
     // Dense-top row owned by this thread (if any): its S1u row index is ru + o
     int y_mt = -1, y_o = 0;
     float y_bias = 0.f;
     for (int o = 0; o < p.n_dense; ++o)
       if (((p.ru + o) & 127) == row) { y_mt = (p.ru + o) >> 7; y_o = o; y_bias = p.dense_bias[o]; }
     float* y_ptr = (p.n_dense > 0 && y_mt >= 0) ? p.y + (size_t)b_first * T * p.n_dense + y_o : nullptr;   // + t*n_dense, + n*T*n_dense
-    const int y_valid = p.B - b_first < 16 ? (p.B - b_first < 0 ? 0 : p.B - b_first) : 16;
+    const int y_valid = p.B - b_first < CPT ? (p.B - b_first < 0 ? 0 : p.B - b_first) : CPT;
     const size_t y_seq_stride = (size_t)T * p.n_dense;
+    // CPT fp32 accumulator columns of one row -> f16, 16-byte stores (8 sequences each) into an MN-major activation tile
+    auto store_row = [&](uint32_t saddr, const uint32_t* r, bool live) {
+      const uint32_t m = live ? 0xFFFFFFFFu : 0u;   // padding rows (rank..rank_pad) must hold zeros
+#pragma unroll
+      for (int j8 = 0; j8 < CPT / 8; ++j8)
+        sts128(saddr + 128u * (uint32_t)j8, pack_f16(__uint_as_float(r[8 * j8 + 0]), __uint_as_float(r[8 * j8 + 1])) & m,
+               pack_f16(__uint_as_float(r[8 * j8 + 2]), __uint_as_float(r[8 * j8 + 3])) & m,
+               pack_f16(__uint_as_float(r[8 * j8 + 4]), __uint_as_float(r[8 * j8 + 5])) & m,
+               pack_f16(__uint_as_float(r[8 * j8 + 6]), __uint_as_float(r[8 * j8 + 7])) & m);
+    };
+    auto load_cols = [&](uint32_t taddr, uint32_t* r) {   // CPT consecutive accumulator columns of this thread's TMEM lane
+#pragma unroll
+      for (int j16 = 0; j16 < CPT / 16; ++j16) tmem_ld16(taddr + 16u * (uint32_t)j16, r + 16 * j16);
+    };
     // t_w(tt) accumulators -> f16 rows [ru_pad, ru_pad + rw_pad) of the S2 B operand.  Runs one step ahead of its use
     // (S1w has no recurrence), at the tail of the previous step's epilogue, so it is never on the critical path.
     auto e1w = [&](uint32_t parity) {
       mbar_wait(bar(BAR_S1W_FULL), parity);
       tc_fence_after();
-      uint32_t aw[16];
+      uint32_t aw[CPT];
 #pragma unroll 1
       for (int mt = 0; mt < e1w_tiles; ++mt) {
-        tmem_ld16(tm_w + (uint32_t)mt * 32u, aw);
+        load_cols(tm_w + (uint32_t)(mt * NS), aw);
         tmem_ld_wait();
-        if ((w_st >> mt) & 1u) store_t_row(tb_w + (uint32_t)mt * 8192u, aw, (w_live >> mt) & 1u);
+        if ((w_st >> mt) & 1u) store_row(tb_w + (uint32_t)mt * kRowBlk, aw, (w_live >> mt) & 1u);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -867,23 +869,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
     if (p.has_s1w) e1w(0u);
     uint32_t s2_use = 0;
     for (int t = 0; t < n_steps; ++t) {
-      // ---- epilogue 1: t_u / t_w accumulators -> f16 rows of the S2 B operand; Dense-top rows -> y(t-1) ----
+      // ---- epilogue 1: t_u accumulators -> f16 rows of the S2 B operand; Dense-top row -> y(t-1) ----
       mbar_wait(bar(BAR_S1_FULL), (uint32_t)t & 1u);
       tc_fence_after();
       if (threadIdx.x == 128) TC_STAMP(8);   // EPI: S1 accumulators seen
-      float yv[16];
+      float yv[CPT];
       {
-        uint32_t au[16];
+        uint32_t au[CPT];
         const bool step_live = t < T;   // the flush pass (t == T) only extracts the Dense-top row
 #pragma unroll 1
         for (int mt = 0; mt < e1u_tiles; ++mt) {
-          tmem_ld16(tm_u + (uint32_t)mt * 32u, au);
+          load_cols(tm_u + (uint32_t)(mt * NS), au);
           tmem_ld_wait();
           if (threadIdx.x == 128) TC_STAMP(0);   // EPI: S1 accumulator tile in registers
-          if (((u_st >> mt) & 1u) && step_live) store_t_row(tb_u + (uint32_t)mt * 8192u, au, (u_live >> mt) & 1u);
+          if (((u_st >> mt) & 1u) && step_live) store_row(tb_u + (uint32_t)mt * kRowBlk, au, (u_live >> mt) & 1u);
           if (mt == y_mt) {   // keep the Dense-top row; it is written out after the t operand has been published
 #pragma unroll
-            for (int n = 0; n < 16; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
+            for (int n = 0; n < CPT; ++n) yv[n] = __uint_as_float(au[n]) + y_bias;
           }
         }
       }
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (t > 0 && y_ptr != nullptr) {   // Dense top of step t-1 (off the critical path: after the arrive)
         float* yp = y_ptr + (size_t)(t - 1) * p.n_dense;
 #pragma unroll
-        for (int n = 0; n < 16; ++n)
+        for (int n = 0; n < CPT; ++n)
           if (n < y_valid) yp[(size_t)n * y_seq_stride] = yv[n];
       }
       if (t == T) break;
@@ -908,40 +910,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       if (p.store_h && t > 0) mbar_wait(bar(BAR_H_STORED), (uint32_t)(t - 1) & 1u);
 #pragma unroll
       for (int ub = 0; ub < NUB; ++ub) {
+        const uint32_t use = s2_use + (uint32_t)ub;
+        const uint32_t buf = kS2Bufs == 2 ? (use & 1u) : 0u, turn = kS2Bufs == 2 ? (use >> 1) : use;
+        mbar_wait(bar(BAR_S2_FULL0 + buf), turn & 1u);   // NS=64: half-buffer A = tiles (i, g)
+        tc_fence_after();
+        if (threadIdx.x == 128) TC_STAMP(10 + 2 * (ub & 1));   // EPI: z block ub seen
+        const uint32_t tb = tm_s2 + buf * (uint32_t)(4 * NS) + lane_addr;   // tile slots: i, g(cell), f, o
+        // staged: (i, g) -> the input product i*g, then (f, o).  Keeps the live accumulator set at 2 x CPT registers
+        // (a 64-sequence tile cannot hold 4 x 32 of them next to 64 cell states) and frees half-buffer A early.
+        float ig[CPT];
         {
-          const uint32_t use = s2_use + (uint32_t)ub;
-          const uint32_t buf = use & 1u;
-          mbar_wait(bar(BAR_S2_FULL0 + buf), (use >> 1) & 1u);
-          tc_fence_after();
-          if (threadIdx.x == 128) TC_STAMP(10 + 2 * (ub & 1));   // EPI: z block ub seen
-          const uint32_t tb = tm_s2 + buf * 128u + lane_addr;
-          uint32_t zi[16], zf[16], zg[16], zo[16];
-          tmem_ld16(tb + 0 * 32, zi);
-          tmem_ld16(tb + 1 * 32, zf);
-          tmem_ld16(tb + 2 * 32, zg);
-          tmem_ld16(tb + 3 * 32, zo);
+          uint32_t zi[CPT], zg[CPT];
+          load_cols(tb + 0u * (uint32_t)NS, zi);
+          load_cols(tb + 1u * (uint32_t)NS, zg);
           tmem_ld_wait();
-          // the accumulators are in registers: hand the TMEM buffer back to the MMA warp right away
-          tc_fence_before();
-          mbar_arrive(bar(BAR_S2_EMPTY0 + buf));
-          float hv[16];
-#pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const float ig = fmaf(0.5f, tanh_approx(__uint_as_float(zi[n]) + bi[ub][0]), 0.5f);
-            const float fg = fmaf(0.5f, tanh_approx(__uint_as_float(zf[n]) + bi[ub][1]), 0.5f);
-            const float gg = tanh_approx(__uint_as_float(zg[n]) + bi[ub][2]);
-            const float og = fmaf(0.5f, tanh_approx(__uint_as_float(zo[n]) + bi[ub][3]), 0.5f);
-            const float c = fmaf(fg, cst[ub][n], ig * gg);
-            cst[ub][n] = c;
-            hv[n] = og * tanh_approx(c);
+          if (kS2Bufs == 1) {
+            tc_fence_before();
+            mbar_arrive(bar(BAR_S2_EMPTY0));
           }
-          sts128(hb_addr + (uint32_t)ub * 8192u, pack_f16(hv[0], hv[1]), pack_f16(hv[2], hv[3]), pack_f16(hv[4], hv[5]), pack_f16(hv[6], hv[7]));
-          sts128(hb_addr + (uint32_t)ub * 8192u + 128u, pack_f16(hv[8], hv[9]), pack_f16(hv[10], hv[11]), pack_f16(hv[12], hv[13]),
-                 pack_f16(hv[14], hv[15]));
-          fence_proxy_async();
-          mbar_arrive(bar(BAR_H_READY + ub));
-          if (threadIdx.x == 128) TC_STAMP(11 + 2 * (ub & 1));   // EPI: block ub done
+#pragma unroll
+          for (int n = 0; n < CPT; ++n)
+            ig[n] = fmaf(0.5f, tanh_approx(__uint_as_float(zi[n]) + bi[ub][0]), 0.5f) * tanh_approx(__uint_as_float(zg[n]) + bi[ub][1]);
         }
+        if (kS2Bufs == 1) {
+          mbar_wait(bar(BAR_S2_FULL1), turn & 1u);         // half-buffer B = tiles (f, o)
+          tc_fence_after();
+        }
+        uint32_t zf[CPT], zo[CPT];
+        load_cols(tb + 2u * (uint32_t)NS, zf);
+        load_cols(tb + 3u * (uint32_t)NS, zo);
+        tmem_ld_wait();
+        // the accumulators are in registers: hand the TMEM buffer back to the MMA warp right away
+        tc_fence_before();
+        mbar_arrive(bar(kS2Bufs == 1 ? BAR_S2_EMPTY1 : BAR_S2_EMPTY0 + buf));
+#pragma unroll
+        for (int j8 = 0; j8 < CPT / 8; ++j8) {
+          float hv[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int n = 8 * j8 + m;
+            const float fg = fmaf(0.5f, tanh_approx(__uint_as_float(zf[n]) + bi[ub][2]), 0.5f);
+            const float og = fmaf(0.5f, tanh_approx(__uint_as_float(zo[n]) + bi[ub][3]), 0.5f);
+            const float c = fmaf(fg, cst[ub][n], ig[n]);
+            cst[ub][n] = c;
+            hv[m] = og * tanh_approx(c);
+          }
+          sts128(hb_addr + (uint32_t)ub * kRowBlk + 128u * (uint32_t)j8, pack_f16(hv[0], hv[1]), pack_f16(hv[2], hv[3]),
+                 pack_f16(hv[4], hv[5]), pack_f16(hv[6], hv[7]));
+        }
+        fence_proxy_async();
+        mbar_arrive(bar(BAR_H_READY + ub));
+        if (threadIdx.x == 128) TC_STAMP(11 + 2 * (ub & 1));   // EPI: block ub done
       }
       s2_use += (uint32_t)nub;
       if (p.store_h) mbar_arrive(bar(BAR_H_DONE));
@@ -991,7 +1010,8 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
       if (j < bu.rank) v = block_left(bu, kk, j);
       else if (j - bu.rank < n_dense) v = dense_k[(size_t)kk * n_out + (j - bu.rank)];
     } else {
-      const int n = c.g * H + c.ub * 128 + row;
+      const int gate = (c.g == 1) ? 2 : (c.g == 2) ? 1 : c.g;   // tile slots are ordered i, g(cell), f, o; Keras columns i, f, c, o
+      const int n = gate * H + c.ub * 128 + row;
       const int kk = c.k0 + k;
       if (c.part == 0) {            // recurrent part: row kk of R_u
         if (kk < bu.rank) v = block_right(bu, kk, n);
@@ -1002,7 +1022,7 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
         for (int j = 0; j < bw.rank; ++j) acc = fmaf(block_left(bw, kk, j), block_right(bw, j, n), acc);
         v = acc;
       }
-      if (c.g != 2) v *= 0.5f;   // sigmoid gates: tanh(z/2) form
+      if (gate != 2) v *= 0.5f;   // sigmoid gates: tanh(z/2) form
     }
     const size_t off = (size_t)(row / 8) * ((size_t)c.kc * 16) + (size_t)(k / 8) * 128 + (size_t)(row % 8) * 16 + (size_t)(k % 8) * 2;
     out[off / 2] = __float2half_rn(v);
@@ -1010,33 +1030,35 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ bias, int H, float* __restrict__ img) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // [ub][g][128]
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // [ub][slot][128], slots ordered i, g(cell), f, o
   if (idx >= 4 * H) return;
-  const int ub = idx / 512, g = (idx / 128) & 3, i = idx & 127;
+  const int ub = idx / 512, slot = (idx / 128) & 3, i = idx & 127;
+  const int g = (slot == 1) ? 2 : (slot == 2) ? 1 : slot;
   img[idx] = bias[g * H + ub * 128 + i] * (g != 2 ? 0.5f : 1.f);
 }
 
 // x (B,T,D) fp32 -> f16 activation tile images [cta][t] (K = Dpad16).  One block = one batch tile x TT steps:
 // coalesced reads of each sequence's TT*D contiguous floats into smem, then contiguous 16-byte tile writes.
-__global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x, int B, int T, int D, int Dpad, int TT,
+__global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x, int B, int T, int D, int Dpad, int TT, int ns,
                                                      uint8_t* __restrict__ img) {
-  extern __shared__ float xs[];   // [kN][TT*D]
-  const uint32_t tile = act_tile_bytes(Dpad);
+  extern __shared__ float xs[];   // [ns][TT*D]
+  const uint32_t tile = act_tile_bytes(Dpad, ns);
   const int cta = blockIdx.y;
   const int t0 = blockIdx.x * TT;
   const int nt = imin(TT, T - t0);
   const int row = nt * D;   // contiguous floats per sequence
-  for (int idx = threadIdx.x; idx < kN * row; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < ns * row; idx += blockDim.x) {
     const int n = idx / row, o = idx - n * row;
-    const int b = cta * kN + n;
+    const int b = cta * ns + n;
     xs[n * (TT * D) + o] = (b < B) ? x[((size_t)b * T + t0) * D + o] : 0.f;
   }
   __syncthreads();
   // one 16-byte store = 8 consecutive sequences of one (t, k)
-  const int per_t = Dpad * (kN / 8);
+  const int ngr = ns / 8;                 // 16-byte words per (t, k): one per group of 8 sequences
+  const int per_t = Dpad * ngr;
   for (int idx = threadIdx.x; idx < nt * per_t; idx += blockDim.x) {
     const int tt = idx / per_t, rem = idx - tt * per_t;
-    const int kg = rem / 32, w = rem - kg * 32;   // within a k-group of 8: [n-group (4)][k%8 (8)] 16-byte words
+    const int kg = rem / (8 * ngr), w = rem - kg * (8 * ngr);   // within a k-group of 8: [n-group][k%8] 16-byte words
     const int ng = w / 8, k = kg * 8 + (w & 7);
     uint32_t v[4];
 #pragma unroll
@@ -1046,21 +1068,21 @@ __global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x
       const float c = k < D ? xs[(n + 1) * (TT * D) + tt * D + k] : 0.f;
       v[i] = pack_f16(a, c);
     }
-    *reinterpret_cast<uint4*>(img + ((size_t)cta * T + t0 + tt) * tile + act_offset(k, ng * 8)) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(img + ((size_t)cta * T + t0 + tt) * tile + act_offset(k, ng * 8, ns)) = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
 
 // last layer h tiles -> y (B,T,H) fp32 (only when the model has no Dense top; the Dense top is fused otherwise)
-__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int H, float* __restrict__ y) {
-  const uint32_t tile = act_tile_bytes(H);
+__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int H, int ns, float* __restrict__ y) {
+  const uint32_t tile = act_tile_bytes(H, ns);
   const int cta = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int item = blockIdx.x * nw + warp; item < T * kN; item += gridDim.x * nw) {
-    const int t = item / kN, n = item - t * kN;
-    const int b = cta * kN + n;
+  for (int item = blockIdx.x * nw + warp; item < T * ns; item += gridDim.x * nw) {
+    const int t = item / ns, n = item - t * ns;
+    const int b = cta * ns + n;
     if (b >= B) continue;
     const uint8_t* tp = img + ((size_t)cta * T + t) * tile;
-    for (int k = lane; k < H; k += 32) y[((size_t)b * T + t) * H + k] = __half2float(*reinterpret_cast<const __half*>(tp + act_offset(k, n)));
+    for (int k = lane; k < H; k += 32) y[((size_t)b * T + t) * H + k] = __half2float(*reinterpret_cast<const __half*>(tp + act_offset(k, n, ns)));
   }
 }
 
@@ -1079,6 +1101,7 @@ struct TcLayerImg {
 struct TcState {
   TcLayerImg layers[kMaxLayers];
   int n_layers = 0;
+  int ns = 0;   // tile width the images / plans were built for (the chunk order depends on resident vs streamed)
 };
 
 // Per-device scratch shared by every handle: the FP16 image of x and the two ping-pong hidden-sequence images
@@ -1104,7 +1127,7 @@ void tc_free(TcState* s) {
   delete s;
 }
 
-static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const char** why) {
+static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p, const char** why) {
   const LayerDesc& L = md.layers[l];
   if (L.n_blocks != 2) { *why = "only merged (non-split) cell forms run on the tensor-core engine"; return false; }
   const Block& bw = L.blocks[0];
@@ -1115,6 +1138,7 @@ static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const 
   if (bu.rank > 256 || bw.rank > 256) { *why = "ranks above 256 are not supported by the tensor-core engine"; return false; }
   const bool last = (l == md.n_layers - 1);
   p = TcLayerParams{};
+  p.ns = ns;
   p.H = H;
   p.ru = bu.rank;
   p.rw = bw.rank;
@@ -1124,6 +1148,8 @@ static bool tc_layer_params(const ModelDesc& md, int l, TcLayerParams& p, const 
   p.store_h = p.n_dense > 0 ? 0 : 1;
   p.rows_u = round_up(p.ru + p.n_dense, 8);
   if (p.rows_u > 384) { *why = "rank + Dense-top outputs exceed three 128-row MMA tiles"; return false; }
+  if (ns == 64 && H > 256) { *why = "64-sequence tiles support units <= 256"; return false; }
+  if (ns == 64 && p.rows_u > 256) { *why = "64-sequence tiles hold two 128-row S1 tiles in TMEM (rank + Dense-top outputs <= 256)"; return false; }
   if (l == 0) {
     if (L.d_in > 64) { *why = "layer-0 input_dim above 64 is not supported by the tensor-core engine yet"; return false; }
     p.Kin = round_up(L.d_in, 16);
@@ -1162,9 +1188,27 @@ bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why) {
   if (!(a.flags & SVDLSTM_RETURN_SEQUENCES)) { *why = "return_sequences=False is an FP32-engine feature"; return false; }
   for (int l = 0; l < md.n_layers; ++l) {
     TcLayerParams p;
-    if (!tc_layer_params(md, l, p, why)) return false;
+    if (!tc_layer_params(md, l, 32, p, why)) return false;
   }
   return true;
+}
+
+// one layer launch; 64-sequence tiles exist for units <= 256 only (32 cell states per unit block per thread)
+template <int NUB, bool STREAM>
+static int tc_launch_layer(const TcLayerParams& p, int n_cta, uint32_t smem_bytes, cudaStream_t stream) {
+  if (p.ns == 64) {
+    if constexpr (NUB <= 2) {
+      SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB, STREAM, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      lstm_tc_layer_kernel<NUB, STREAM, 64><<<n_cta, kTcThreads, smem_bytes, stream>>>(p);
+      return 0;
+    } else {
+      set_error("tensor-core engine: 64-sequence tiles need units <= 256");
+      return -1;
+    }
+  }
+  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB, STREAM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  lstm_tc_layer_kernel<NUB, STREAM, 32><<<n_cta, kTcThreads, smem_bytes, stream>>>(p);
+  return 0;
 }
 
 int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
@@ -1176,11 +1220,22 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   }
   TcState* st = *state;
   const int L = md.n_layers;
+  // sequences per CTA tile: 32 by default; 64 amortises the per-step costs over twice the sequences (SVDLSTM_TC_NS overrides)
+  int ns = 32;
+  if (const char* e = getenv("SVDLSTM_TC_NS")) ns = atoi(e) == 64 ? 64 : 32;
+  if (ns == 64) {
+    for (int l = 0; l < L; ++l) {
+      TcLayerParams q;
+      if (!tc_layer_params(md, l, 64, q, &why)) { ns = 32; break; }
+    }
+  }
+  if (st->ns != ns) weights_dirty = true;
   if (weights_dirty) {
+    st->ns = ns;
     for (int l = 0; l < L; ++l) {
       TcLayerImg& li = st->layers[l];
       TcLayerParams p;
-      SVD_REQUIRE(tc_layer_params(md, l, p, &why), "tensor-core engine: %s", why);
+      SVD_REQUIRE(tc_layer_params(md, l, ns, p, &why), "tensor-core engine: %s", why);
       if (li.wimg) cudaFree(li.wimg);
       if (li.bias) cudaFree(li.bias);
       li.wimg = nullptr;
@@ -1228,7 +1283,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     SVD_CUDA_TRY(cudaGetLastError());
   }
   const int B = a.B, T = a.T;
-  const int n_cta = (B + kN - 1) / kN;
+  const int n_cta = (B + ns - 1) / ns;
   // workspaces (per device, shared by all handles)
   int dev = 0;
   SVD_CUDA_TRY(cudaGetDevice(&dev));
@@ -1238,7 +1293,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   ws->used = true;
   ws->last_stream = stream;
   const int Dpad = st->layers[0].prm.Kin;
-  const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad);
+  const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad, ns);
   if (ws->xseq_bytes < xbytes) {
     if (ws->xseq) {
       SVD_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1249,7 +1304,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   }
   for (int l = 0; l < L; ++l) {
     if (!st->layers[l].prm.store_h) continue;
-    const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H);
+    const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H, ns);
     const int slot = l & 1;
     if (ws->seq_bytes[slot] < hb) {
       if (ws->seq[slot]) {
@@ -1263,7 +1318,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   {
     const int D = md.input_dim;
     const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
-    pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * kN * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, ws->xseq);
+    pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * ns * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, ns, ws->xseq);
   }
   ++nl;
   static long long* dbg_buf = nullptr;
@@ -1282,32 +1337,23 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     p.y = a.y;
     p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
-    bool launched = true;
-#define SVD_TC_LAUNCH(NUB_, STREAM_)                                                                                               \
-  do {                                                                                                                              \
-    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB_, STREAM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
-    lstm_tc_layer_kernel<NUB_, STREAM_><<<n_cta, kTcThreads, sp.total, stream>>>(p);                                                \
-  } while (0)
+    int lrc = -1;
     switch ((p.H / 128) * 2 + (p.streaming ? 1 : 0)) {
-      case 2: SVD_TC_LAUNCH(1, false); break;
-      case 3: SVD_TC_LAUNCH(1, true); break;
-      case 4: SVD_TC_LAUNCH(2, false); break;
-      case 5: SVD_TC_LAUNCH(2, true); break;
-      case 6: SVD_TC_LAUNCH(3, false); break;
-      case 7: SVD_TC_LAUNCH(3, true); break;
-      case 8: SVD_TC_LAUNCH(4, false); break;
-      case 9: SVD_TC_LAUNCH(4, true); break;
-      default: launched = false;
+      case 2: lrc = tc_launch_layer<1, false>(p, n_cta, sp.total, stream); break;
+      case 3: lrc = tc_launch_layer<1, true>(p, n_cta, sp.total, stream); break;
+      case 4: lrc = tc_launch_layer<2, false>(p, n_cta, sp.total, stream); break;
+      case 5: lrc = tc_launch_layer<2, true>(p, n_cta, sp.total, stream); break;
+      case 6: lrc = tc_launch_layer<3, false>(p, n_cta, sp.total, stream); break;
+      case 7: lrc = tc_launch_layer<3, true>(p, n_cta, sp.total, stream); break;
+      case 8: lrc = tc_launch_layer<4, false>(p, n_cta, sp.total, stream); break;
+      case 9: lrc = tc_launch_layer<4, true>(p, n_cta, sp.total, stream); break;
+      default: set_error("tensor-core engine: unsupported units %d", p.H);
     }
-#undef SVD_TC_LAUNCH
-    if (!launched) {
-      set_error("tensor-core engine: unsupported units %d", p.H);
-      return -1;
-    }
+    if (lrc != 0) return lrc;
     ++nl;
   }
   if (st->layers[L - 1].prm.store_h) {   // no Dense top: the output is the last hidden sequence itself
-    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, a.y);
+    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, ns, a.y);
     ++nl;
   }
   SVD_CUDA_TRY(cudaGetLastError());
