@@ -90,6 +90,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -404,15 +411,18 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 }
 
 #ifdef SVDLSTM_TC_TIMELINE
-#define TC_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && t < 64) p.dbg[t * 16 + (slot)] = clock64(); } while (0)
-#define TC_CHUNK_STAMP() do { if (p.dbg != nullptr && blockIdx.x == 0 && dbg_t == 20 && dbg_n < 250) p.dbg[64 * 16 + dbg_n++] = clock64(); } while (0)
+#define TC_STAMP(slot) do { if (p.dbg != nullptr && stamp_cta && t < 64) p.dbg[t * 16 + (slot)] = clock64(); } while (0)
+#define TC_CHUNK_STAMP() do { if (p.dbg != nullptr && stamp_cta && dbg_t == 20 && dbg_n < 250) p.dbg[64 * 16 + dbg_n++] = clock64(); } while (0)
 #else
 #define TC_STAMP(slot) do { } while (0)
 #define TC_CHUNK_STAMP() do { } while (0)
 #endif
 
+// One CTA = one layer x one tile of NS sequences x all T steps.  prog_in / prog_out (layer-pipelined launch only): per-tile
+// step counters in global memory through which the previous layer's CTA publishes -- and this CTA announces -- how many
+// hidden-sequence tiles have landed in the hand-off image.
 template <int NUB, bool STREAM, int NS>
-__global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
+__device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta) {
   constexpr int CPT = NS / 2;                 // accumulator columns per epilogue thread (two warps per TMEM lane quarter)
   constexpr uint32_t kRowBlk = (uint32_t)NS * 256u;   // bytes of 128 K-rows of an activation tile (16 k-groups)
   constexpr uint32_t kK64 = (uint32_t)NS * 8u;        // descriptor-lo step of 64 K-rows (8 k-groups of NS*16 bytes)
@@ -421,7 +431,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   const TcSmemPlan sp = tc_plan(p);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta = blockIdx.x;
   const int H = p.H, T = p.T;
   constexpr int nub = NUB;
   const int nst = p.in_stages;
@@ -527,6 +536,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
       uint32_t ld_n = 0;     // how many times that stage has been used
       int ld_t = 0;          // step index of the next tile to load
       auto load_next = [&]() {
+        if (prog_in != nullptr) {   // layer-pipelined launch: the previous layer must have published tile ld_t
+          if (ld_acquire_gpu(prog_in) <= ld_t) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(prog_in) <= ld_t)
+              if (clock64() - t0 > 8000000000LL) __trap();
+          }
+          fence_proxy_async_all();   // the tile was written through the async proxy of another SM
+        }
         if (ld_n > 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
         mbar_expect_tx(bar(BAR_IN_FULL + ld_s), in_tile);
         bulk_g2s(sbase + sp.inbuf + ld_s * in_tile, src + (size_t)ld_t * in_tile, in_tile, bar(BAR_IN_FULL + ld_s));
@@ -545,6 +562,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
           bulk_commit();
           bulk_wait_read0();
           mbar_arrive(bar(BAR_H_STORED));
+          if (prog_out != nullptr) {   // publish: the tile is complete in global memory, then the step counter
+            bulk_wait_all0();
+            fence_proxy_async_all();
+            st_release_gpu(prog_out, t + 1);
+          }
         }
       }
       if (p.store_h) bulk_wait_all0();
@@ -973,6 +995,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLa
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  (void)stamp_cta;
+}
+
+// layers launched one after the other (any batch size): grid = tiles of one layer
+template <int NUB, bool STREAM, int NS>
+__global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
+  tc_layer_body<NUB, STREAM, NS>(p, (int)blockIdx.x, nullptr, nullptr, blockIdx.x == 0);
+}
+
+// ALL layers in one (cooperative, fully co-resident) launch: CTA b runs layer b / n_tiles on tile b % n_tiles and the layers
+// form a pipeline over time -- layer l+1 consumes h_l(t) a few steps after layer l produced it.  With L layers x B/NS tiles
+// <= the SM count this doubles the sequences per SM (NS = 64) without idling SMs, which halves the shared-memory-port cost
+// per sequence of re-streamed weights.
+struct TcPipeParams {
+  TcLayerParams layer[kMaxLayers];
+  int n_layers, n_tiles;
+  int* progress;   // [n_layers][n_tiles] steps published, zeroed before the launch
+};
+template <int NUB, int NS>
+__global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_pipe_kernel(const __grid_constant__ TcPipeParams pp) {
+  const int layer = (int)blockIdx.x / pp.n_tiles, tile = (int)blockIdx.x - layer * pp.n_tiles;
+  const TcLayerParams& p = pp.layer[layer];
+  const int* prog_in = layer > 0 ? pp.progress + (size_t)(layer - 1) * pp.n_tiles + tile : nullptr;
+  int* prog_out = layer + 1 < pp.n_layers ? pp.progress + (size_t)layer * pp.n_tiles + tile : nullptr;
+  if (p.streaming) tc_layer_body<NUB, true, NS>(p, tile, prog_in, prog_out, tile == 0);
+  else tc_layer_body<NUB, false, NS>(p, tile, prog_in, prog_out, tile == 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1108,8 +1156,10 @@ struct TcState {
 // (C3: 134 MB + 2 x 2.1 GB).  A rank sweep holds hundreds of handles; per-handle scratch would not fit.  Work on
 // one stream is ordered, so sharing is safe there; a forward on a different stream first drains the previous one.
 struct TcWorkspace {
-  uint8_t* seq[2] = {nullptr, nullptr};
-  size_t seq_bytes[2] = {0, 0};
+  uint8_t* seq[kMaxLayers] = {};     // hidden-sequence images: slots l & 1 (layers in turn) or l (layers pipelined)
+  size_t seq_bytes[kMaxLayers] = {};
+  int* progress = nullptr;           // layer-pipelined launch: [layer][tile] published-step counters
+  size_t progress_elems = 0;
   uint8_t* xseq = nullptr;
   size_t xseq_bytes = 0;
   cudaStream_t last_stream = nullptr;
@@ -1211,6 +1261,16 @@ static int tc_launch_layer(const TcLayerParams& p, int n_cta, uint32_t smem_byte
   return 0;
 }
 
+// all layers in one cooperative launch (co-residency of every CTA is what makes the inter-layer waits safe)
+template <int NUB, int NS>
+static int tc_launch_pipe(const TcPipeParams& pp, uint32_t smem_bytes, cudaStream_t stream) {
+  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_pipe_kernel<NUB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  void* args[] = {const_cast<TcPipeParams*>(&pp)};
+  SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_tc_pipe_kernel<NUB, NS>), dim3((unsigned)(pp.n_layers * pp.n_tiles)),
+                                           dim3(kTcThreads), args, smem_bytes, stream));
+  return 0;
+}
+
 int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
   const char* why = "";
   int nl = 0;
@@ -1220,14 +1280,35 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   }
   TcState* st = *state;
   const int L = md.n_layers;
-  // sequences per CTA tile: 32 by default; 64 amortises the per-step costs over twice the sequences (SVDLSTM_TC_NS overrides)
+  // Launch shape.  "pipe": all layers in ONE co-resident launch (CTA = layer x tile), possible when layers x tiles fits the
+  // SMs; 64-sequence tiles make that true for twice the batch and halve the per-sequence cost of streamed weights.
+  // "seq": one launch per layer, 32-sequence tiles, any batch.  SVDLSTM_TC_MODE=seq|pipe and SVDLSTM_TC_NS=32|64 override.
+  int n_sm = 148;
+  {
+    int dev0 = 0;
+    SVD_CUDA_TRY(cudaGetDevice(&dev0));
+    SVD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev0));
+  }
+  bool same_h = true;
+  for (int l = 1; l < L; ++l) same_h = same_h && md.layers[l].units == md.layers[0].units;
+  bool ok64 = true;
+  for (int l = 0; l < L; ++l) {
+    TcLayerParams q;
+    if (!tc_layer_params(md, l, 64, q, &why)) ok64 = false;
+  }
+  const char* mode_env = getenv("SVDLSTM_TC_MODE");
+  const char* ns_env = getenv("SVDLSTM_TC_NS");
+  const bool allow_pipe = L >= 2 && same_h && !(mode_env && mode_env[0] == 's');
   int ns = 32;
-  if (const char* e = getenv("SVDLSTM_TC_NS")) ns = atoi(e) == 64 ? 64 : 32;
-  if (ns == 64) {
-    for (int l = 0; l < L; ++l) {
-      TcLayerParams q;
-      if (!tc_layer_params(md, l, 64, q, &why)) { ns = 32; break; }
-    }
+  bool pipe = false;
+  if (ns_env) {
+    ns = (atoi(ns_env) == 64 && ok64) ? 64 : 32;
+    pipe = allow_pipe && L * ((a.B + ns - 1) / ns) <= n_sm;
+  } else if (allow_pipe && L * ((a.B + 31) / 32) <= n_sm) {
+    pipe = true;
+  } else if (allow_pipe && ok64 && L * ((a.B + 63) / 64) <= n_sm) {
+    pipe = true;
+    ns = 64;
   }
   if (st->ns != ns) weights_dirty = true;
   if (weights_dirty) {
@@ -1305,7 +1386,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   for (int l = 0; l < L; ++l) {
     if (!st->layers[l].prm.store_h) continue;
     const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H, ns);
-    const int slot = l & 1;
+    const int slot = pipe ? l : (l & 1);
     if (ws->seq_bytes[slot] < hb) {
       if (ws->seq[slot]) {
         SVD_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1314,6 +1395,18 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
       SVD_CUDA_TRY(cudaMalloc(&ws->seq[slot], hb));
       ws->seq_bytes[slot] = hb;
     }
+  }
+  if (pipe) {
+    const size_t need = (size_t)L * n_cta;
+    if (ws->progress_elems < need) {
+      if (ws->progress) {
+        SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(ws->progress);
+      }
+      SVD_CUDA_TRY(cudaMalloc(&ws->progress, sizeof(int) * need));
+      ws->progress_elems = need;
+    }
+    SVD_CUDA_TRY(cudaMemsetAsync(ws->progress, 0, sizeof(int) * need, stream));
   }
   {
     const int D = md.input_dim;
@@ -1327,16 +1420,24 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     SVD_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * kDbgPerLayer * kMaxLayers));
     SVD_CUDA_TRY(cudaMemset(dbg_buf, 0, sizeof(long long) * kDbgPerLayer * kMaxLayers));
   }
+  TcPipeParams pp{};
+  uint32_t pipe_smem = 0;
   for (int l = 0; l < L; ++l) {
     TcLayerParams p = st->layers[l].prm;
     p.T = T;
     p.B = B;
     p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
-    p.in_seq = (l == 0) ? ws->xseq : ws->seq[(l - 1) & 1];
-    p.out_seq = p.store_h ? ws->seq[l & 1] : nullptr;
+    const int in_slot = pipe ? l - 1 : ((l - 1) & 1), out_slot = pipe ? l : (l & 1);
+    p.in_seq = (l == 0) ? ws->xseq : ws->seq[in_slot];
+    p.out_seq = p.store_h ? ws->seq[out_slot] : nullptr;
     p.y = a.y;
     p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
+    if (pipe) {
+      pp.layer[l] = p;
+      pipe_smem = sp.total > pipe_smem ? sp.total : pipe_smem;
+      continue;
+    }
     int lrc = -1;
     switch ((p.H / 128) * 2 + (p.streaming ? 1 : 0)) {
       case 2: lrc = tc_launch_layer<1, false>(p, n_cta, sp.total, stream); break;
@@ -1352,8 +1453,25 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     if (lrc != 0) return lrc;
     ++nl;
   }
+  if (pipe) {
+    pp.n_layers = L;
+    pp.n_tiles = n_cta;
+    pp.progress = ws->progress;
+    int lrc = -1;
+    switch ((md.layers[0].units / 128) * 2 + (ns == 64 ? 1 : 0)) {
+      case 2: lrc = tc_launch_pipe<1, 32>(pp, pipe_smem, stream); break;
+      case 3: lrc = tc_launch_pipe<1, 64>(pp, pipe_smem, stream); break;
+      case 4: lrc = tc_launch_pipe<2, 32>(pp, pipe_smem, stream); break;
+      case 5: lrc = tc_launch_pipe<2, 64>(pp, pipe_smem, stream); break;
+      case 6: lrc = tc_launch_pipe<3, 32>(pp, pipe_smem, stream); break;
+      case 8: lrc = tc_launch_pipe<4, 32>(pp, pipe_smem, stream); break;
+      default: set_error("tensor-core engine: unsupported units %d for the pipelined launch", md.layers[0].units);
+    }
+    if (lrc != 0) return lrc;
+    ++nl;
+  }
   if (st->layers[L - 1].prm.store_h) {   // no Dense top: the output is the last hidden sequence itself
-    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[(L - 1) & 1], B, T, st->layers[L - 1].prm.H, ns, a.y);
+    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[pipe ? L - 1 : ((L - 1) & 1)], B, T, st->layers[L - 1].prm.H, ns, a.y);
     ++nl;
   }
   SVD_CUDA_TRY(cudaGetLastError());
