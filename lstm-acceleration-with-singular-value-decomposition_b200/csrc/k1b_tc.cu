@@ -1134,6 +1134,44 @@ __global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T,
   }
 }
 
+// Dense / TimeDistributed(Dense) top from the last hidden-sequence image (only when it could not be fused into S1u):
+// y[b, t, o] = sum_k h[k][b] W[k][o] + bias[o].  One block per (step, tile): the 16-byte words of the tile (8 sequences of
+// one unit each) are read coalesced; thread (q, n-group) accumulates a quarter of the units for 8 sequences.
+__global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restrict__ img, int B, int T, int H, int ns,
+                                                        const float* __restrict__ dk, const float* __restrict__ db, int n_out,
+                                                        float* __restrict__ y) {
+  __shared__ float part[64][8][8];   // [k-slice (<= 64)][n-group][sequence in group]
+  const uint32_t tile = act_tile_bytes(H, ns);
+  const int cta = blockIdx.y, t = blockIdx.x;
+  const int ngr = ns / 8, nks = 256 / ngr;          // n-groups, k-slices
+  const int ng = threadIdx.x % ngr, ks = threadIdx.x / ngr;
+  const uint8_t* tp = img + ((size_t)cta * T + t) * tile;
+  for (int o = 0; o < n_out; ++o) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = ks; k < H; k += nks) {
+      const uint4 v = *reinterpret_cast<const uint4*>(tp + act_offset(k, ng * 8, ns));
+      const float w = dk[(size_t)k * n_out + o];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        acc[2 * i] = fmaf(f.x, w, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(f.y, w, acc[2 * i + 1]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[ks][ng][i] = acc[i];
+    __syncthreads();
+    if ((int)threadIdx.x < ns) {
+      const int n = threadIdx.x, b = cta * ns + n;
+      float sum = db[o];
+      for (int s2 = 0; s2 < nks; ++s2) sum += part[s2][n / 8][n % 8];
+      if (b < B) y[((size_t)b * T + t) * n_out + o] = sum;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1194,12 +1232,13 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   p.rw = bw.rank;
   p.ru_pad = round_up(bu.rank, 16);
   p.has_s1w = l > 0;
-  p.n_dense = (last && md.n_out > 0) ? md.n_out : 0;
+  // The Dense top rides in spare rows of the S1u tiles when they fit TMEM (3 tiles of 128 rows at 32-sequence tiles, 2 at
+  // 64); otherwise the layer stores its hidden sequence and dense_top_kernel finishes the job.
+  const int s1_rows_max = ns == 64 ? 256 : 384;
+  p.n_dense = (last && md.n_out > 0 && round_up(bu.rank + md.n_out, 8) <= s1_rows_max) ? md.n_out : 0;
   p.store_h = p.n_dense > 0 ? 0 : 1;
   p.rows_u = round_up(p.ru + p.n_dense, 8);
-  if (p.rows_u > 384) { *why = "rank + Dense-top outputs exceed three 128-row MMA tiles"; return false; }
   if (ns == 64 && H > 256) { *why = "64-sequence tiles support units <= 256"; return false; }
-  if (ns == 64 && p.rows_u > 256) { *why = "64-sequence tiles hold two 128-row S1 tiles in TMEM (rank + Dense-top outputs <= 256)"; return false; }
   if (l == 0) {
     if (L.d_in > 64) { *why = "layer-0 input_dim above 64 is not supported by the tensor-core engine yet"; return false; }
     p.Kin = round_up(L.d_in, 16);
@@ -1470,8 +1509,13 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     if (lrc != 0) return lrc;
     ++nl;
   }
-  if (st->layers[L - 1].prm.store_h) {   // no Dense top: the output is the last hidden sequence itself
-    unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(ws->seq[pipe ? L - 1 : ((L - 1) & 1)], B, T, st->layers[L - 1].prm.H, ns, a.y);
+  if (st->layers[L - 1].prm.store_h) {
+    const uint8_t* last_seq = ws->seq[pipe ? L - 1 : ((L - 1) & 1)];
+    if (md.n_out > 0)      // Dense top that did not fit the S1u tiles
+      dense_top_kernel<<<dim3((unsigned)T, (unsigned)n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, ns, md.dense_kernel,
+                                                                              md.dense_bias, md.n_out, a.y);
+    else                   // no Dense top: the output is the last hidden sequence itself
+      unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, ns, a.y);
     ++nl;
   }
   SVD_CUDA_TRY(cudaGetLastError());
