@@ -346,8 +346,8 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
                 "peak_source": pk["source"] + " (cuBLAS bf16 sustained; f16 runs at the same tensor rate)",
-                "kernel": "lstm_tc_layer_kernel x%d layers (one forward = one 'launch' here; pack_x included in the time)" % a.layers
-                          if eng_id == 3 else eng_name,
+                "kernel": "lstm_tc_pipe_kernel: all %d layers in one co-resident launch, 64-sequence tiles (one forward = pack_x + this launch)"
+                          % a.layers if eng_id == 3 else eng_name,
                 "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms,
                 "hbm_bytes_algorithmic": int(B * T * (D * 4 + 4) + (a.layers - 1) * 2 * B * T * a.hidden * 2 + B * T * D * 2 * 2)}
     line = {"metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": value, "unit": "sequence-timesteps/s", "n_gpus": world,

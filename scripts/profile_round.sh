@@ -11,7 +11,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.s
 for rk in 128 32; do
   CMD="python scripts/tc_time.py $rk 4096 128"
   $CMD > $O/plain_tc_$rk.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:lstm_tc_layer_kernel -s 2 -c 2 -f -o $O/tc_layer_rank${rk}_$R $CMD > $O/ncu_tc_$rk.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:lstm_tc_ -s 2 -c 1 -f -o $O/tc_layer_rank${rk}_$R $CMD > $O/ncu_tc_$rk.log 2>&1
 done
 CMD="python scripts/prof_batch1.py"
 $CMD > $O/plain_b1.log 2>&1 && \
