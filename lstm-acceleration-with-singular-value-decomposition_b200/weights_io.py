@@ -7,7 +7,10 @@ code/load_preprocess.py:93-126 writes them un-transposed; ``transposed=`` select
 """
 from __future__ import annotations
 
+import io
+import json
 import os
+import zipfile
 
 import numpy as np
 
@@ -87,3 +90,59 @@ def synthetic_layers(D, H, L, seed=0, n_out=1):
     lim = math.sqrt(6.0 / (H + n_out))
     dense = (rng.uniform(-lim, lim, size=(H, n_out)).astype(np.float32), np.zeros(n_out, np.float32))
     return layers, dense
+
+
+def save_model_weights_json(layers, dense, path):
+    """code/load_preprocess.py:80-90 layout: {"layer<i>": [get_weights() arrays as nested lists]}, LSTM layers then the Dense top."""
+    data = {}
+    for i, (W, U, b) in enumerate(layers):
+        data["layer%d" % i] = [np.asarray(W).tolist(), np.asarray(U).tolist(), np.asarray(b).tolist()]
+    data["layer%d" % len(layers)] = [np.asarray(dense[0]).tolist(), np.asarray(dense[1]).tolist()]
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(data, f, ensure_ascii=False, indent=4)
+
+
+def load_model_weights_json(path):
+    """Inverse of save_model_weights_json (and reader of the reference's own JSON export)."""
+    with open(path, encoding="utf-8") as f:
+        data = json.load(f)
+    keys = sorted(data, key=lambda k: int(k[len("layer"):]))
+    layers = []
+    for k in keys[:-1]:
+        W, U, b = (np.asarray(a, np.float32) for a in data[k])
+        layers.append((W, U, b))
+    dk, db = (np.asarray(a, np.float32) for a in data[keys[-1]])
+    return layers, (dk.reshape(-1, dk.shape[-1] if dk.ndim > 1 else 1), db.reshape(-1))
+
+
+def load_model_weights_zip(path, transposed=True):
+    """The shipped code/model_weights.zip: the same per-gate CSV tree as code/model_weights/ (CRLF line ends), read
+    without unpacking.  Returns the load_model_weights_csv structure."""
+    with zipfile.ZipFile(path) as z:
+        names = [n for n in z.namelist() if n.lower().endswith(".csv")]
+
+        def find(layer, fname):
+            for n in names:
+                parts = n.replace("\\", "/").split("/")
+                if len(parts) >= 2 and parts[-2] == layer and parts[-1] == fname:
+                    return n
+            raise FileNotFoundError("%s/%s not in %s" % (layer, fname, path))
+
+        def read(layer, fname):
+            return np.loadtxt(io.StringIO(z.read(find(layer, fname)).decode("utf-8")), delimiter=",")
+
+        layer_names = sorted({n.replace("\\", "/").split("/")[-2] for n in names
+                              if n.replace("\\", "/").split("/")[-2].startswith("lstm")})
+        layers = []
+        for name in layer_names:
+            Ws = [np.atleast_2d(read(name, "W%s.csv" % g)) for g in GATES]
+            Us = [np.atleast_2d(read(name, "U%s.csv" % g)) for g in GATES]
+            bs = [read(name, "b%s.csv" % g).ravel() for g in GATES]
+            if transposed:
+                Ws = [w.T for w in Ws]
+                Us = [u.T for u in Us]
+            layers.append((np.concatenate(Ws, 1).astype(np.float32), np.concatenate(Us, 1).astype(np.float32),
+                           np.concatenate(bs).astype(np.float32)))
+        dk = read("dense_top", "weights.csv").reshape(-1, 1).astype(np.float32)
+        db = read("dense_top", "bias.csv").reshape(1).astype(np.float32)
+    return layers, (dk, db)

@@ -55,9 +55,13 @@ def main():
     class Shard:                      # every process generates only its own sequences (seeded per sequence block)
         n_sequences = N
 
-        def __call__(self, l, h):
-            g = torch.Generator(device=dev).manual_seed(1000 + l)
-            return torch.randn(h - l, T, 16, generator=g, device=dev)
+        def __call__(self, l, h):          # blocks of 1024 sequences seeded by block index: the data do not depend on the sharding
+            parts = []
+            for blk in range(l // 1024, (h + 1023) // 1024):
+                g = torch.Generator(device=dev).manual_seed(1000 + blk)
+                xb = torch.randn(1024, T, 16, generator=g, device=dev)
+                parts.append(xb[max(l - blk * 1024, 0):min(h - blk * 1024, 1024)])
+            return torch.cat(parts, 0)
 
     X = Shard()
     x_loc = X(lo, hi)

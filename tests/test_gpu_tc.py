@@ -110,3 +110,36 @@ def test_tc_rejects_what_it_cannot_run():
                                             return_sequences=True)
     with pytest.raises((RuntimeError, ValueError), match="units"):
         sm64(x, engine="tc")
+
+
+def test_tc_launch_shapes_agree(monkeypatch):
+    """The engine picks its launch shape from the batch: all layers in one co-resident launch ("pipe", 32- or 64-sequence
+    tiles) when layers x tiles fits the SMs, else one launch per layer ("seq").  The per-sequence arithmetic is the same
+    in every shape, so the outputs must agree to float32 rounding of the Dense-top sum."""
+    _, sm = _models(256, 2)
+    m = svdlstm.truncate_singular_model(sm, 48)
+    x = torch.randn(200, 24, 16, generator=torch.Generator().manual_seed(9)).cuda()
+    outs = {}
+    for mode, ns in (("seq", "32"), ("seq", "64"), ("pipe", "32"), ("pipe", "64")):
+        monkeypatch.setenv("SVDLSTM_TC_MODE", mode)
+        monkeypatch.setenv("SVDLSTM_TC_NS", ns)
+        outs[(mode, ns)] = m(x, engine="tc").clone()
+    monkeypatch.delenv("SVDLSTM_TC_MODE")
+    monkeypatch.delenv("SVDLSTM_TC_NS")
+    outs["auto"] = m(x, engine="tc").clone()
+    ref = outs[("seq", "32")]
+    for k, v in outs.items():
+        assert float((v - ref).abs().max()) < 2e-6, k
+
+
+def test_tc_three_layers_pipelined_and_large_batch_fallback(oracle):
+    """3 layers x tiles <= SMs runs pipelined with one hand-off image per layer; a batch too large for that falls back
+    to per-layer launches.  Both against the float64 oracle on a sample."""
+    _, sm = _models(128, 3)
+    m = svdlstm.truncate_singular_model(sm, 24)
+    x = np.random.default_rng(10).standard_normal((70, 16, 16)).astype(np.float32)
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc 3 layers pipelined")
+    xb = torch.randn(148 * 64 + 40, 6, 16, generator=torch.Generator().manual_seed(11)).cuda()   # > 148 tiles of 64 per layer
+    yb = m(xb, engine="tc")
+    idx = torch.tensor([0, 31, 32, 63, 64, 5000, 148 * 64 + 39])
+    _check(yb[idx.cuda()].cpu().numpy(), oracle_twin(oracle, m).predict(xb[idx.cuda()].cpu().numpy()), "tc large batch (per-layer launches)")

@@ -118,3 +118,21 @@ def test_regularizer_surface():
         svdlstm.OrthogonalRegularizer(0.1, mode="diag")
     o = svdlstm.OrthogonalRegularizer(0.5)
     assert o.from_raw([0, 0, 3.0, 0], (4, 9)) == 0.5 * 0.5 * 3.0 / 6.0
+
+
+def test_weights_json_roundtrip_and_zip(tmp_path, dropbear_weights):
+    """the reference's JSON export layout (load_preprocess.py:80-90) and the shipped model_weights.zip."""
+    layers, dense = dropbear_weights
+    pth = str(tmp_path / "w.json")
+    svdlstm.save_model_weights_json(layers, dense, pth)
+    l2, d2 = svdlstm.load_model_weights_json(pth)
+    assert len(l2) == len(layers)
+    for (W, U, b), (W2, U2, b2) in zip(layers, l2):
+        assert np.array_equal(W, W2) and np.array_equal(U, U2) and np.array_equal(b, b2)
+    assert np.array_equal(np.asarray(dense[0]).reshape(-1), d2[0].reshape(-1))
+    zp = "/root/reference/code/model_weights.zip"
+    if os.path.exists(zp):
+        lz, dz = svdlstm.load_model_weights_zip(zp)
+        for (W, U, b), (Wz, Uz, bz) in zip(layers, lz):
+            assert np.array_equal(W, Wz) and np.array_equal(U, Uz) and np.array_equal(b, bz)
+        assert np.allclose(np.asarray(dense[1]).reshape(-1), dz[1])
