@@ -20,7 +20,7 @@
 // which is what lets ranks up to 256 (1.3 MB of factors per layer) run on the tensor cores at all.
 // Warp roles: warp 0 = weight streamer, warp 1 = MMA issuer (whole warp converged, one elected lane
 // issues: the divergent single-thread form costs 2-3x more cycles per tcgen05.mma, see
-// scripts/ubench_umma.cu), warp 2 = input ring + hidden-sequence stores (bulk copies), warps 4-11 =
+// scripts/ubench_umma.cu), warp 2 = hidden-sequence stores, warp 3 = input ring (bulk copies), warps 4-11 =
 // epilogue (TMEM -> registers -> activations -> FP16 operand in smem; two warps per TMEM lane quarter,
 // 16 columns each).  Cell state c stays in FP32 registers for all T steps.  The Dense(1) top of the last
 // layer rides in spare rows of the S1u tile (its output for step t-1 falls out of step t's first MMA chain).
@@ -527,15 +527,14 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         }
       }
     }
-  } else if (warp == 2) {
-    // ======================= input ring + hidden-sequence stores ====================================
+  } else if (warp == 3) {
+    // ======================= input ring: one bulk copy per step, as early as the ring allows ======================
     if (lane == 0) {
       const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
-      uint8_t* out = p.store_h ? p.out_seq + (size_t)cta * T * h_tile : nullptr;
       int ld_s = 0;          // ring stage of the next tile to load
       uint32_t ld_n = 0;     // how many times that stage has been used
-      int ld_t = 0;          // step index of the next tile to load
-      auto load_next = [&]() {
+#pragma unroll 1
+      for (int ld_t = 0; ld_t < T; ++ld_t) {
         if (prog_in != nullptr) {   // layer-pipelined launch: the previous layer must have published tile ld_t
           if (ld_acquire_gpu(prog_in) <= ld_t) {
             const long long t0 = clock64();
@@ -547,29 +546,28 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         if (ld_n > 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
         mbar_expect_tx(bar(BAR_IN_FULL + ld_s), in_tile);
         bulk_g2s(sbase + sp.inbuf + ld_s * in_tile, src + (size_t)ld_t * in_tile, in_tile, bar(BAR_IN_FULL + ld_s));
-        ++ld_t;
         if (++ld_s == nst) { ld_s = 0; ++ld_n; }
-      };
-#pragma unroll 1
-      for (int tl = 0; tl < nst - 1 && tl < T; ++tl) load_next();
+      }
+    }
+  } else if (warp == 2) {
+    // ======================= hidden-sequence stores (hand-off to the next layer) ====================================
+    if (lane == 0 && p.store_h) {
+      uint8_t* out = p.out_seq + (size_t)cta * T * h_tile;
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        if (ld_t < T) load_next();
-        if (p.store_h) {
-          // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
-          mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
-          bulk_s2g(out + (size_t)t * h_tile, sbase + sp.hbuf, h_tile);
-          bulk_commit();
-          bulk_wait_read0();
-          mbar_arrive(bar(BAR_H_STORED));
-          if (prog_out != nullptr) {   // publish: the tile is complete in global memory, then the step counter
-            bulk_wait_all0();
-            fence_proxy_async_all();
-            st_release_gpu(prog_out, t + 1);
-          }
+        // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
+        mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
+        bulk_s2g(out + (size_t)t * h_tile, sbase + sp.hbuf, h_tile);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(bar(BAR_H_STORED));
+        if (prog_out != nullptr) {   // publish: the tile is complete in global memory, then the step counter
+          bulk_wait_all0();
+          fence_proxy_async_all();
+          st_release_gpu(prog_out, t + 1);
         }
       }
-      if (p.store_h) bulk_wait_all0();
+      bulk_wait_all0();
     }
   } else if (warp == 1) {
     // ======================= MMA issuer (whole warp, converged; one elected lane issues) =============
@@ -1261,9 +1259,10 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   p.w_slots = 1;
   p.in_stages = 3;
   if (tc_plan(p).total > kSmemCap) p.in_stages = 2;
+  if (tc_plan(p).total > kSmemCap && p.has_s1w) p.in_stages = 1;   // the tile of step t+1 is fetched while step t computes
   if (tc_plan(p).total > kSmemCap) {
     p.streaming = 1;
-    p.in_stages = 2;
+    p.in_stages = p.has_s1w ? 1 : 2;   // every KB goes to the weight ring: its depth must cover the L2 latency
     p.w_slots = kMaxWSlots;
     while (p.w_slots > 3 && tc_plan(p).total > kSmemCap) --p.w_slots;
     if (tc_plan(p).total > kSmemCap) { *why = "activation buffers of this layer do not fit shared memory next to a weight ring"; return false; }
