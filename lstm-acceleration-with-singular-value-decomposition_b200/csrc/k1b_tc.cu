@@ -274,6 +274,8 @@ struct TcLayerParams {
   const uint8_t* wimg;      // weight stream image: [segment W][segment U][segment 2]
   const PackChunk* chunks;  // the same stream as a chunk table (offset, extent) in consumption order: [W | U | 2]
   int n_chunks_w, n_chunks_u, n_chunks_2;
+  const uint32_t* slots;    // streamed: (offset >> 8) | (bytes >> 8) << 16 per ring slot fill, consecutive chunks packed up to 16 KB
+  int n_slots_w, n_slots_u, n_slots_2;
   const float* bias;        // [nub][4][128]; gates i,f,o pre-scaled by 0.5 (sigmoid(x) = 0.5 tanh(x/2) + 0.5)
   const uint8_t* in_seq;    // activation tile images [cta][t], K = Kin
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
@@ -309,7 +311,7 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   s.bars = off; off += 512;
   s.tmem_slot = off; off += 16;
   // streaming: the chunk table (offset, bytes in 256-byte units) lives in smem -- with a 227 KB carve-out there is no L1 to cache it
-  s.ctab = off; off += p.streaming ? (uint32_t)(((p.n_chunks_w + p.n_chunks_u + p.n_chunks_2) * 4 + 15) & ~15) : 0u;
+  s.ctab = off; off += p.streaming ? (uint32_t)(((p.n_slots_w + p.n_slots_u + p.n_slots_2) * 4 + 15) & ~15) : 0u;
   s.total = off;
   return s;
 }
@@ -448,12 +450,9 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)ns * kSlotBytes; i += kTcThreads * 16u)
       *reinterpret_cast<uint4*>(smem + sp.w + i) = make_uint4(0, 0, 0, 0);
   if (STREAM) {
-    const int nc = p.n_chunks_w + p.n_chunks_u + p.n_chunks_2;
+    const int nc = p.n_slots_w + p.n_slots_u + p.n_slots_2;
     uint32_t* ctab = reinterpret_cast<uint32_t*>(smem + sp.ctab);
-    for (int i = threadIdx.x; i < nc; i += kTcThreads) {
-      const PackChunk c = p.chunks[i];
-      ctab[i] = (c.byte_off >> 8) | (((uint32_t)c.rows * (uint32_t)c.kc * 2u) >> 8) << 16;
-    }
+    for (int i = threadIdx.x; i < nc; i += kTcThreads) ctab[i] = p.slots[i];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxWSlots; ++s) {
@@ -502,7 +501,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         // walk the chunk table in consumption order: [W] then per step [U][2][W of the next step], finally [U] (Dense flush)
         int slot = 0;
         uint32_t use = 0;   // how many times the ring wrapped
-        const int nw = p.n_chunks_w, nu = p.n_chunks_u, n2 = p.n_chunks_2;
+        const int nw = p.n_slots_w, nu = p.n_slots_u, n2 = p.n_slots_2;
         int t = 0, ph = p.has_s1w ? 0 : 1;   // ph 0: W of step 0; then per step 1: U, 2: segment 2, 3: W of step t+1
 #pragma unroll 1
         while (true) {
@@ -583,47 +582,44 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     const uint32_t w_lo0 = desc_lo(sbase + sp.w, 128u);
     constexpr bool streaming = STREAM;
     const uint32_t a_hi64 = desc_hi(1024u);   // kc = 64 chunks
-    int w_slot = 0;
-    uint32_t w_use = 0;
+    int w_slot = -1;            // streamed: ring slot the cursor is in (-1: none yet)
+    uint32_t w_use = 0;         // how many times the ring wrapped
+    uint32_t slot_left = 0;     // bytes of the current slot not yet consumed (consecutive chunks share a slot up to 16 KB)
     int dbg_n = 0, dbg_t = -1;
     (void)dbg_n;
     (void)dbg_t;
-    uint32_t a_lo = w_lo0;   // descriptor word of the next chunk (resident: walks the image; streaming: walks the ring)
+    uint32_t a_lo = w_lo0;   // descriptor word of the next chunk (resident: walks the image; streamed: walks the ring slot)
     if (!streaming) mbar_wait(bar(BAR_W_FULL), 0);
+    // Where the next weight chunk lives.  Streamed: consecutive chunks of a segment are packed into 16 KB slots by the same
+    // greedy rule the host used for the slot table; moving on to a new slot hands the previous one back to the streamer.
+    auto next_chunk = [&](uint32_t bytes) -> uint32_t {
+      if (streaming && slot_left < bytes) {
+        if (w_slot >= 0) umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
+        if (++w_slot == ns) { w_slot = 0; ++w_use; }
+        mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
+        tc_fence_after();
+        slot_left = kSlotBytes;
+        a_lo = w_lo0 + (uint32_t)w_slot * (kSlotBytes >> 4);
+      }
+      const uint32_t a = a_lo;
+      a_lo += bytes >> 4;
+      slot_left -= bytes;   // (resident: unused)
+      return a;
+    };
+    auto new_segment = [&]() { slot_left = 0; };   // streamed: a segment starts in a fresh slot
     // one weight chunk = NM <= 4 MMAs (K = 16 each): A = chunk (K-major, SBO = 256*NM), B = activation rows
     // remainder chunk (K extent not a multiple of 64): nm < 4 single MMAs
     auto chunk = [&](int nm, uint32_t bytes, uint32_t a_hi, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
       TC_CHUNK_STAMP();
-      if (streaming) {
-        mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
-        tc_fence_after();
-      }
-#pragma unroll 1
-      for (int k = 0; k < nm; ++k)
-        umma_f16_x<1, NS>(d_tmem, a_lo + 16u * (uint32_t)k, a_hi, b_lo + (uint32_t)(2 * NS) * (uint32_t)k, act_hi, idesc, k > 0 ? 1u : first_accumulates,
-                          elected);
-      if (streaming) {
-        umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
-        a_lo += kSlotBytes >> 4;
-        if (++w_slot == ns) { w_slot = 0; ++w_use; a_lo = w_lo0; }
-      } else {
-        a_lo += bytes >> 4;
-      }
+      const uint32_t a = next_chunk(bytes);
+      if (nm == 2) umma_f16_x<2, NS>(d_tmem, a, a_hi, b_lo, act_hi, idesc, first_accumulates, elected);        // ranks 17..32
+      else if (nm == 1) umma_f16_x<1, NS>(d_tmem, a, a_hi, b_lo, act_hi, idesc, first_accumulates, elected);   // ranks <= 16, x(t)
+      else umma_f16_x<3, NS>(d_tmem, a, a_hi, b_lo, act_hi, idesc, first_accumulates, elected);
     };
     auto chunk64 = [&](uint32_t bytes, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {   // the common case, no switch
       TC_CHUNK_STAMP();
-      if (streaming) {
-        mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
-        tc_fence_after();
-      }
-      umma_f16_x<4, NS>(d_tmem, a_lo, a_hi64, b_lo, act_hi, idesc, first_accumulates, elected);
-      if (streaming) {
-        umma_commit(bar(BAR_W_EMPTY + w_slot), elected);
-        a_lo += kSlotBytes >> 4;
-        if (++w_slot == ns) { w_slot = 0; ++w_use; a_lo = w_lo0; }
-      } else {
-        a_lo += bytes >> 4;
-      }
+      const uint32_t a = next_chunk(bytes);
+      umma_f16_x<4, NS>(d_tmem, a, a_hi64, b_lo, act_hi, idesc, first_accumulates, elected);
     };
     // resident mode, one K chunk of nm MMAs per gate tile: the whole unit block (4 gates) goes out as one asm block
     auto gates_block = [&](int nm, uint32_t d_tmem, uint32_t b_lo, uint32_t first_accumulates) {
@@ -649,6 +645,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       tc_fence_after();
       const uint32_t in_lo = in_lo0 + (uint32_t)in_s * in_stage_lo;
       if (!streaming) a_lo = w_lo0;
+      new_segment();
       uint32_t d = tm_s1w;
 #pragma unroll 1
       for (int r0 = 0; r0 < p.rows_w; r0 += 128) {
@@ -672,6 +669,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       dbg_t = t;
       // ---- S1u: [t_u ; y] = A1u . h(t-1), K block by K block as the epilogue publishes h(t-1)
       if (!streaming) a_lo = w_lo0 + (p.segw_bytes >> 4);
+      new_segment();
       {
         uint32_t b = h_lo0;
 #pragma unroll 1
@@ -704,6 +702,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         be0 = in_lo0 + (uint32_t)in_s * in_stage_lo;
       }
       tc_fence_after();
+      new_segment();
 #pragma unroll 1
       for (int ub = 0; ub < nub; ++ub) {
         // NS=32: two whole-block buffers (4 gate tiles each), used alternately.  NS=64: ONE block of TMEM, split into
@@ -1177,6 +1176,7 @@ __global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 struct TcLayerImg {
   PackChunk* chunks = nullptr;
+  uint32_t* slots = nullptr;
   uint8_t* wimg = nullptr;
   float* bias = nullptr;
   TcLayerParams prm;
@@ -1208,6 +1208,7 @@ void tc_free(TcState* s) {
   for (int l = 0; l < kMaxLayers; ++l) {
     if (s->layers[l].wimg) cudaFree(s->layers[l].wimg);
     if (s->layers[l].chunks) cudaFree(s->layers[l].chunks);
+    if (s->layers[l].slots) cudaFree(s->layers[l].slots);
     if (s->layers[l].bias) cudaFree(s->layers[l].bias);
   }
   delete s;
@@ -1263,6 +1264,19 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   if (tc_plan(p).total > kSmemCap) {
     p.streaming = 1;
     p.in_stages = p.has_s1w ? 1 : 2;   // every KB goes to the weight ring: its depth must cover the L2 latency
+    // ring-slot fills: consecutive chunks of a segment share a slot up to 16 KB (same greedy rule as the MMA warp's cursor)
+    auto count_slots = [&](auto&& for_seg, int& n) {
+      uint32_t cur = kSlotBytes + 1;   // forces a new slot at the segment start
+      n = 0;
+      for_seg([&](uint32_t b) {
+        if (cur + b > kSlotBytes) { ++n; cur = 0; }
+        cur += b;
+      });
+    };
+    p.n_slots_w = 0;
+    if (p.has_s1w) count_slots([&](auto&& f) { for_seg_w(p, [&](uint32_t b, int, int, int) { f(b); }); }, p.n_slots_w);
+    count_slots([&](auto&& f) { for_seg_u(p, [&](uint32_t b, int, int, int, int) { f(b); }); }, p.n_slots_u);
+    count_slots([&](auto&& f) { for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { f(b); }); }, p.n_slots_2);
     p.w_slots = kMaxWSlots;
     while (p.w_slots > 3 && tc_plan(p).total > kSmemCap) --p.w_slots;
     if (tc_plan(p).total > kSmemCap) { *why = "activation buffers of this layer do not fit shared memory next to a weight ring"; return false; }
@@ -1387,6 +1401,35 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
       // pageable source: the copy is staged before the call returns, so `chunks` may die afterwards
       SVD_CUDA_TRY(cudaMemcpyAsync(li.chunks, chunks.data(), sizeof(PackChunk) * chunks.size(), cudaMemcpyHostToDevice, stream));
       p.chunks = li.chunks;
+      if (li.slots) {
+        cudaFree(li.slots);   // (the stream was synchronised above if a table existed)
+        li.slots = nullptr;
+      }
+      p.slots = nullptr;
+      if (p.streaming) {
+        std::vector<uint32_t> slots;
+        int seg = -1;
+        uint32_t cur = 0, start = 0;
+        auto flush = [&]() {
+          if (cur) slots.push_back((start >> 8) | ((cur >> 8) << 16));
+          cur = 0;
+        };
+        for (const PackChunk& c : chunks) {
+          const uint32_t b = (uint32_t)c.rows * (uint32_t)c.kc * 2u;
+          if (c.seg != seg || cur + b > kSlotBytes) {
+            flush();
+            start = c.byte_off;
+            seg = c.seg;
+          }
+          cur += b;
+        }
+        flush();
+        SVD_REQUIRE((int)slots.size() == p.n_slots_w + p.n_slots_u + p.n_slots_2, "tensor-core engine: slot table mismatch (%d vs %d)",
+                    (int)slots.size(), p.n_slots_w + p.n_slots_u + p.n_slots_2);
+        SVD_CUDA_TRY(cudaMalloc(&li.slots, sizeof(uint32_t) * slots.size()));
+        SVD_CUDA_TRY(cudaMemcpy(li.slots, slots.data(), sizeof(uint32_t) * slots.size(), cudaMemcpyHostToDevice));
+        p.slots = li.slots;
+      }
       SVD_REQUIRE((int)chunks.size() == p.n_chunks_w + p.n_chunks_u + p.n_chunks_2, "tensor-core engine: chunk table mismatch");
       const LayerDesc& Ld = md.layers[l];
       pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, Ld.blocks[0], Ld.blocks[1], p.H, Ld.d_in, p.ru_pad,
