@@ -234,3 +234,26 @@ def test_weight_counts_device_models(dropbear_weights):
     assert svdlstm.count_weights(rm) == expect
     assert rm._fused_handle().count_weights() == expect - 16
     assert 0 < svdlstm.weight_reduction_percent(full, rm) < 100
+
+
+def test_svd_c5_size_matrix():
+    """BASELINE configs[4] factor size: the merged recurrent matrix of an H=1024 layer (1024 x 4096), large Jacobi path.
+    Singular values against LAPACK (float64) to 1e-5 relative including the smallest; reconstruction and orthogonality."""
+    import time
+    rng = np.random.default_rng(1024)
+    A = (rng.standard_normal((1024, 4096)) / 64.0).astype(np.float32)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    (U, S, Vt), sw = svdlstm.svd_batched(A, return_sweeps=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    s_ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    S = S.cpu().numpy().astype(np.float64).reshape(-1)
+    assert np.max(np.abs(S - s_ref) / s_ref) < 1e-5
+    Ud, Vd = U.double(), Vt.double()
+    rec = (Ud * torch.from_numpy(S).cuda()) @ Vd
+    assert float((rec - torch.from_numpy(A.astype(np.float64)).cuda()).abs().max()) < 2e-5
+    eye = torch.eye(1024, dtype=torch.float64, device="cuda")
+    assert float((Ud.reshape(1024, 1024).T @ Ud.reshape(1024, 1024) - eye).abs().max()) < 1e-5
+    assert float((Vd.reshape(1024, 4096) @ Vd.reshape(1024, 4096).T - eye).abs().max()) < 1e-5
+    print("SVD 1024x4096: %d sweeps, %.2f s" % (int(sw[0]), dt))
