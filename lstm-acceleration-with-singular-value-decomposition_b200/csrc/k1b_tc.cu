@@ -30,6 +30,7 @@
 // remain the parity path.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -43,8 +44,8 @@ constexpr int kInStagesMax = 3;      // max input prefetch ring depth
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTcThreads = 32 * (4 + kEpiWarps);
-constexpr int kMaxWSlots = 12;
-constexpr uint32_t kSlotBytes = 16384;
+constexpr int kMaxWSlots = 6;
+constexpr uint32_t kSlotBytes = 32768;
 constexpr int kMaxUB = 4;            // unit blocks of 128 (H <= 512)
 constexpr uint32_t kSmemCap = 227u * 1024u;
 constexpr int kDbgPerLayer = 64 * 16 + 256;   // timeline: 16 stamps x 64 steps + per-chunk issue stamps of step 20
@@ -219,6 +220,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -1169,11 +1176,14 @@ __global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restric
   }
 }
 
+#include "k1c_pair.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+struct TcPairState;
 struct TcLayerImg {
   PackChunk* chunks = nullptr;
   uint32_t* slots = nullptr;
@@ -1186,6 +1196,7 @@ struct TcState {
   TcLayerImg layers[kMaxLayers];
   int n_layers = 0;
   int ns = 0;   // tile width the images / plans were built for (the chunk order depends on resident vs streamed)
+  TcPairState* pair = nullptr;   // images of the paired-CTA kernel (k1c_pair.cuh), built on first use
 };
 
 // Per-device scratch shared by every handle: the FP16 image of x and the two ping-pong hidden-sequence images
@@ -1203,8 +1214,11 @@ struct TcWorkspace {
 };
 static TcWorkspace g_tc_ws[16];
 
+#include "k1c_pair_host.cuh"
+
 void tc_free(TcState* s) {
   if (!s) return;
+  pair_free(s->pair);
   for (int l = 0; l < kMaxLayers; ++l) {
     if (s->layers[l].wimg) cudaFree(s->layers[l].wimg);
     if (s->layers[l].chunks) cudaFree(s->layers[l].chunks);
@@ -1341,6 +1355,22 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     SVD_CUDA_TRY(cudaGetDevice(&dev0));
     SVD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev0));
   }
+  if (weights_dirty) {   // both image sets follow the weights; each is rebuilt when its path next runs
+    st->ns = 0;
+    if (st->pair) st->pair->built = false;
+  }
+  const char* mode_env = getenv("SVDLSTM_TC_MODE");
+  {
+    // Paired-CTA kernel (k1c_pair.cuh): tiles of 128 sequences on two SMs, each streaming half of the weights.
+    const bool force_pair = mode_env && strcmp(mode_env, "pair") == 0;
+    if (force_pair) {
+      SVD_REQUIRE(pair_supported(md, &why), "tensor-core engine (SVDLSTM_TC_MODE=pair): %s", why);
+      int dev0 = 0;
+      SVD_CUDA_TRY(cudaGetDevice(&dev0));
+      SVD_REQUIRE(dev0 >= 0 && dev0 < 16, "tensor-core engine: device ordinal %d out of range", dev0);
+      return run_tc_pair(md, &st->pair, weights_dirty, a, stream, n_sm, &g_tc_ws[dev0], launches);
+    }
+  }
   bool same_h = true;
   for (int l = 1; l < L; ++l) same_h = same_h && md.layers[l].units == md.layers[0].units;
   bool ok64 = true;
@@ -1348,7 +1378,6 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
     TcLayerParams q;
     if (!tc_layer_params(md, l, 64, q, &why)) ok64 = false;
   }
-  const char* mode_env = getenv("SVDLSTM_TC_MODE");
   const char* ns_env = getenv("SVDLSTM_TC_NS");
   const bool allow_pipe = L >= 2 && same_h && !(mode_env && mode_env[0] == 's');
   int ns = 32;

@@ -1,0 +1,47 @@
+"""Times the tensor-core engine on the C3 shape, single-CTA kernel vs paired-CTA kernel, for a list of ranks."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import svdlstm  # noqa: E402
+
+ranks = [int(r) for r in sys.argv[1].split(",")] if len(sys.argv) > 1 else [128]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+H = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+L = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+layers, dense = svdlstm.synthetic_layers(16, H, L, seed=0)
+full = svdlstm.full_model_from_weights(layers, dense)
+sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+x = torch.randn(B, T, 16, generator=torch.Generator().manual_seed(0)).cuda()
+for r in ranks:
+    model = svdlstm.truncate_singular_model(sm, r)
+    ys = {}
+    for mode in ("single", "pair"):
+        if mode == "pair":
+            os.environ["SVDLSTM_TC_MODE"] = "pair"
+        else:
+            os.environ.pop("SVDLSTM_TC_MODE", None)
+        for _ in range(2):
+            y = model(x, engine="tc_bf16")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            y = model(x, engine="tc_bf16")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        ys[mode] = y
+        macs = 0
+        d = 16
+        for _ in range(L):
+            macs += min(r, d) * (d + 4 * H) + min(r, H) * 5 * H
+            d = H
+        tf = 2 * macs * B * T / (ms * 1e-3) / 1e12
+        print("rank %3d %-6s: %.3f ms  %.1f M seq-steps/s  %.1f TFLOP/s = %.1f%% of 1384" % (r, mode, ms, B * T / ms / 1e3, tf, 100 * tf / 1384), flush=True)
+    d = (ys["pair"] - ys["single"]).abs().max().item()
+    print("rank %3d max|pair - single| = %.3e  (|y| max %.3f)" % (r, d, ys["single"].abs().max().item()), flush=True)

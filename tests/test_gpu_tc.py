@@ -165,3 +165,45 @@ def test_tc_full_c3_size_properties():
     assert float(err.max()) < 2e-3 * scale + 2e-4
     assert float(err[:, -128:].max()) < 2.0 * float(err[:, :512].max()) + 1e-4     # no drift over the sequence
     assert torch.equal(m(x, engine="tc"), y)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# paired-CTA kernel (csrc/k1c_pair.cuh, tcgen05 cta_group::2): opt-in with SVDLSTM_TC_MODE=pair
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def pair_mode(monkeypatch):
+    monkeypatch.setenv("SVDLSTM_TC_MODE", "pair")
+    monkeypatch.setenv("SVDLSTM_PAIR_DEBUG", "1")   # a protocol bug is reported as an error instead of hanging the GPU
+    yield
+    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
+
+
+@pytest.mark.parametrize("L,rank,B,T", [(1, 128, 128, 6), (2, 128, 300, 9), (2, 64, 128, 5), (2, 40, 200, 7), (2, 256, 130, 5), (3, 128, 128, 5)])
+def test_tc_pair_matches_oracle_and_single_cta(oracle, monkeypatch, L, rank, B, T):
+    """Two CTAs per 128-sequence tile, M=256 N=128 pair MMAs, h / t_u exchanged through distributed shared memory
+    (st.async + tx-counted mbarriers), the next layer's t_w handed over instead of h.  Same arithmetic as the
+    single-CTA kernel (identical FP16 operands, identical K order): results must be BIT-IDENTICAL to it whenever
+    the Dense top is fused in both (ranks < 256), and within the engine's tolerance of the float64 oracle."""
+    _, sm = _models(256, L)
+    m = svdlstm.truncate_singular_model(sm, rank)
+    x = np.random.default_rng(7).standard_normal((B, T, 16)).astype(np.float32)
+    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
+    y_single = m.predict(x, engine="tc")
+    monkeypatch.setenv("SVDLSTM_TC_MODE", "pair")
+    monkeypatch.setenv("SVDLSTM_PAIR_DEBUG", "1")
+    y_pair = m.predict(x, engine="tc")
+    y_pair2 = m.predict(x, engine="tc")
+    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
+    assert np.array_equal(y_pair, y_pair2), "paired kernel is not deterministic"
+    if rank < 256:
+        assert np.array_equal(y_pair, y_single), "paired kernel differs from the single-CTA kernel: max %.3e" % np.abs(y_pair - y_single).max()
+    _check(y_pair, oracle_twin(oracle, m).predict(x), "tc pair L=%d r=%d" % (L, rank))
+
+
+def test_tc_pair_rejects_unsupported(pair_mode):
+    """The paired kernel needs H in {256, 512} and a Dense top; anything else is an error, never a silent fallback."""
+    _, sm = _models(128, 2)
+    m = svdlstm.truncate_singular_model(sm, 32)
+    x = np.zeros((4, 3, 16), np.float32)
+    with pytest.raises((ValueError, RuntimeError)):
+        m.predict(x, engine="tc")
