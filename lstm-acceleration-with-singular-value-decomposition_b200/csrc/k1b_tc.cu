@@ -44,9 +44,9 @@ constexpr int kInStagesMax = 3;      // max input prefetch ring depth
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTcThreads = 32 * (4 + kEpiWarps);
-constexpr int kMaxWSlots = 6;
-constexpr uint32_t kSlotBytes = 32768;
-constexpr int kMaxUB = 4;            // unit blocks of 128 (H <= 512)
+constexpr int kMaxWSlots = 12;
+constexpr uint32_t kSlotBytes = 32768;   // preferred ring-slot size (two 16 KB chunks per hand-over); 16 KB when fewer than 4 would fit
+constexpr int kMaxUB = 8;            // unit blocks of 128 (H <= 1024; above 512 with 16 epilogue warps, see tc_layer_body)
 constexpr uint32_t kSmemCap = 227u * 1024u;
 constexpr int kDbgPerLayer = 64 * 16 + 256;   // timeline: 16 stamps x 64 steps + per-chunk issue stamps of step 20
 
@@ -298,7 +298,8 @@ struct TcLayerParams {
   int has_s1w;              // layers >= 1
   int store_h;              // hand h(t) tiles to the next layer through HBM
   int in_stages;            // depth of the input prefetch ring
-  int streaming, w_slots;   // weight stream: 0 = resident; 1 = ring of w_slots 16 KB slots
+  int streaming, w_slots;   // weight stream: 0 = resident; 1 = ring of w_slots slots of slot_bytes
+  uint32_t slot_bytes;
   uint32_t segw_bytes, segu_bytes, seg2_bytes;
   long long* dbg;           // optional timeline buffer (CTA 0): 16 clock64 stamps per step; nullptr = off
 };
@@ -311,7 +312,7 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   TcSmemPlan s;
   uint32_t off = 0;
   s.w = off;
-  off += p.streaming ? (uint32_t)p.w_slots * kSlotBytes : ((p.segw_bytes + p.segu_bytes + p.seg2_bytes + 1023u) & ~1023u);
+  off += p.streaming ? (uint32_t)p.w_slots * p.slot_bytes : ((p.segw_bytes + p.segu_bytes + p.seg2_bytes + 1023u) & ~1023u);
   s.hbuf = off; off += act_tile_bytes(p.H, p.ns);
   s.tbuf = off; off += act_tile_bytes(p.ru_pad + p.rw_pad, p.ns);
   s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin, p.ns);
@@ -430,9 +431,13 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 // One CTA = one layer x one tile of NS sequences x all T steps.  prog_in / prog_out (layer-pipelined launch only): per-tile
 // step counters in global memory through which the previous layer's CTA publishes -- and this CTA announces -- how many
 // hidden-sequence tiles have landed in the hand-off image.
-template <int NUB, bool STREAM, int NS>
+// EW = epilogue warps (8, or 16 for H > 512: the cell state of NUB x 128 cells x NS sequences lives in their registers).
+template <int NUB, bool STREAM, int NS, int EW = kEpiWarps>
 __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta) {
-  constexpr int CPT = NS / 2;                 // accumulator columns per epilogue thread (two warps per TMEM lane quarter)
+  constexpr int CPT = NS * 4 / EW;            // accumulator columns per epilogue thread (EW / 4 warps per TMEM lane quarter)
+  constexpr int kTcThreads = 32 * (4 + EW);   // (shadow the 8-warp defaults of the file scope)
+  constexpr int kEpiThreads = 32 * EW;
+  static_assert(CPT == 8 || CPT == 16 || CPT == 32, "8, 16 or 32 accumulator columns per epilogue thread");
   constexpr uint32_t kRowBlk = (uint32_t)NS * 256u;   // bytes of 128 K-rows of an activation tile (16 k-groups)
   constexpr uint32_t kK64 = (uint32_t)NS * 8u;        // descriptor-lo step of 64 K-rows (8 k-groups of NS*16 bytes)
   constexpr int kS2Bufs = NS == 32 ? 2 : 1;   // S2 accumulator buffers that fit TMEM (4 gates x NS columns each)
@@ -454,7 +459,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
   for (uint32_t i = threadIdx.x * 16u; i < sp.bars - sp.hbuf; i += kTcThreads * 16u)
     *reinterpret_cast<uint4*>(smem + sp.hbuf + i) = make_uint4(0, 0, 0, 0);
   if (p.streaming)   // stale bytes behind short chunks feed unused accumulator rows only, but keep them finite
-    for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)ns * kSlotBytes; i += kTcThreads * 16u)
+    for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)ns * p.slot_bytes; i += kTcThreads * 16u)
       *reinterpret_cast<uint4*>(smem + sp.w + i) = make_uint4(0, 0, 0, 0);
   if (STREAM) {
     const int nc = p.n_slots_w + p.n_slots_u + p.n_slots_2;
@@ -523,7 +528,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
             const uint32_t bytes = (e >> 16) << 8;
             if (use > 0) mbar_wait(bar(BAR_W_EMPTY + slot), (use - 1u) & 1u);
             mbar_expect_tx(bar(BAR_W_FULL + slot), bytes);
-            bulk_g2s(sbase + sp.w + (uint32_t)slot * kSlotBytes, p.wimg + ((size_t)(e & 0xFFFFu) << 8), bytes, bar(BAR_W_FULL + slot));
+            bulk_g2s(sbase + sp.w + (uint32_t)slot * p.slot_bytes, p.wimg + ((size_t)(e & 0xFFFFu) << 8), bytes, bar(BAR_W_FULL + slot));
             if (++slot == ns) { slot = 0; ++use; }
           }
           if (ph == 0) ph = 1;
@@ -589,6 +594,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     const uint32_t w_lo0 = desc_lo(sbase + sp.w, 128u);
     constexpr bool streaming = STREAM;
     const uint32_t a_hi64 = desc_hi(1024u);   // kc = 64 chunks
+    const uint32_t slot_bytes = p.slot_bytes, slot_lo = p.slot_bytes >> 4;   // in registers: this warp pays every load's latency
     int w_slot = -1;            // streamed: ring slot the cursor is in (-1: none yet)
     uint32_t w_use = 0;         // how many times the ring wrapped
     uint32_t slot_left = 0;     // bytes of the current slot not yet consumed (consecutive chunks share a slot up to 16 KB)
@@ -605,8 +611,8 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         if (++w_slot == ns) { w_slot = 0; ++w_use; }
         mbar_wait(bar(BAR_W_FULL + w_slot), w_use & 1u);
         tc_fence_after();
-        slot_left = kSlotBytes;
-        a_lo = w_lo0 + (uint32_t)w_slot * (kSlotBytes >> 4);
+        slot_left = slot_bytes;
+        a_lo = w_lo0 + (uint32_t)w_slot * slot_lo;
       }
       const uint32_t a = a_lo;
       a_lo += bytes >> 4;
@@ -875,6 +881,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     auto load_cols = [&](uint32_t taddr, uint32_t* r) {   // CPT consecutive accumulator columns of this thread's TMEM lane
 #pragma unroll
       for (int j16 = 0; j16 < CPT / 16; ++j16) tmem_ld16(taddr + 16u * (uint32_t)j16, r + 16 * j16);
+      if constexpr (CPT == 8) tmem_ld8(taddr, r);
     };
     // t_w(tt) accumulators -> f16 rows [ru_pad, ru_pad + rw_pad) of the S2 B operand.  Runs one step ahead of its use
     // (S1w has no recurrence), at the tail of the previous step's epilogue, so it is never on the critical path.
@@ -1003,9 +1010,9 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
 }
 
 // layers launched one after the other (any batch size): grid = tiles of one layer
-template <int NUB, bool STREAM, int NS>
-__global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_layer_kernel(const TcLayerParams p) {
-  tc_layer_body<NUB, STREAM, NS>(p, (int)blockIdx.x, nullptr, nullptr, blockIdx.x == 0);
+template <int NUB, bool STREAM, int NS, int EW = kEpiWarps>
+__global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_layer_kernel(const TcLayerParams p) {
+  tc_layer_body<NUB, STREAM, NS, EW>(p, (int)blockIdx.x, nullptr, nullptr, blockIdx.x == 0);
 }
 
 // ALL layers in one (cooperative, fully co-resident) launch: CTA b runs layer b / n_tiles on tile b % n_tiles and the layers
@@ -1017,14 +1024,14 @@ struct TcPipeParams {
   int n_layers, n_tiles;
   int* progress;   // [n_layers][n_tiles] steps published, zeroed before the launch
 };
-template <int NUB, int NS>
-__global__ void __launch_bounds__(kTcThreads, 1) lstm_tc_pipe_kernel(const __grid_constant__ TcPipeParams pp) {
+template <int NUB, int NS, int EW = kEpiWarps>
+__global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_pipe_kernel(const __grid_constant__ TcPipeParams pp) {
   const int layer = (int)blockIdx.x / pp.n_tiles, tile = (int)blockIdx.x - layer * pp.n_tiles;
   const TcLayerParams& p = pp.layer[layer];
   const int* prog_in = layer > 0 ? pp.progress + (size_t)(layer - 1) * pp.n_tiles + tile : nullptr;
   int* prog_out = layer + 1 < pp.n_layers ? pp.progress + (size_t)layer * pp.n_tiles + tile : nullptr;
-  if (p.streaming) tc_layer_body<NUB, true, NS>(p, tile, prog_in, prog_out, tile == 0);
-  else tc_layer_body<NUB, false, NS>(p, tile, prog_in, prog_out, tile == 0);
+  if (p.streaming) tc_layer_body<NUB, true, NS, EW>(p, tile, prog_in, prog_out, tile == 0);
+  else if constexpr (NUB <= 4) tc_layer_body<NUB, false, NS, EW>(p, tile, prog_in, prog_out, tile == 0);   // (H > 512 never fits resident)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1235,7 +1242,8 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   const Block& bu = L.blocks[1];
   if (bu.left == nullptr || bw.left == nullptr) { *why = "full (unfactored) cells are not low-rank: use the FP32 engines"; return false; }
   const int H = L.units;
-  if (H % 128 != 0 || H > 128 * kMaxUB) { *why = "tensor-core engine needs units in {128, 256, 384, 512}"; return false; }
+  if (H % 128 != 0 || H > 128 * kMaxUB || (H > 512 && H != 1024)) { *why = "tensor-core engine needs units in {128, 256, 384, 512, 1024}"; return false; }
+  if (H > 512 && ns != 32) { *why = "units above 512 run with 32-sequence tiles"; return false; }
   if (bu.rank > 256 || bw.rank > 256) { *why = "ranks above 256 are not supported by the tensor-core engine"; return false; }
   const bool last = (l == md.n_layers - 1);
   p = TcLayerParams{};
@@ -1278,21 +1286,27 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   if (tc_plan(p).total > kSmemCap) {
     p.streaming = 1;
     p.in_stages = p.has_s1w ? 1 : 2;   // every KB goes to the weight ring: its depth must cover the L2 latency
-    // ring-slot fills: consecutive chunks of a segment share a slot up to 16 KB (same greedy rule as the MMA warp's cursor)
+    // ring-slot fills: consecutive chunks of a segment share a slot up to slot_bytes (same greedy rule as the MMA warp's cursor).
+    // 32 KB slots halve the hand-overs (commit + full wait) of the MMA warp, which is issue-bound; when fewer than four of them
+    // fit next to the activation buffers (H = 1024) the ring falls back to 16 KB slots to keep enough copies in flight.
     auto count_slots = [&](auto&& for_seg, int& n) {
-      uint32_t cur = kSlotBytes + 1;   // forces a new slot at the segment start
+      uint32_t cur = p.slot_bytes + 1;   // forces a new slot at the segment start
       n = 0;
       for_seg([&](uint32_t b) {
-        if (cur + b > kSlotBytes) { ++n; cur = 0; }
+        if (cur + b > p.slot_bytes) { ++n; cur = 0; }
         cur += b;
       });
     };
-    p.n_slots_w = 0;
-    if (p.has_s1w) count_slots([&](auto&& f) { for_seg_w(p, [&](uint32_t b, int, int, int) { f(b); }); }, p.n_slots_w);
-    count_slots([&](auto&& f) { for_seg_u(p, [&](uint32_t b, int, int, int, int) { f(b); }); }, p.n_slots_u);
-    count_slots([&](auto&& f) { for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { f(b); }); }, p.n_slots_2);
-    p.w_slots = kMaxWSlots;
-    while (p.w_slots > 3 && tc_plan(p).total > kSmemCap) --p.w_slots;
+    for (uint32_t sb : {kSlotBytes, 16384u}) {
+      p.slot_bytes = sb;
+      p.n_slots_w = 0;
+      if (p.has_s1w) count_slots([&](auto&& f) { for_seg_w(p, [&](uint32_t b, int, int, int) { f(b); }); }, p.n_slots_w);
+      count_slots([&](auto&& f) { for_seg_u(p, [&](uint32_t b, int, int, int, int) { f(b); }); }, p.n_slots_u);
+      count_slots([&](auto&& f) { for_seg_2(p, [&](uint32_t b, int, int, int, int, int) { f(b); }); }, p.n_slots_2);
+      p.w_slots = kMaxWSlots;
+      while (p.w_slots > 2 && tc_plan(p).total > kSmemCap) --p.w_slots;
+      if (tc_plan(p).total <= kSmemCap && p.w_slots >= (sb == kSlotBytes ? 3 : 2)) break;
+    }
     if (tc_plan(p).total > kSmemCap) { *why = "activation buffers of this layer do not fit shared memory next to a weight ring"; return false; }
   }
   return true;
@@ -1327,6 +1341,15 @@ static int tc_launch_layer(const TcLayerParams& p, int n_cta, uint32_t smem_byte
   return 0;
 }
 
+// units = 1024: 8 unit blocks, weights always streamed, 32-sequence tiles, 16 epilogue warps (cell state: 8 x 8 registers per thread)
+static int tc_launch_layer_1024(const TcLayerParams& p, int n_cta, uint32_t smem_bytes, cudaStream_t stream) {
+  SVD_REQUIRE(p.streaming && p.ns == 32, "tensor-core engine: units = 1024 needs a streamed weight ring and 32-sequence tiles");
+  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<8, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  lstm_tc_layer_kernel<8, true, 32, 16><<<n_cta, 32 * (4 + 16), smem_bytes, stream>>>(p);
+  return 0;
+}
+static int tc_launch_pipe_1024(const void* pp, int n_cta, uint32_t smem_bytes, cudaStream_t stream);
+
 // all layers in one cooperative launch (co-residency of every CTA is what makes the inter-layer waits safe)
 template <int NUB, int NS>
 static int tc_launch_pipe(const TcPipeParams& pp, uint32_t smem_bytes, cudaStream_t stream) {
@@ -1334,6 +1357,15 @@ static int tc_launch_pipe(const TcPipeParams& pp, uint32_t smem_bytes, cudaStrea
   void* args[] = {const_cast<TcPipeParams*>(&pp)};
   SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_tc_pipe_kernel<NUB, NS>), dim3((unsigned)(pp.n_layers * pp.n_tiles)),
                                            dim3(kTcThreads), args, smem_bytes, stream));
+  return 0;
+}
+
+static int tc_launch_pipe_1024(const void* pp_, int n_cta, uint32_t smem_bytes, cudaStream_t stream) {
+  const TcPipeParams* pp = static_cast<const TcPipeParams*>(pp_);
+  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_pipe_kernel<8, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  void* args[] = {const_cast<TcPipeParams*>(pp)};
+  SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_tc_pipe_kernel<8, 32, 16>), dim3((unsigned)n_cta), dim3(32 * (4 + 16)), args,
+                                           smem_bytes, stream));
   return 0;
 }
 
@@ -1445,7 +1477,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
         };
         for (const PackChunk& c : chunks) {
           const uint32_t b = (uint32_t)c.rows * (uint32_t)c.kc * 2u;
-          if (c.seg != seg || cur + b > kSlotBytes) {
+          if (c.seg != seg || cur + b > p.slot_bytes) {
             flush();
             start = c.byte_off;
             seg = c.seg;
@@ -1558,6 +1590,7 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
       case 7: lrc = tc_launch_layer<3, true>(p, n_cta, sp.total, stream); break;
       case 8: lrc = tc_launch_layer<4, false>(p, n_cta, sp.total, stream); break;
       case 9: lrc = tc_launch_layer<4, true>(p, n_cta, sp.total, stream); break;
+      case 17: lrc = tc_launch_layer_1024(p, n_cta, sp.total, stream); break;
       default: set_error("tensor-core engine: unsupported units %d", p.H);
     }
     if (lrc != 0) return lrc;
@@ -1572,9 +1605,10 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
       case 2: lrc = tc_launch_pipe<1, 32>(pp, pipe_smem, stream); break;
       case 3: lrc = tc_launch_pipe<1, 64>(pp, pipe_smem, stream); break;
       case 4: lrc = tc_launch_pipe<2, 32>(pp, pipe_smem, stream); break;
-      case 5: lrc = tc_launch_pipe<2, 64>(pp, pipe_smem, stream); break;
+      case 5: lrc = tc_launch_pipe<2, 64>(pp, pipe_smem, stream); break;   // (16 epilogue warps measured slower here: 5.75 vs 5.55 ms at rank 64)
       case 6: lrc = tc_launch_pipe<3, 32>(pp, pipe_smem, stream); break;
       case 8: lrc = tc_launch_pipe<4, 32>(pp, pipe_smem, stream); break;
+      case 16: lrc = tc_launch_pipe_1024(&pp, L * n_cta, pipe_smem, stream); break;
       default: set_error("tensor-core engine: unsupported units %d for the pipelined launch", md.layers[0].units);
     }
     if (lrc != 0) return lrc;

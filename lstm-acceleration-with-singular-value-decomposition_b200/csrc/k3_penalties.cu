@@ -49,8 +49,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 
 __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restrict__ items, int n_items, const Work* __restrict__ work,
                                                         int n_work, double* partial /*n_work x 2*/, unsigned int* ticket, double* out) {
-  __shared__ float As[kTile][kTile + 1];
-  __shared__ float Bs[kTile][kTile + 1];
+  __shared__ double As[kTile][kTile + 1];   // converted to float64 ONCE per tile load: the inner loop is DFMA + LDS.64 only
+  __shared__ double Bs[kTile][kTile + 1];
   __shared__ double red[8];
   __shared__ double nrmA[kTile], nrmB[kTile];
   __shared__ bool is_last;
@@ -91,19 +91,19 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
           if (ia < R) va = __ldg(it.columns ? it.data + (size_t)k * it.ld + ia : it.data + (size_t)ia * it.ld + k);
           if (ib < R) vb = __ldg(it.columns ? it.data + (size_t)k * it.ld + ib : it.data + (size_t)ib * it.ld + k);
         }
-        As[rr][kk] = va;
-        Bs[rr][kk] = vb;
+        As[rr][kk] = (double)va;
+        Bs[rr][kk] = (double)vb;
       }
       __syncthreads();
 #pragma unroll 8
       for (int kk = 0; kk < kTile; ++kk) {
         const double av = As[ti][kk];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += av * (double)Bs[tj + u][kk];
+        for (int u = 0; u < 4; ++u) acc[u] += av * Bs[tj + u][kk];
       }
       if (tid < 2 * kTile) {
-        const float* row = tid < kTile ? As[tid] : Bs[tid - kTile];
-        for (int kk = 0; kk < kTile; ++kk) nacc += (double)row[kk] * row[kk];
+        const double* row = tid < kTile ? As[tid] : Bs[tid - kTile];
+        for (int kk = 0; kk < kTile; ++kk) nacc += row[kk] * row[kk];
       }
       __syncthreads();
     }

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""BASELINE configs[4] (C5) pieces that run today at full size on one GPU: factorisation of the 3-layer H=1024 model
-(K2: six matrices up to 1024 x 4096), rank-128 truncation, and ONE fused penalty launch (K3) over all 12 factor
-matrices + 6 sigma vectors, checked against the oracle on the largest item.  The recurrent forward at H=1024 runs on
-the FP32 general engine only (the tensor-core engine holds c in registers: units <= 512) -- see DESIGN.md section 7."""
+"""BASELINE configs[4] (C5) on ONE GPU = one rank's shard of the 8-GPU job: factorisation of the 3-layer H=1024 model
+(K2: six matrices up to 1024 x 4096), rank-128 truncation, ONE fused penalty launch (K3) over all 12 factor matrices +
+6 sigma vectors (device-resident, as in a training loop; checked against the oracle on the largest item), and the
+recurrent forward of the shard (1024 of the 8192 sequences x T=4096) on the tensor-core engine (units = 1024 path:
+16 epilogue warps, streamed weights), checked against the FP32 engine on a sub-sample.  argv: [T] [B]"""
 import json
 import os
 import sys
@@ -30,7 +31,7 @@ def main():
     tm = svdlstm.truncate_singular_model(sm, r)
     spec = []
     for layer in tm.layers[:-1]:
-        w = layer.get_weights()
+        w = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in layer.get_weights()]   # factors live on the device in a training loop
         spec += [(w[0], False, False), (w[1], False, False)] + [(w[i], True, False) for i in (2, 3, 4, 5)]
     svdlstm.evaluate_penalties(spec)
     torch.cuda.synchronize()
@@ -41,14 +42,38 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    nbytes = sum(np.asarray(a).size * 4 for a, _, _ in spec)
-    big = max(range(len(spec)), key=lambda i: np.asarray(spec[i][0]).size)
-    ref = O.penalty_raw_sums(np.asarray(spec[big][0]), mode="rows")
+    nbytes = sum(a.numel() * 4 for a, _, _ in spec)
+    big = max(range(len(spec)), key=lambda i: spec[i][0].numel())
+    ref = O.penalty_raw_sums(spec[big][0].cpu().numpy(), mode="rows")
     rel = max(abs(raw[big][k] - ref[k]) / (abs(ref[k]) + 1e-12) for k in range(4))
-    print(json.dumps({"config": "C5 pieces: L=3 H=1024 rank 128", "svd_factorisation_s": round(t_svd, 3),
-                      "penalty_items": len(spec), "penalty_launches": svdlstm.launches() - l0, "penalty_ms": round(ms, 3),
-                      "penalty_bytes_read_once": nbytes, "penalty_GBps": round(nbytes / ms / 1e6, 1),
-                      "largest_item_shape": list(np.asarray(spec[big][0]).shape), "max_rel_err_vs_oracle": rel}))
+    out = {"config": "C5 shard of one GPU: L=3 H=1024 rank 128", "svd_factorisation_s": round(t_svd, 3),
+           "penalty_items": len(spec), "penalty_launches": svdlstm.launches() - l0, "penalty_ms": round(ms, 3),
+           "penalty_bytes_read_once": nbytes, "penalty_GBps": round(nbytes / ms / 1e6, 1),
+           "largest_item_shape": list(spec[big][0].shape), "max_rel_err_vs_oracle": rel}
+    # ---- the recurrent forward of this GPU's shard on the tensor-core engine
+    T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    x = torch.randn(B, T, 16, generator=torch.Generator().manual_seed(0)).cuda()
+    y = tm(x, engine="tc")           # warm-up: packs the weight streams, allocates the hand-off images
+    torch.cuda.synchronize()
+    e0.record()
+    y = tm(x, engine="tc")
+    e1.record()
+    torch.cuda.synchronize()
+    fms = e0.elapsed_time(e1)
+    macs, d = 0, 16
+    for _ in range(L):
+        macs += min(r, d) * (d + 4 * H) + min(r, H) * 5 * H
+        d = H
+    sub = x[:32, :24].contiguous()
+    err = (tm(sub, engine="tc") - tm(sub, engine="general")).abs().max().item()
+    scale = tm(sub, engine="general").abs().max().item()
+    out.update({"forward_B": B, "forward_T": T, "forward_ms": round(fms, 2), "forward_Mseqsteps_per_s": round(B * T / fms / 1e3, 2),
+                "forward_algorithmic_TFLOPs": round(2 * macs * B * T / (fms * 1e-3) / 1e12, 1),
+                "forward_frac_of_1384": round(2 * macs * B * T / (fms * 1e-3) / 1e12 / 1384, 4),
+                "forward_max_abs_tc_minus_fp32_subsample": err, "forward_subsample_output_max": scale,
+                "forward_finite": bool(torch.isfinite(y).all().item())})
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -17,3 +17,8 @@ CMD="python scripts/prof_batch1.py"
 $CMD > $O/plain_b1.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:lstm_wavefront_kernel -s 1 -c 1 -f -o $O/b1_wavefront_$R $CMD > $O/ncu_b1.log 2>&1
 for f in $O/plain_tc_128.log $O/plain_tc_32.log $O/plain_b1.log; do tail -n 2 $f; done
+# 4) launch list of the C5 shard pieces (K2 Jacobi rounds, K3 fused penalties, the units = 1024 tensor-core kernel) at T = 128
+CMD="python scripts/c5_parts.py 128"
+$CMD > $O/plain_c5_$R.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'penalties_kernel|lstm_tc_|pack_' -c 60 --csv --log-file $O/launches_c5_$R.csv $CMD > $O/ncu_c5_$R.log 2>&1
+tail -n 1 $O/plain_c5_$R.log | cut -c1-300

@@ -1,4 +1,4 @@
-"""Times the tensor-core engine on the C3 workload shape for a list of ranks."""
+"""Times the tensor-core engine for a list of ranks.  argv: ranks B T H L (defaults: the C3 workload shape)."""
 import os
 import sys
 
@@ -11,7 +11,8 @@ import svdlstm  # noqa: E402
 ranks = [int(r) for r in sys.argv[1].split(",")] if len(sys.argv) > 1 else [8, 16, 32]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-H, L = 256, 2
+H = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+L = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 layers, dense = svdlstm.synthetic_layers(16, H, L, seed=0)
 full = svdlstm.full_model_from_weights(layers, dense)
 sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)

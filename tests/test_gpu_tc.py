@@ -207,3 +207,14 @@ def test_tc_pair_rejects_unsupported(pair_mode):
     x = np.zeros((4, 3, 16), np.float32)
     with pytest.raises((ValueError, RuntimeError)):
         m.predict(x, engine="tc")
+
+
+def test_tc_units_1024_matches_oracle(oracle):
+    """BASELINE configs[4] shape (units = 1024, 3 layers, rank 128): 8 unit blocks, 16 epilogue warps (the cell state of
+    1024 cells x 32 sequences lives in their registers), weights streamed through 16 KB ring slots; ragged batch."""
+    _, sm = _models(1024, 3)
+    m = svdlstm.truncate_singular_model(sm, 128)
+    x = np.random.default_rng(9).standard_normal((37, 7, 16)).astype(np.float32)
+    y = m.predict(x, engine="tc")
+    assert m.last_engine() == svdlstm.ENGINE_TC
+    _check(y, oracle_twin(oracle, m).predict(x), "tc units=1024 L=3 r=128")
