@@ -6,7 +6,11 @@
 // w_left / w_right / u_left / u_right.  ONE launch walks a work list covering every item of a model:
 //   kind 0  L1 / L2 partial sums over a 4096-element chunk                     (HBM-bound, 4 B/elt once)
 //   kind 1  one 32x32 tile (bi<=bj) of the Gram matrix Y Y^T in float64, with the row norms of both
-//           row blocks accumulated on the fly -> sum_{i!=j}|P_ij|/(|y_i||y_j|) and ||Y Y^T - I||_F^2
+//           row blocks accumulated on the fly -> sum_{i!=j}|P_ij|/(|y_i||y_j|) and ||Y Y^T - I||_F^2.
+//           Wide factors (more than kSplitF features, e.g. the 128 x 4096 right factors of H = 1024) are SPLIT-K:
+//           each CTA covers kSplitF features and parks its partial tile in scratch; the last CTA of the tile
+//           (per-tile ticket) adds the parts in split order -- |.| and the norms are nonlinear, so they are
+//           applied only to the complete tile -- and reports into the tile's first work slot (fixed position)
 // Partials go to a scratch buffer; the last CTA to finish (atomic ticket) reduces them per item in
 // a FIXED order, so results are bit-reproducible run to run.  Raw sums are emitted so that both
 // the reference's definitions (L1/L2^2, mean |off-diagonal| of the normalised Gram) and the
@@ -23,9 +27,14 @@ namespace {
 
 constexpr int kChunk = 4096;
 constexpr int kTile = 32;
+constexpr int kSplitF = 256;   // features per Gram CTA
+constexpr int kPartDoubles = kTile * kTile + 2 * kTile;   // one parked partial: the tile + both row-norm blocks
 
 struct Work {
   int item, kind, a, b;
+  int split, n_splits;   // this CTA's feature range [split * kSplitF, ...) of n_splits
+  int slot;              // split tiles: index of the tile's ticket / scratch block
+  int base;              // split tiles: work index that receives the tile's result
 };
 
 struct ItemDev {
@@ -48,12 +57,16 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restrict__ items, int n_items, const Work* __restrict__ work,
-                                                        int n_work, double* partial /*n_work x 2*/, unsigned int* ticket, double* out) {
+                                                        int n_work, double* partial /*n_work x 2, zeroed*/, unsigned int* ticket /*[0] + per split tile, zeroed*/,
+                                                        double* scratch /*per split tile: n_splits x kPartDoubles*/, const int* __restrict__ scratch_off,
+                                                        double* out) {
   __shared__ double As[kTile][kTile + 1];   // converted to float64 ONCE per tile load: the inner loop is DFMA + LDS.64 only
   __shared__ double Bs[kTile][kTile + 1];
   __shared__ double red[8];
   __shared__ double nrmA[kTile], nrmB[kTile];
   __shared__ bool is_last;
+  __shared__ bool tile_last;
+  int out_slot = blockIdx.x;   // where this CTA's (r0, r1) go
   const int tid = threadIdx.x;
   const Work wk = work[blockIdx.x];
   const ItemDev it = items[wk.item];
@@ -79,14 +92,16 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
     const int ti = tid >> 3, tj = (tid & 7) * 4;
     double acc[4] = {0, 0, 0, 0};
     double nacc = 0.0;
-    for (int k0 = 0; k0 < F; k0 += kTile) {
+    const int kbeg = wk.split * kSplitF;
+    const int kend = wk.n_splits == 1 ? F : (kbeg + kSplitF < F ? kbeg + kSplitF : F);
+    for (int k0 = kbeg; k0 < kend; k0 += kTile) {
       for (int idx = tid; idx < kTile * kTile; idx += 256) {
         int rr, kk;
         if (it.columns) { kk = idx / kTile; rr = idx - kk * kTile; }   // coalesce along the vector index
         else { rr = idx / kTile; kk = idx - rr * kTile; }
         const int k = k0 + kk;
         float va = 0.f, vb = 0.f;
-        if (k < F) {
+        if (k < kend) {
           const int ia = i0 + rr, ib = j0 + rr;
           if (ia < R) va = __ldg(it.columns ? it.data + (size_t)k * it.ld + ia : it.data + (size_t)ia * it.ld + k);
           if (ib < R) vb = __ldg(it.columns ? it.data + (size_t)k * it.ld + ib : it.data + (size_t)ib * it.ld + k);
@@ -106,6 +121,32 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
         for (int kk = 0; kk < kTile; ++kk) nacc += row[kk] * row[kk];
       }
       __syncthreads();
+    }
+    bool finish = true;
+    if (wk.n_splits > 1) {
+      // park the partial tile; the last CTA of the tile adds the parts in split order
+      double* mine = scratch + (size_t)scratch_off[wk.slot] + (size_t)wk.split * kPartDoubles;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mine[tid * 4 + u] = acc[u];
+      if (tid < 2 * kTile) mine[kTile * kTile + tid] = nacc;
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) tile_last = (atomicAdd(ticket + 1 + wk.slot, 1u) == (unsigned int)wk.n_splits - 1u);
+      __syncthreads();
+      finish = tile_last;
+      if (finish) {
+        __threadfence();
+        const volatile double* parts = scratch + (size_t)scratch_off[wk.slot];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = 0.0;
+        nacc = 0.0;
+        for (int sp = 0; sp < wk.n_splits; ++sp) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += parts[(size_t)sp * kPartDoubles + tid * 4 + u];
+          if (tid < 2 * kTile) nacc += parts[(size_t)sp * kPartDoubles + kTile * kTile + tid];
+        }
+        out_slot = wk.base;
+      }
     }
     if (tid < kTile) nrmA[tid] = sqrt(fmax(nacc, 1e-12));
     else if (tid < 2 * kTile) nrmB[tid - kTile] = sqrt(fmax(nacc, 1e-12));
@@ -128,10 +169,13 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
     }
     r0 = block_sum_256(off * mult, red);
     r1 = block_sum_256(fro * mult, red);
+    if (!finish) out_slot = -1;   // a parked part reports nothing (its slot stays zero)
   }
   if (tid == 0) {
-    partial[2 * (size_t)blockIdx.x] = r0;
-    partial[2 * (size_t)blockIdx.x + 1] = r1;
+    if (out_slot >= 0) {
+      partial[2 * (size_t)out_slot] = r0;
+      partial[2 * (size_t)out_slot + 1] = r1;
+    }
     __threadfence();
     const unsigned int t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
@@ -158,7 +202,6 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
     if (lane == 0)
       for (int u = 0; u < 4; ++u) out[4 * i + u] = s[u];
   }
-  if (tid == 0) *ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,18 +245,31 @@ extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items,
   cudaStream_t stream = (cudaStream_t)stream_;
   std::vector<ItemDev> hi(n_items);
   std::vector<Work> hw;
+  std::vector<int> soff;          // per split tile: offset of its scratch block (doubles)
+  size_t scratch_doubles = 0;
   for (int i = 0; i < n_items; ++i) {
     const svdlstm_penalty_item& s = items[i];
     SVD_REQUIRE(s.data && s.rows >= 1 && s.cols >= 1 && s.ld >= s.cols, "svdlstm_penalties: item %d has bad shape (%d,%d) ld=%d", i, s.rows, s.cols, s.ld);
     hi[i] = ItemDev{s.data, s.rows, s.cols, s.ld, s.gram, s.columns, (int)hw.size(), 0};
     const size_t total = (size_t)s.rows * s.cols;
     const int nchunks = (int)((total + kChunk - 1) / kChunk);
-    for (int c = 0; c < nchunks; ++c) hw.push_back(Work{i, 0, c, 0});
+    for (int c = 0; c < nchunks; ++c) hw.push_back(Work{i, 0, c, 0, 0, 1, 0, 0});
     if (s.gram) {
       const int R = s.columns ? s.cols : s.rows;
+      const int F = s.columns ? s.rows : s.cols;
       const int nb = (R + kTile - 1) / kTile;
+      const int nsp = (F + kSplitF - 1) / kSplitF;
       for (int a = 0; a < nb; ++a)
-        for (int b = a; b < nb; ++b) hw.push_back(Work{i, 1, a, b});
+        for (int b = a; b < nb; ++b) {
+          if (nsp <= 1) {
+            hw.push_back(Work{i, 1, a, b, 0, 1, 0, 0});
+          } else {
+            const int base = (int)hw.size(), slot = (int)soff.size();
+            soff.push_back((int)scratch_doubles);
+            scratch_doubles += (size_t)nsp * kPartDoubles;
+            for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 1, a, b, sp, nsp, slot, base});
+          }
+        }
     }
     hi[i].n_work = (int)hw.size() - hi[i].first_work;
   }
@@ -222,20 +278,29 @@ extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items,
   Work* dw = nullptr;
   double* partial = nullptr;
   unsigned int* ticket = nullptr;
+  double* scratch = nullptr;
+  int* dsoff = nullptr;
+  const size_t n_tick = 1 + soff.size();
   SVD_CUDA_TRY(cudaMallocAsync(&di, sizeof(ItemDev) * n_items, stream));
   SVD_CUDA_TRY(cudaMallocAsync(&dw, sizeof(Work) * n_work, stream));
   SVD_CUDA_TRY(cudaMallocAsync(&partial, sizeof(double) * 2 * n_work, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&ticket, sizeof(unsigned int), stream));
-  SVD_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+  SVD_CUDA_TRY(cudaMallocAsync(&ticket, sizeof(unsigned int) * n_tick, stream));
+  SVD_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(double) * (scratch_doubles ? scratch_doubles : 1), stream));
+  SVD_CUDA_TRY(cudaMallocAsync(&dsoff, sizeof(int) * (soff.size() ? soff.size() : 1), stream));
+  SVD_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int) * n_tick, stream));
+  SVD_CUDA_TRY(cudaMemsetAsync(partial, 0, sizeof(double) * 2 * n_work, stream));
+  if (!soff.empty()) SVD_CUDA_TRY(cudaMemcpyAsync(dsoff, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice, stream));
   // pageable -> device: the runtime stages these synchronously, so the vectors may die after the call
   SVD_CUDA_TRY(cudaMemcpyAsync(di, hi.data(), sizeof(ItemDev) * n_items, cudaMemcpyHostToDevice, stream));
   SVD_CUDA_TRY(cudaMemcpyAsync(dw, hw.data(), sizeof(Work) * n_work, cudaMemcpyHostToDevice, stream));
-  penalties_kernel<<<n_work, 256, 0, stream>>>(di, n_items, dw, n_work, partial, ticket, out);
+  penalties_kernel<<<n_work, 256, 0, stream>>>(di, n_items, dw, n_work, partial, ticket, scratch, dsoff, out);
   SVD_CUDA_TRY(cudaGetLastError());
   SVD_CUDA_TRY(cudaFreeAsync(di, stream));
   SVD_CUDA_TRY(cudaFreeAsync(dw, stream));
   SVD_CUDA_TRY(cudaFreeAsync(partial, stream));
   SVD_CUDA_TRY(cudaFreeAsync(ticket, stream));
+  SVD_CUDA_TRY(cudaFreeAsync(scratch, stream));
+  SVD_CUDA_TRY(cudaFreeAsync(dsoff, stream));
   return 0;
 }
 

@@ -95,7 +95,9 @@ def test_penalties_vs_oracle(oracle):
     items = [rng.standard_normal((1, 15)), rng.standard_normal((16, 60)), rng.standard_normal((70, 33)),
              np.linalg.qr(rng.standard_normal((40, 40)))[0], rng.standard_normal((130, 257)), rng.standard_normal((1, 5000))]
     items = [a.astype(np.float32) for a in items]
-    spec = [(a, a.shape[0] > 1, False) for a in items] + [(items[2], True, True)]
+    wide = rng.standard_normal((40, 1000)).astype(np.float32)     # split-K Gram tiles: 4 feature ranges per tile
+    tall = rng.standard_normal((600, 50)).astype(np.float32)      # columns mode with 600 features: 3 ranges
+    spec = [(a, a.shape[0] > 1, False) for a in items] + [(items[2], True, True), (wide, True, False), (tall, True, True)]
     raw = svdlstm.evaluate_penalties(spec)
     raw2 = svdlstm.evaluate_penalties(spec)
     assert np.array_equal(raw, raw2), "fixed-order reduction must be bit-reproducible"
