@@ -1369,7 +1369,13 @@ static int tc_launch_pipe_1024(const void* pp_, int n_cta, uint32_t smem_bytes, 
   return 0;
 }
 
+static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches, int force_ns);
+
 int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
+  return run_tc_one(md, state, weights_dirty, a, stream, launches, 0);
+}
+
+static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches, int force_ns) {
   const char* why = "";
   int nl = 0;
   if (*state == nullptr) {
@@ -1414,14 +1420,38 @@ int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const Forwa
   const bool allow_pipe = L >= 2 && same_h && !(mode_env && mode_env[0] == 's');
   int ns = 32;
   bool pipe = false;
-  if (ns_env) {
-    ns = (atoi(ns_env) == 64 && ok64) ? 64 : 32;
+  if (ns_env || force_ns) {
+    ns = ((force_ns ? force_ns : atoi(ns_env)) == 64 && ok64) ? 64 : 32;
     pipe = allow_pipe && L * ((a.B + ns - 1) / ns) <= n_sm;
   } else if (allow_pipe && L * ((a.B + 31) / 32) <= n_sm) {
     pipe = true;
   } else if (allow_pipe && ok64 && L * ((a.B + 63) / 64) <= n_sm) {
     pipe = true;
     ns = 64;
+  }
+  if (!pipe && allow_pipe && !ns_env && !force_ns) {
+    // Batches too large for one co-resident launch (the rank x sequence sweep: 65 536 sequences): run them as chunks that ARE
+    // pipelined -- layers x tiles <= SM count at the widest tile -- instead of layer-by-layer launches with 32-sequence tiles
+    // (measured on C4: 82 ms -> see DESIGN.md section 5 per forward of 65 536 x 200).  Chunks are independent sequences.
+    const int nsc = ok64 ? 64 : 32;
+    const int chunk = (n_sm / L) * nsc;
+    if (chunk >= nsc && a.B > chunk) {
+      const int n_chunks = (a.B + chunk - 1) / chunk;
+      const int per = round_up((a.B + n_chunks - 1) / n_chunks, nsc);
+      int total = 0;
+      for (int b0 = 0; b0 < a.B; b0 += per) {
+        ForwardArgs sub = a;
+        sub.B = imin(per, a.B - b0);
+        sub.x = a.x + (size_t)b0 * a.T * md.input_dim;
+        sub.y = a.y + (size_t)b0 * a.T * (md.n_out > 0 ? md.n_out : md.layers[L - 1].units);
+        int nl_sub = 0;
+        const int rc = run_tc_one(md, state, weights_dirty && b0 == 0, sub, stream, &nl_sub, nsc);
+        if (rc != 0) return rc;
+        total += nl_sub;
+      }
+      *launches = total;
+      return 0;
+    }
   }
   if (st->ns != ns) weights_dirty = true;
   if (weights_dirty) {

@@ -218,3 +218,18 @@ def test_tc_units_1024_matches_oracle(oracle):
     y = m.predict(x, engine="tc")
     assert m.last_engine() == svdlstm.ENGINE_TC
     _check(y, oracle_twin(oracle, m).predict(x), "tc units=1024 L=3 r=128")
+
+
+def test_tc_large_batch_runs_as_pipelined_chunks():
+    """A batch too large for one co-resident launch (layers x tiles > SM count) is cut into chunks that are each pipelined
+    with 64-sequence tiles; per-sequence results must equal those of a small batch bit for bit (the chunking, the tile
+    width and the position of a sequence never change its arithmetic)."""
+    _, sm = _models(256, 2)
+    m = svdlstm.truncate_singular_model(sm, 48)
+    B = 74 * 64 + 200          # one full chunk of 148 / 2 tiles + a ragged one
+    x = torch.randn(B, 5, 16, generator=torch.Generator().manual_seed(11)).cuda()
+    y = m(x, engine="tc")
+    assert bool(torch.isfinite(y).all())
+    idx = torch.tensor([0, 63, 64, 4735, 4736, B - 1]).cuda()
+    assert torch.equal(m(x[idx], engine="tc"), y[idx])
+    assert torch.equal(m(x[4000:4100], engine="tc"), y[4000:4100])
