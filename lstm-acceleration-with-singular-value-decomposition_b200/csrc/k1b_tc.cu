@@ -949,47 +949,62 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         tc_fence_after();
         if (threadIdx.x == 128) TC_STAMP(10 + 2 * (ub & 1));   // EPI: z block ub seen
         const uint32_t tb = tm_s2 + buf * (uint32_t)(4 * NS) + lane_addr;   // tile slots: i, g(cell), f, o
-        // staged: (i, g) -> the input product i*g, then (f, o).  Keeps the live accumulator set at 2 x CPT registers
-        // (a 64-sequence tile cannot hold 4 x 32 of them next to 64 cell states) and frees half-buffer A early.
+        // staged: (i, g) -> the input product i*g, then (f, o), which frees half-buffer A early.  Inside each stage the
+        // accumulators come out of TMEM in chunks of 8 columns, the loads of chunk k+1 in flight while chunk k goes through
+        // the MUFU: TMEM reads (64 B/clk/SM: 4 096 cycles for the 256 KB of gate accumulators of one step) and the 5 tanh per
+        // cell (5 120 cycles) are the two floors of this epilogue and used to run back to back, not overlapped.
         float ig[CPT];
         {
-          uint32_t zi[CPT], zg[CPT];
-          load_cols(tb + 0u * (uint32_t)NS, zi);
-          load_cols(tb + 1u * (uint32_t)NS, zg);
-          tmem_ld_wait();
-          if (kS2Bufs == 1) {
-            tc_fence_before();
-            mbar_arrive(bar(BAR_S2_EMPTY0));
-          }
+          uint32_t za[2][8], zb[2][8];
+          tmem_ld8(tb + 0u * (uint32_t)NS, za[0]);
+          tmem_ld8(tb + 1u * (uint32_t)NS, zb[0]);
 #pragma unroll
-          for (int n = 0; n < CPT; ++n)
-            ig[n] = fmaf(0.5f, tanh_approx(__uint_as_float(zi[n]) + bi[ub][0]), 0.5f) * tanh_approx(__uint_as_float(zg[n]) + bi[ub][1]);
+          for (int k = 0; k < CPT / 8; ++k) {
+            tmem_ld_wait();
+            if (k + 1 < CPT / 8) {
+              tmem_ld8(tb + 0u * (uint32_t)NS + 8u * (uint32_t)(k + 1), za[(k + 1) & 1]);
+              tmem_ld8(tb + 1u * (uint32_t)NS + 8u * (uint32_t)(k + 1), zb[(k + 1) & 1]);
+            } else if (kS2Bufs == 1) {   // every load of half-buffer A has completed
+              tc_fence_before();
+              mbar_arrive(bar(BAR_S2_EMPTY0));
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+              ig[8 * k + m] = fmaf(0.5f, tanh_approx(__uint_as_float(za[k & 1][m]) + bi[ub][0]), 0.5f) *
+                              tanh_approx(__uint_as_float(zb[k & 1][m]) + bi[ub][1]);
+          }
         }
         if (kS2Bufs == 1) {
           mbar_wait(bar(BAR_S2_FULL1), turn & 1u);         // half-buffer B = tiles (f, o)
           tc_fence_after();
         }
-        uint32_t zf[CPT], zo[CPT];
-        load_cols(tb + 2u * (uint32_t)NS, zf);
-        load_cols(tb + 3u * (uint32_t)NS, zo);
-        tmem_ld_wait();
-        // the accumulators are in registers: hand the TMEM buffer back to the MMA warp right away
-        tc_fence_before();
-        mbar_arrive(bar(kS2Bufs == 1 ? BAR_S2_EMPTY1 : BAR_S2_EMPTY0 + buf));
+        {
+          uint32_t zf[2][8], zo[2][8];
+          tmem_ld8(tb + 2u * (uint32_t)NS, zf[0]);
+          tmem_ld8(tb + 3u * (uint32_t)NS, zo[0]);
 #pragma unroll
-        for (int j8 = 0; j8 < CPT / 8; ++j8) {
-          float hv[8];
+          for (int k = 0; k < CPT / 8; ++k) {
+            tmem_ld_wait();
+            if (k + 1 < CPT / 8) {
+              tmem_ld8(tb + 2u * (uint32_t)NS + 8u * (uint32_t)(k + 1), zf[(k + 1) & 1]);
+              tmem_ld8(tb + 3u * (uint32_t)NS + 8u * (uint32_t)(k + 1), zo[(k + 1) & 1]);
+            } else {   // the accumulators are in registers: hand the TMEM buffer back to the MMA warp right away
+              tc_fence_before();
+              mbar_arrive(bar(kS2Bufs == 1 ? BAR_S2_EMPTY1 : BAR_S2_EMPTY0 + buf));
+            }
+            float hv[8];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const int n = 8 * j8 + m;
-            const float fg = fmaf(0.5f, tanh_approx(__uint_as_float(zf[n]) + bi[ub][2]), 0.5f);
-            const float og = fmaf(0.5f, tanh_approx(__uint_as_float(zo[n]) + bi[ub][3]), 0.5f);
-            const float c = fmaf(fg, cst[ub][n], ig[n]);
-            cst[ub][n] = c;
-            hv[m] = og * tanh_approx(c);
+            for (int m = 0; m < 8; ++m) {
+              const int n = 8 * k + m;
+              const float fg = fmaf(0.5f, tanh_approx(__uint_as_float(zf[k & 1][m]) + bi[ub][2]), 0.5f);
+              const float og = fmaf(0.5f, tanh_approx(__uint_as_float(zo[k & 1][m]) + bi[ub][3]), 0.5f);
+              const float c = fmaf(fg, cst[ub][n], ig[n]);
+              cst[ub][n] = c;
+              hv[m] = og * tanh_approx(c);
+            }
+            sts128(hb_addr + (uint32_t)ub * kRowBlk + 128u * (uint32_t)k, pack_f16(hv[0], hv[1]), pack_f16(hv[2], hv[3]),
+                   pack_f16(hv[4], hv[5]), pack_f16(hv[6], hv[7]));
           }
-          sts128(hb_addr + (uint32_t)ub * kRowBlk + 128u * (uint32_t)j8, pack_f16(hv[0], hv[1]), pack_f16(hv[2], hv[3]),
-                 pack_f16(hv[4], hv[5]), pack_f16(hv[6], hv[7]));
         }
         fence_proxy_async();
         mbar_arrive(bar(BAR_H_READY + ub));
