@@ -295,8 +295,15 @@ struct TcLayerParams {
   int kx;                   // layer 0: K extent of the x part of S2 (= Kin); else 0
   int rows_u, rows_w;       // rows of the S1 A operands, multiples of 8 (rows_u includes the Dense-top rows)
   int n_dense;              // Dense-top outputs fused into S1u (0 = none)
-  int has_s1w;              // layers >= 1
+  int has_s1w;              // layers >= 1 that receive h of the previous layer: they compute their own t_w = A1w . in(t)
   int store_h;              // hand h(t) tiles to the next layer through HBM
+  // t_w hand-off: the NEXT layer's t_w(t) = (L_w sigma_w)^T h(t) shares its B operand with this layer's S1u, so it rides in
+  // extra rows [x_r0, x_r0 + rx) of the S1u tiles (falling out of step t+1's first MMA chain, like the Dense top) and is handed
+  // over -- already in the layout the next layer's S2 consumes -- instead of h: the next layer has no S1w segment to stream
+  // and no H-row input tile; the hand-off image is rx_pad/H of the size.
+  int store_x;              // this layer ships t_w tiles of the next layer (then store_h = 0)
+  int rx, rx_pad, x_r0;     // rows of the next layer's t_w, padded to 16, first S1u row
+  int early_part;           // what the early (input) part of S2 contracts with: 1 = dense W0 (layer 0: x), 2 = R_w (t_w tiles / own t_w)
   int in_stages;            // depth of the input prefetch ring
   int streaming, w_slots;   // weight stream: 0 = resident; 1 = ring of w_slots slots of slot_bytes
   uint32_t slot_bytes;
@@ -305,7 +312,7 @@ struct TcLayerParams {
 };
 
 struct TcSmemPlan {
-  uint32_t w, hbuf, tbuf, inbuf, bars, tmem_slot, ctab, total;
+  uint32_t w, hbuf, tbuf, inbuf, xbuf, bars, tmem_slot, ctab, total;
 };
 
 __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
@@ -316,6 +323,7 @@ __host__ __device__ inline TcSmemPlan tc_plan(const TcLayerParams& p) {
   s.hbuf = off; off += act_tile_bytes(p.H, p.ns);
   s.tbuf = off; off += act_tile_bytes(p.ru_pad + p.rw_pad, p.ns);
   s.inbuf = off; off += (uint32_t)p.in_stages * act_tile_bytes(p.Kin, p.ns);
+  s.xbuf = off; off += p.store_x ? act_tile_bytes(p.rx_pad, p.ns) : 0u;
   s.bars = off; off += 512;
   s.tmem_slot = off; off += 16;
   // streaming: the chunk table (offset, bytes in 256-byte units) lives in smem -- with a 227 KB carve-out there is no L1 to cache it
@@ -382,7 +390,7 @@ __host__ __device__ inline void for_seg_u(const P& p, F&& f) {
 template <class P, class F>
 __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
   const int ke = p.has_s1w ? p.rw_pad : p.kx;
-  const int part_e = p.has_s1w ? 2 : 1;
+  const int part_e = p.early_part;
   if (p.streaming) {   // streamed: tile by tile (early chunks, then late chunks of the same tile)
 #pragma unroll 1
     for (int ub = 0; ub < p.H / 128; ++ub)
@@ -452,7 +460,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
   const uint32_t in_tile = act_tile_bytes(p.Kin, NS), h_tile = act_tile_bytes(H, NS);
   const uint32_t bar0 = sbase + sp.bars;
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int n_steps = T + (p.n_dense > 0 ? 1 : 0);   // the Dense-top output of step T-1 needs one more S1u pass
+  const int n_steps = T + ((p.n_dense > 0 || p.store_x) ? 1 : 0);   // the Dense-top / t_w rows of step T-1 need one more S1u pass
 
   // ---- one-time setup ---------------------------------------------------------------------------
   // zero the activation buffers (h(-1) = 0; padded rows must be finite)
@@ -562,13 +570,15 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     }
   } else if (warp == 2) {
     // ======================= hidden-sequence stores (hand-off to the next layer) ====================================
-    if (lane == 0 && p.store_h) {
-      uint8_t* out = p.out_seq + (size_t)cta * T * h_tile;
+    if (lane == 0 && (p.store_h || p.store_x)) {
+      const uint32_t o_tile = p.store_x ? act_tile_bytes(p.rx_pad, NS) : h_tile;   // what is handed over: t_w(t) of the next layer, or h(t)
+      const uint32_t o_src = sbase + (p.store_x ? sp.xbuf : sp.hbuf);
+      uint8_t* out = p.out_seq + (size_t)cta * T * o_tile;
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        // h(t) complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
+        // tile t complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
         mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
-        bulk_s2g(out + (size_t)t * h_tile, sbase + sp.hbuf, h_tile);
+        bulk_s2g(out + (size_t)t * o_tile, o_src, o_tile);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar(BAR_H_STORED));
@@ -845,10 +855,16 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     const int b_first = cta * NS + c0;         // global sequence index of this thread's first column
     // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
-    uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0;
+    uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0, x_ld = 0, x_st = 0, x_live = 0;
     int e1u_tiles = 0, e1w_tiles = 0;
     for (int mt = 0; mt < 3; ++mt) {
       const int r0 = mt * 128, j = r0 + row;
+      if (p.store_x) {
+        const int lo = r0 + q * 32;   // this warp's 32 rows of the tile
+        if (r0 < p.rows_u && lo + 32 > p.x_r0 && lo < p.x_r0 + p.rx_pad) x_ld |= 1u << mt;   // warp-uniform
+        if (j >= p.x_r0 && j < p.x_r0 + p.rx_pad) x_st |= 1u << mt;
+        if (j >= p.x_r0 && j < p.x_r0 + p.rx) x_live |= 1u << mt;
+      }
       if (r0 < p.rows_u && r0 + q * 32 < e1_rows_u) { u_ld |= 1u << mt; e1u_tiles = mt + 1; }   // warp-uniform
       if (j < p.ru_pad) u_st |= 1u << mt;
       if (j < p.ru) u_live |= 1u << mt;
@@ -929,6 +945,19 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         if (threadIdx.x == 128) TC_STAMP(6);   // EPI: proxy fence done
         mbar_arrive(bar(BAR_T_READY));
         if (threadIdx.x == 128) TC_STAMP(9);   // EPI: t operand written + arrived
+      }
+      if (p.store_x && t > 0) {   // the next layer's t_w(t-1): off the critical path, after the t operand has been published
+        if (t > 1) mbar_wait(bar(BAR_H_STORED), (uint32_t)(t - 2) & 1u);   // the tile of step t-2 has been shipped
+        uint32_t ax[CPT];
+#pragma unroll 1
+        for (int mt = 0; mt < 3; ++mt) {
+          if (!((x_ld >> mt) & 1u)) continue;
+          load_cols(tm_u + (uint32_t)(mt * NS), ax);
+          tmem_ld_wait();
+          if ((x_st >> mt) & 1u) store_row(sbase + sp.xbuf + act_offset(mt * 128 + row - p.x_r0, c0, NS), ax, (x_live >> mt) & 1u);
+        }
+        fence_proxy_async();
+        mbar_arrive(bar(BAR_H_DONE));
       }
       if (t > 0 && y_ptr != nullptr) {   // Dense top of step t-1 (off the critical path: after the arrive)
         float* yp = y_ptr + (size_t)(t - 1) * p.n_dense;
@@ -1068,8 +1097,8 @@ __device__ __forceinline__ float block_left(const Block& b, int k, int j) {   //
   return b.left[(size_t)k * b.left_ld + j] * (b.scale ? b.scale[j] : 1.f);
 }
 
-__global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, int H, int D, int ru_pad,
-                                    const float* __restrict__ dense_k, int n_dense, int n_out, __half* __restrict__ img) {
+__global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, Block bw_next, int x_r0, int rx, int H, int D,
+                                    int ru_pad, const float* __restrict__ dense_k, int n_dense, int n_out, __half* __restrict__ img) {
   const PackChunk c = chunks[blockIdx.x];
   __half* out = img + c.byte_off / 2;
   const int total = c.rows * c.kc;
@@ -1083,6 +1112,7 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
       const int j = c.r0 + row, kk = c.k0 + k;
       if (j < bu.rank) v = block_left(bu, kk, j);
       else if (j - bu.rank < n_dense) v = dense_k[(size_t)kk * n_out + (j - bu.rank)];
+      else if (rx > 0 && j >= x_r0 && j - x_r0 < rx) v = block_left(bw_next, kk, j - x_r0);   // the next layer's (L_w sigma_w)^T rows
     } else {
       const int gate = (c.g == 1) ? 2 : (c.g == 2) ? 1 : c.g;   // tile slots are ordered i, g(cell), f, o; Keras columns i, f, c, o
       const int n = gate * H + c.ub * 128 + row;
@@ -1250,6 +1280,19 @@ void tc_free(TcState* s) {
   delete s;
 }
 
+// Does layer l hand the NEXT layer's t_w over (instead of its own h)?  Needs the extra S1u rows to fit the S1u TMEM tiles
+// (3 tiles of 128 rows at 32-sequence tiles, 2 at 64) and merged factored cells on both sides.  SVDLSTM_TC_HANDOFF=h disables it.
+static bool tc_tw_handoff(const ModelDesc& md, int l, int ns) {
+  if (l + 1 >= md.n_layers) return false;
+  const char* e = getenv("SVDLSTM_TC_HANDOFF");
+  if (e && e[0] == 'h') return false;
+  const LayerDesc& A = md.layers[l];
+  const LayerDesc& B = md.layers[l + 1];
+  if (A.n_blocks != 2 || B.n_blocks != 2 || B.blocks[0].left == nullptr) return false;
+  const int s1_rows_max = ns == 64 ? 256 : 384;
+  return round_up(A.blocks[1].rank, 8) + round_up(B.blocks[0].rank, 8) <= s1_rows_max;
+}
+
 static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p, const char** why) {
   const LayerDesc& L = md.layers[l];
   if (L.n_blocks != 2) { *why = "only merged (non-split) cell forms run on the tensor-core engine"; return false; }
@@ -1274,10 +1317,26 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   p.n_dense = (last && md.n_out > 0 && round_up(bu.rank + md.n_out, 8) <= s1_rows_max) ? md.n_out : 0;
   p.store_h = p.n_dense > 0 ? 0 : 1;
   p.rows_u = round_up(p.ru + p.n_dense, 8);
+  const bool in_tw = l > 0 && tc_tw_handoff(md, l - 1, ns), out_tw = tc_tw_handoff(md, l, ns);
+  if (out_tw) {
+    p.store_x = 1;
+    p.store_h = 0;
+    p.rx = md.layers[l + 1].blocks[0].rank;
+    p.rx_pad = round_up(p.rx, 16);
+    p.x_r0 = p.rows_u;
+    p.rows_u = round_up(p.x_r0 + p.rx, 8);
+  }
+  p.early_part = l == 0 ? 1 : 2;
+  if (in_tw) p.has_s1w = 0;
   if (ns == 64 && H > 256) { *why = "64-sequence tiles support units <= 256"; return false; }
   if (l == 0) {
     if (L.d_in > 64) { *why = "layer-0 input_dim above 64 is not supported by the tensor-core engine yet"; return false; }
     p.Kin = round_up(L.d_in, 16);
+    p.kx = p.Kin;
+    p.rw_pad = 0;
+    p.rows_w = 0;
+  } else if (in_tw) {   // the input tiles ARE t_w(t): they enter the early part of S2 directly, like x(t) on layer 0
+    p.Kin = round_up(bw.rank, 16);
     p.kx = p.Kin;
     p.rw_pad = 0;
     p.rows_w = 0;
@@ -1298,7 +1357,10 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   p.in_stages = 3;
   if (tc_plan(p).total > kSmemCap) p.in_stages = 2;
   if (tc_plan(p).total > kSmemCap && p.has_s1w) p.in_stages = 1;   // the tile of step t+1 is fetched while step t computes
-  if (tc_plan(p).total > kSmemCap) {
+  // 64-sequence tiles always stream: with ONE S2 accumulator buffer the streamed issue order (tile by tile, half-buffer (i,g)
+  // handed to the epilogue while (f,o) is still being issued) overlaps MMA and epilogue where the resident order (whole unit
+  // block per asm block) cannot -- measured 4.95 vs 5.26 ms at ranks 8-16, 5.08 vs 5.47 ms at rank 32 on C3.
+  if (tc_plan(p).total > kSmemCap || ns == 64) {
     p.streaming = 1;
     p.in_stages = p.has_s1w ? 1 : 2;   // every KB goes to the weight ring: its depth must cover the L2 latency
     // ring-slot fills: consecutive chunks of a segment share a slot up to slot_bytes (same greedy rule as the MMA warp's cursor).
@@ -1538,7 +1600,8 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
       }
       SVD_REQUIRE((int)chunks.size() == p.n_chunks_w + p.n_chunks_u + p.n_chunks_2, "tensor-core engine: chunk table mismatch");
       const LayerDesc& Ld = md.layers[l];
-      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, Ld.blocks[0], Ld.blocks[1], p.H, Ld.d_in, p.ru_pad,
+      const Block bw_next = l + 1 < L ? md.layers[l + 1].blocks[0] : Block{};
+      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, Ld.blocks[0], Ld.blocks[1], bw_next, p.x_r0, p.rx, p.H, Ld.d_in, p.ru_pad,
                                                                        md.dense_kernel, p.n_dense, md.n_out,
                                                                        reinterpret_cast<__half*>(li.wimg));
       pack_bias_kernel<<<(4 * p.H + 255) / 256, 256, 0, stream>>>(Ld.bias, p.H, li.bias);
@@ -1571,8 +1634,8 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     ws->xseq_bytes = xbytes;
   }
   for (int l = 0; l < L; ++l) {
-    if (!st->layers[l].prm.store_h) continue;
-    const size_t hb = (size_t)n_cta * T * act_tile_bytes(st->layers[l].prm.H, ns);
+    if (!st->layers[l].prm.store_h && !st->layers[l].prm.store_x) continue;
+    const size_t hb = (size_t)n_cta * T * (st->layers[l].prm.store_x ? act_tile_bytes(st->layers[l].prm.rx_pad, ns) : act_tile_bytes(st->layers[l].prm.H, ns));
     const int slot = pipe ? l : (l & 1);
     if (ws->seq_bytes[slot] < hb) {
       if (ws->seq[slot]) {
@@ -1616,7 +1679,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
     const int in_slot = pipe ? l - 1 : ((l - 1) & 1), out_slot = pipe ? l : (l & 1);
     p.in_seq = (l == 0) ? ws->xseq : ws->seq[in_slot];
-    p.out_seq = p.store_h ? ws->seq[out_slot] : nullptr;
+    p.out_seq = (p.store_h || p.store_x) ? ws->seq[out_slot] : nullptr;
     p.y = a.y;
     p.dense_bias = md.dense_bias;
     const TcSmemPlan sp = tc_plan(p);
