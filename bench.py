@@ -368,13 +368,17 @@ def main():
             traffic = json.load(open(tp)).get("rank_%d" % a.rank)
         except Exception:
             traffic = None
+    # rows handed from layer to layer per sequence-step: the next layer's t_w (rank rows, padded to 16) when they fit the S1u
+    # TMEM tiles next to this layer's t_u rows, else the hidden state itself
+    r_eff = min(a.rank, a.hidden)
+    handoff_rows = (r_eff + 15) // 16 * 16 if 2 * ((r_eff + 7) // 8 * 8) <= 256 else a.hidden
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
                 "peak_source": pk["source"] + " (cuBLAS bf16 sustained; f16 runs at the same tensor rate)",
                 "kernel": "lstm_tc_pipe_kernel: all %d layers in one co-resident launch, 64-sequence tiles (one forward = pack_x + this launch)"
                           % a.layers if eng_id == 3 else eng_name,
                 "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms,
-                "hbm_bytes_algorithmic": int(B * T * (D * 4 + 4) + (a.layers - 1) * 2 * B * T * a.hidden * 2 + B * T * D * 2 * 2)}
+                "hbm_bytes_algorithmic": int(B * T * (D * 4 + 4) + (a.layers - 1) * 2 * B * T * handoff_rows * 2 + B * T * D * 2 * 2)}
     line = {"metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": value, "unit": "sequence-timesteps/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16" if eng_id == 3 else "f32", "data": "synthetic", "config": workload_config(a),
