@@ -41,7 +41,7 @@ typedef struct svdlstm_model_s* svdlstm_handle;
 #define SVDLSTM_ENGINE_GENERAL  1   /* FP32 CUDA-core batched persistent kernel (any shape)        */
 #define SVDLSTM_ENGINE_WAVEFRONT 2  /* FP32 register-resident warp-per-layer wavefront (H,D,r<=32) */
 #define SVDLSTM_ENGINE_TC       3   /* tcgen05 tensor-core persistent kernel: FP16 operands, FP32 accumulate + cell state
-                                       (reduced precision; merged 3-/2-factor cells, units in {128..512}, ranks <= 256,
+                                       (reduced precision; merged 3-/2-factor cells, units in {128..512, 1024}, ranks <= 256,
                                        return_sequences, zero initial state, no mask) */
 #define SVDLSTM_ENGINE_TC_BF16  SVDLSTM_ENGINE_TC   /* first version of that engine used BF16 operands; alias kept */
 
