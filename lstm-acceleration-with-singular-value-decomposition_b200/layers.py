@@ -125,6 +125,12 @@ class Handle:
         else:
             B, T = int(x.shape[0]), int(x.shape[1])
         n = self.n_out if self.n_out > 0 else self.units[-1]
+        if (not return_sequences and _engine_id(engine) == C.ENGINE_TC and not time_major and not go_backwards
+                and initial_state is None and mask is None and not want_state):
+            # The tensor-core kernel always produces the whole output sequence (the Dense top is fused into its S1 tiles, one
+            # step behind); return_sequences=False (svd_classes_v3.py:428-431: last output only) is the last step of it.
+            y, _, _ = self.forward(x, return_sequences=True, engine=engine)
+            return y[:, -1].contiguous(), None, None
         if return_sequences:
             y = torch.empty((T, B, n) if time_major else (B, T, n), dtype=torch.float32, device=dev)
         else:

@@ -233,3 +233,17 @@ def test_tc_large_batch_runs_as_pipelined_chunks():
     idx = torch.tensor([0, 63, 64, 4735, 4736, B - 1]).cuda()
     assert torch.equal(m(x[idx], engine="tc"), y[idx])
     assert torch.equal(m(x[4000:4100], engine="tc"), y[4000:4100])
+
+
+def test_tc_last_output_only():
+    """return_sequences=False (svd_classes_v3.py:428-431) on the tensor-core engine = the last step of the sequence it
+    always computes; must equal the sliced full output bit for bit and match the FP32 engine's last output."""
+    layers, dense = svdlstm.synthetic_layers(16, 128, 2, seed=3)
+    full = svdlstm.full_model_from_weights(layers, dense)          # return_sequences=False model
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=False)
+    m = svdlstm.truncate_singular_model(sm, 24)
+    x = torch.randn(50, 12, 16, generator=torch.Generator().manual_seed(10)).cuda()
+    y_tc = m(x, engine="tc")
+    y32 = m(x, engine="general")
+    assert tuple(y_tc.shape) == tuple(y32.shape) == (50, 1)
+    assert float((y_tc - y32).abs().max()) < 2e-3 * float(y32.abs().max()) + 2e-4
