@@ -308,6 +308,13 @@ struct TcLayerParams {
   int streaming, w_slots;   // weight stream: 0 = resident; 1 = ring of w_slots slots of slot_bytes
   uint32_t slot_bytes;
   uint32_t segw_bytes, segu_bytes, seg2_bytes;
+  // initial_state / return_state (svd_classes_v3.py:393,433-434) of THIS layer, (B, H) float32 each, or nullptr.  h enters and leaves
+  // as float32 but lives as FP16 between steps, exactly like every h(t) of this engine (h_n is that FP16 value): a sequence run in
+  // time chunks with the state carried over is bit-identical to the unchunked run.
+  const float* h0;
+  const float* c0;
+  float* h_n;
+  float* c_n;
   long long* dbg;           // optional timeline buffer (CTA 0): 16 clock64 stamps per step; nullptr = off
 };
 
@@ -440,7 +447,9 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 // step counters in global memory through which the previous layer's CTA publishes -- and this CTA announces -- how many
 // hidden-sequence tiles have landed in the hand-off image.
 // EW = epilogue warps (8, or 16 for H > 512: the cell state of NUB x 128 cells x NS sequences lives in their registers).
-template <int NUB, bool STREAM, int NS, int EW = kEpiWarps>
+// STATE = initial_state / return_state plumbing compiled in (a separate instantiation: even untaken, its extra live pointers cost
+// the epilogue-bound ranks 20 %).
+template <int NUB, bool STREAM, int NS, int EW = kEpiWarps, bool STATE = false>
 __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta) {
   constexpr int CPT = NS * 4 / EW;            // accumulator columns per epilogue thread (EW / 4 warps per TMEM lane quarter)
   constexpr int kTcThreads = 32 * (4 + EW);   // (shadow the 8-warp defaults of the file scope)
@@ -495,6 +504,22 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     mbar_init(bar(BAR_H_DONE), kEpiThreads);
     mbar_init(bar(BAR_H_STORED), 1);
     fence_barrier_init();
+  }
+  if (STATE && p.h0 != nullptr) {   // h(-1) = initial state, as the FP16 B operand of the first S1u pass
+    __syncthreads();       // (after the zero fill above)
+    if (warp >= 4) {
+      const int ew0 = warp - 4, row0 = (ew0 & 3) * 32 + lane, cc0 = (ew0 >> 2) * CPT;
+      for (int ub = 0; ub < NUB; ++ub)
+        for (int j8 = 0; j8 < CPT / 8; ++j8) {
+          float v[8];
+          for (int m = 0; m < 8; ++m) {
+            const int b = cta * NS + cc0 + 8 * j8 + m;
+            v[m] = b < p.B ? p.h0[(size_t)b * H + ub * 128 + row0] : 0.f;
+          }
+          sts128(sbase + sp.hbuf + act_offset(ub * 128 + row0, cc0 + 8 * j8, NS), pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]),
+                 pack_f16(v[6], v[7]));
+        }
+    }
   }
   if (warp == 1) tmem_alloc(sbase + sp.tmem_slot, 512);
   fence_proxy_async();   // generic-proxy zero fill -> visible to the async proxy (MMA / bulk copies)
@@ -853,6 +878,13 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
 #pragma unroll
       for (int g = 0; g < 4; ++g) bi[u][g] = p.bias[(u * 4 + g) * 128 + row];
     const int b_first = cta * NS + c0;         // global sequence index of this thread's first column
+    if (STATE && p.c0 != nullptr) {
+#pragma unroll
+      for (int u = 0; u < NUB; ++u)
+#pragma unroll
+        for (int n = 0; n < CPT; ++n)
+          if (b_first + n < p.B) cst[u][n] = p.c0[(size_t)(b_first + n) * H + u * 128 + row];
+    }
     // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
     uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0, x_ld = 0, x_st = 0, x_live = 0;
@@ -1044,6 +1076,20 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       if (p.has_s1w && t + 1 < T) e1w((uint32_t)(t + 1) & 1u);
       if (threadIdx.x == 128) TC_STAMP(14);      // EPI: h(t) published
     }
+    if (STATE && p.h_n != nullptr) {   // return_state: h(T-1) as this engine holds it (FP16 between steps): read back this thread's own stores
+      for (int u = 0; u < NUB; ++u)
+        for (int n = 0; n < CPT; ++n)
+          if (b_first + n < p.B)
+            p.h_n[(size_t)(b_first + n) * H + u * 128 + row] =
+                __half2float(*reinterpret_cast<const __half*>(smem + sp.hbuf + act_offset(u * 128 + row, c0 + n, NS)));
+    }
+    if (STATE && p.c_n != nullptr) {   // return_state: c(T-1), float32 all along
+#pragma unroll
+      for (int u = 0; u < NUB; ++u)
+#pragma unroll
+        for (int n = 0; n < CPT; ++n)
+          if (b_first + n < p.B) p.c_n[(size_t)(b_first + n) * H + u * 128 + row] = cst[u][n];
+    }
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -1054,9 +1100,9 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
 }
 
 // layers launched one after the other (any batch size): grid = tiles of one layer
-template <int NUB, bool STREAM, int NS, int EW = kEpiWarps>
+template <int NUB, bool STREAM, int NS, int EW = kEpiWarps, bool STATE = false>
 __global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_layer_kernel(const TcLayerParams p) {
-  tc_layer_body<NUB, STREAM, NS, EW>(p, (int)blockIdx.x, nullptr, nullptr, blockIdx.x == 0);
+  tc_layer_body<NUB, STREAM, NS, EW, STATE>(p, (int)blockIdx.x, nullptr, nullptr, blockIdx.x == 0);
 }
 
 // ALL layers in one (cooperative, fully co-resident) launch: CTA b runs layer b / n_tiles on tile b % n_tiles and the layers
@@ -1390,7 +1436,8 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
 }
 
 bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why) {
-  if (a.mask || a.h0 || a.h_n || a.c_n) { *why = "mask / initial_state / return_state are FP32-engine features"; return false; }
+  if (a.mask) { *why = "mask is an FP32-engine feature"; return false; }
+  if ((a.h0 == nullptr) != (a.c0 == nullptr)) { *why = "initial_state needs both h and c"; return false; }
   if (a.flags & (SVDLSTM_GO_BACKWARDS | SVDLSTM_TIME_MAJOR)) { *why = "go_backwards / time_major are FP32-engine features"; return false; }
   if (!(a.flags & SVDLSTM_RETURN_SEQUENCES)) { *why = "return_sequences=False is an FP32-engine feature"; return false; }
   for (int l = 0; l < md.n_layers; ++l) {
@@ -1412,6 +1459,11 @@ static int tc_launch_layer(const TcLayerParams& p, int n_cta, uint32_t smem_byte
       set_error("tensor-core engine: 64-sequence tiles need units <= 256");
       return -1;
     }
+  }
+  if (p.h0 || p.h_n || p.c_n) {   // initial_state / return_state: the instantiation that carries the state plumbing
+    SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB, STREAM, 32, kEpiWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    lstm_tc_layer_kernel<NUB, STREAM, 32, kEpiWarps, true><<<n_cta, kTcThreads, smem_bytes, stream>>>(p);
+    return 0;
   }
   SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_layer_kernel<NUB, STREAM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   lstm_tc_layer_kernel<NUB, STREAM, 32><<<n_cta, kTcThreads, smem_bytes, stream>>>(p);
@@ -1480,6 +1532,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     const bool force_pair = mode_env && strcmp(mode_env, "pair") == 0;
     if (force_pair) {
       SVD_REQUIRE(pair_supported(md, &why), "tensor-core engine (SVDLSTM_TC_MODE=pair): %s", why);
+      SVD_REQUIRE(!(a.h0 || a.h_n || a.c_n), "tensor-core engine (SVDLSTM_TC_MODE=pair): initial_state / return_state are not supported by the paired kernel");
       int dev0 = 0;
       SVD_CUDA_TRY(cudaGetDevice(&dev0));
       SVD_REQUIRE(dev0 >= 0 && dev0 < 16, "tensor-core engine: device ordinal %d out of range", dev0);
@@ -1497,7 +1550,11 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   const bool allow_pipe = L >= 2 && same_h && !(mode_env && mode_env[0] == 's');
   int ns = 32;
   bool pipe = false;
-  if (ns_env || force_ns) {
+  const bool has_state = a.h0 || a.h_n || a.c_n;
+  if (has_state) {
+    // initial_state / return_state: one launch per layer, 32-sequence tiles (the kernel instantiations that carry the state plumbing)
+    SVD_REQUIRE(md.layers[0].units <= 512, "tensor-core engine: initial_state / return_state need units <= 512");
+  } else if (ns_env || force_ns) {
     ns = ((force_ns ? force_ns : atoi(ns_env)) == 64 && ok64) ? 64 : 32;
     pipe = allow_pipe && L * ((a.B + ns - 1) / ns) <= n_sm;
   } else if (allow_pipe && L * ((a.B + 31) / 32) <= n_sm) {
@@ -1506,7 +1563,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     pipe = true;
     ns = 64;
   }
-  if (!pipe && allow_pipe && !ns_env && !force_ns) {
+  if (!pipe && allow_pipe && !ns_env && !force_ns && !has_state) {   // (state arrays are (layer, B, H): not sliceable by one pointer offset)
     // Batches too large for one co-resident launch (the rank x sequence sweep: 65 536 sequences): run them as chunks that ARE
     // pipelined -- layers x tiles <= SM count at the widest tile -- instead of layer-by-layer launches with 32-sequence tiles
     // (measured on C4: 82 ms -> see DESIGN.md section 5 per forward of 65 536 x 200).  Chunks are independent sequences.
@@ -1682,6 +1739,14 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     p.out_seq = (p.store_h || p.store_x) ? ws->seq[out_slot] : nullptr;
     p.y = a.y;
     p.dense_bias = md.dense_bias;
+    {
+      size_t soff = 0;   // state arrays: [layer][B][units]
+      for (int i = 0; i < l; ++i) soff += (size_t)B * md.layers[i].units;
+      p.h0 = a.h0 ? a.h0 + soff : nullptr;
+      p.c0 = a.c0 ? a.c0 + soff : nullptr;
+      p.h_n = a.h_n ? a.h_n + soff : nullptr;
+      p.c_n = a.c_n ? a.c_n + soff : nullptr;
+    }
     const TcSmemPlan sp = tc_plan(p);
     if (pipe) {
       pp.layer[l] = p;

@@ -192,6 +192,22 @@ class Sequential:
             a = l.call(a, engine=eng) if isinstance(l, SingularLSTM) else l.call(a)
         return a
 
+    def stream(self, X, state=None, engine=None):
+        """Stateful streaming on the device (the reference's ``stateful=True`` use, svd_classes_v3.py:421-426, for the
+        real-time setting of svd_acceleration_v3.py:151): run one time chunk X (batch, time, features) starting from
+        ``state`` = (hs, cs) -- lists with one (batch, units) tensor per LSTM layer, as returned by the previous call, or
+        None for zeros -- and return (y, state).  Chunked runs equal one long run: bit for bit on the tensor-core
+        engine, to float32 rounding on the FP32 engines."""
+        x = C.dev_tensor(X)
+        if x.dim() != 3:
+            raise ValueError("expected input of shape (batch, time, features)")
+        self.build((None, None, int(x.shape[-1])))
+        if not self._fusable():
+            raise ValueError("stream() needs a stack of LSTM layers (+ Dense top) that runs as one fused handle")
+        eng = engine if engine is not None else self.engine
+        y, hs, cs = self._fused_handle().forward(x, initial_state=state, return_sequences=True, want_state=True, engine=eng)
+        return y, (hs, cs)
+
     def predict(self, X, batch_size=32, verbose=0, engine=None):
         """Keras ``model.predict`` (svd_acceleration_v3.py:148,151): host array in, host array out.
         Sequences are independent, so the whole batch runs as one launch regardless of batch_size."""

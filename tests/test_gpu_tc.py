@@ -247,3 +247,38 @@ def test_tc_last_output_only():
     y32 = m(x, engine="general")
     assert tuple(y_tc.shape) == tuple(y32.shape) == (50, 1)
     assert float((y_tc - y32).abs().max()) < 2e-3 * float(y32.abs().max()) + 2e-4
+
+
+@pytest.mark.parametrize("H,L,rank,B", [(256, 2, 128, 100), (128, 2, 16, 45), (256, 1, 64, 33)])
+def test_tc_state_carried_over_time_chunks(H, L, rank, B):
+    """initial_state / return_state on the tensor-core engine (svd_classes_v3.py:393,433-434): a sequence run in two
+    time chunks with (h, c) carried over must equal the unchunked run BIT FOR BIT (h lives as FP16 between steps
+    either way, c as FP32), and the returned state must match the FP32 engine's within the engine tolerance."""
+    _, sm = _models(H, L)
+    m = svdlstm.truncate_singular_model(sm, rank)
+    x = torch.randn(B, 14, 16, generator=torch.Generator().manual_seed(12)).cuda()
+    m(x[:2], engine="tc")                                   # builds the fused handle
+    h = m._fused_handle()
+    y_all, hs_all, cs_all = h.forward(x, want_state=True, engine="tc")
+    y_a, hs_a, cs_a = h.forward(x[:, :5].contiguous(), want_state=True, engine="tc")
+    y_b, hs_b, cs_b = h.forward(x[:, 5:].contiguous(), initial_state=(hs_a, cs_a), want_state=True, engine="tc")
+    assert torch.equal(torch.cat([y_a, y_b], 1), y_all)
+    for l in range(L):
+        assert torch.equal(cs_b[l], cs_all[l]) and torch.equal(hs_b[l], hs_all[l])
+    y32, hs32, cs32 = h.forward(x, want_state=True, engine="general")
+    for l in range(L):
+        assert float((hs_all[l] - hs32[l]).abs().max()) < 3e-3
+        assert float((cs_all[l] - cs32[l]).abs().max()) < 3e-3 * max(1.0, float(cs32[l].abs().max()))
+
+
+def test_tc_stream_api_matches_one_long_run():
+    """Sequential.stream: three time chunks with the state handed back in == one run (tensor-core engine: bit for bit)."""
+    _, sm = _models(256, 2)
+    m = svdlstm.truncate_singular_model(sm, 96)
+    x = torch.randn(70, 21, 16, generator=torch.Generator().manual_seed(13)).cuda()
+    y_all = m(x, engine="tc")
+    state, parts = None, []
+    for lo, hi in ((0, 4), (4, 13), (13, 21)):
+        y, state = m.stream(x[:, lo:hi].contiguous(), state, engine="tc")
+        parts.append(y)
+    assert torch.equal(torch.cat(parts, 1), y_all)
