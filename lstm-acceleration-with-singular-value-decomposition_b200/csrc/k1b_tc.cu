@@ -889,7 +889,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
     uint32_t u_ld = 0, u_st = 0, u_live = 0, w_ld = 0, w_st = 0, w_live = 0, x_ld = 0, x_st = 0, x_live = 0;
     int e1u_tiles = 0, e1w_tiles = 0;
-    for (int mt = 0; mt < 3; ++mt) {
+    for (int mt = 0; mt < 4; ++mt) {   // up to 4 S1u tiles (layers without an S1w of their own), 2 S1w tiles
       const int r0 = mt * 128, j = r0 + row;
       if (p.store_x) {
         const int lo = r0 + q * 32;   // this warp's 32 rows of the tile
@@ -982,7 +982,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
         if (t > 1) mbar_wait(bar(BAR_H_STORED), (uint32_t)(t - 2) & 1u);   // the tile of step t-2 has been shipped
         uint32_t ax[CPT];
 #pragma unroll 1
-        for (int mt = 0; mt < 3; ++mt) {
+        for (int mt = 0; mt < 4; ++mt) {
           if (!((x_ld >> mt) & 1u)) continue;
           load_cols(tm_u + (uint32_t)(mt * NS), ax);
           tmem_ld_wait();
@@ -1326,17 +1326,21 @@ void tc_free(TcState* s) {
   delete s;
 }
 
-// Does layer l hand the NEXT layer's t_w over (instead of its own h)?  Needs the extra S1u rows to fit the S1u TMEM tiles
-// (3 tiles of 128 rows at 32-sequence tiles, 2 at 64) and merged factored cells on both sides.  SVDLSTM_TC_HANDOFF=h disables it.
-static bool tc_tw_handoff(const ModelDesc& md, int l, int ns) {
-  if (l + 1 >= md.n_layers) return false;
+// Which layers hand the NEXT layer's t_w over (instead of their own h)?  The extra S1u rows must fit the S1u TMEM tiles: 2 tiles of
+// 128 rows at 64-sequence tiles, 3 at 32 -- or 4 when the layer has no S1w of its own (layer 0, and every layer that itself receives
+// t_w: its S1w TMEM region is free).  Needs merged factored cells on both sides.  SVDLSTM_TC_HANDOFF=h disables it.
+static int tc_s1u_tiles_max(int ns, bool no_s1w) { return no_s1w ? 4 : (ns == 64 ? 2 : 3); }
+static void tc_handoff_chain(const ModelDesc& md, int ns, bool out[kMaxLayers]) {
   const char* e = getenv("SVDLSTM_TC_HANDOFF");
-  if (e && e[0] == 'h') return false;
-  const LayerDesc& A = md.layers[l];
-  const LayerDesc& B = md.layers[l + 1];
-  if (A.n_blocks != 2 || B.n_blocks != 2 || B.blocks[0].left == nullptr) return false;
-  const int s1_rows_max = ns == 64 ? 256 : 384;
-  return round_up(A.blocks[1].rank, 8) + round_up(B.blocks[0].rank, 8) <= s1_rows_max;
+  const bool off = e && e[0] == 'h';
+  for (int l = 0; l < kMaxLayers; ++l) out[l] = false;
+  for (int l = 0; l + 1 < md.n_layers; ++l) {
+    const LayerDesc& A = md.layers[l];
+    const LayerDesc& B = md.layers[l + 1];
+    if (off || A.n_blocks != 2 || B.n_blocks != 2 || B.blocks[0].left == nullptr) continue;
+    const bool no_s1w = l == 0 || out[l - 1];
+    out[l] = round_up(A.blocks[1].rank, 8) + round_up(B.blocks[0].rank, 8) <= 128 * tc_s1u_tiles_max(ns, no_s1w);
+  }
 }
 
 static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p, const char** why) {
@@ -1359,11 +1363,13 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   p.has_s1w = l > 0;
   // The Dense top rides in spare rows of the S1u tiles when they fit TMEM (3 tiles of 128 rows at 32-sequence tiles, 2 at
   // 64); otherwise the layer stores its hidden sequence and dense_top_kernel finishes the job.
-  const int s1_rows_max = ns == 64 ? 256 : 384;
+  bool handoff[kMaxLayers];
+  tc_handoff_chain(md, ns, handoff);
+  const bool in_tw = l > 0 && handoff[l - 1], out_tw = handoff[l];
+  const int s1_rows_max = 128 * tc_s1u_tiles_max(ns, l == 0 || in_tw);
   p.n_dense = (last && md.n_out > 0 && round_up(bu.rank + md.n_out, 8) <= s1_rows_max) ? md.n_out : 0;
   p.store_h = p.n_dense > 0 ? 0 : 1;
   p.rows_u = round_up(p.ru + p.n_dense, 8);
-  const bool in_tw = l > 0 && tc_tw_handoff(md, l - 1, ns), out_tw = tc_tw_handoff(md, l, ns);
   if (out_tw) {
     p.store_x = 1;
     p.store_h = 0;
