@@ -378,7 +378,10 @@ def make_LSTM_reduced_model(model, cutoff=.05, merged_kernel=True, *, rank=None,
 
 def truncate_singular_model(model, rank):
     """Top-r truncation of a 3-factor model (keep first r columns / entries / rows of every factor;
-    SURVEY App. A) -- the explicit-rank sweep primitive for the 3-factor form."""
+    SURVEY App. A) -- the explicit-rank sweep primitive for the 3-factor form.  ``rank`` is one rank for every
+    matrix or a pair (rank_w, rank_u) for the input / recurrent factors (the old API's per-matrix ranks,
+    old_versions/svd_classes.py:139-182)."""
+    rank_w_req, rank_u_req = (rank if isinstance(rank, (tuple, list)) else (rank, rank))
     smodel = Sequential()
     smodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
     for layer in model.layers[:-1]:
@@ -386,17 +389,17 @@ def truncate_singular_model(model, rank):
         s_w, s_u, w_l, w_r, u_l, u_r, b = [v.tensor for v in cell.weights]
         H = layer.units
         if cell.merged_kernel:
-            rw, ru = min(rank, cell.rank_w), min(rank, cell.rank_u)
+            rw, ru = min(int(rank_w_req), cell.rank_w), min(int(rank_u_req), cell.rank_u)
             w = [w_l[:, :rw], s_w[:, :rw], w_r[:rw]]
             u = [u_l[:, :ru], s_u[:, :ru], u_r[:ru]]
         else:
-            def cut(l, s, r_, k):
-                kk = min(rank, k)
+            def cut(l, s, r_, k, rank=None):
+                kk = min(int(rank), k)
                 ls = [l[:, g * k:g * k + kk] for g in range(4)]
                 ss = [s[:, g * k:g * k + kk] for g in range(4)]
                 return [torch.cat(ls, 1), torch.cat(ss, 1), r_[:kk]]
-            w = cut(w_l, s_w, w_r, cell.rank_w)
-            u = cut(u_l, s_u, u_r, cell.rank_u)
+            w = cut(w_l, s_w, w_r, cell.rank_w, rank_w_req)
+            u = cut(u_l, s_u, u_r, cell.rank_u, rank_u_req)
         ncell = SingularLSTMCell(H, w=w, u=u, b=b, merged_kernel=cell.merged_kernel,
                                  kernel_regularizer=cell.kernel_regularizer, recurrent_regularizer=cell.recurrent_regularizer,
                                  train_uv=cell.train_uv, uv_regularizer=cell.uv_regularizer)

@@ -282,3 +282,24 @@ def test_tc_stream_api_matches_one_long_run():
         y, state = m.stream(x[:, lo:hi].contiguous(), state, engine="tc")
         parts.append(y)
     assert torch.equal(torch.cat(parts, 1), y_all)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3])
+def test_tc_very_short_sequences(oracle, T):
+    """T = 1..3: the Dense-top / t_w rows of step T-1 come from the extra flush pass; nothing may depend on T >= a few steps."""
+    _, sm = _models(256, 2)
+    m = svdlstm.truncate_singular_model(sm, 128)
+    x = np.random.default_rng(20 + T).standard_normal((70, T, 16)).astype(np.float32)
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc T=%d" % T)
+
+
+def test_tc_mixed_ranks_and_wide_dense(oracle):
+    """Different W / U ranks per layer (the greedy sweep's ragged ranks) and a Dense top with several outputs: the t_w hand-off
+    rows, the t_u rows and the Dense rows share the S1u tiles in every combination."""
+    layers, dense = svdlstm.synthetic_layers(16, 256, 3, seed=5, n_out=5)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    for ranks in ((40, 72), (128, 24), (100, 128)):
+        m = svdlstm.truncate_singular_model(sm, ranks)      # (rank of the input factors, rank of the recurrent factors)
+        x = np.random.default_rng(31).standard_normal((50, 6, 16)).astype(np.float32)
+        _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc mixed ranks %s" % (ranks,))
