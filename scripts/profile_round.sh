@@ -8,7 +8,7 @@ O=gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-batch1"
 $BENCH > $O/plain_bench_$R.log 2>&1 && \
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $O/launches_$R.csv $BENCH > $O/ncu_bench_$R.log 2>&1
-for rk in 128 32; do
+for rk in 256 128 32; do
   CMD="python scripts/tc_time.py $rk 4096 128"
   $CMD > $O/plain_tc_$rk.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:lstm_tc_ -s 2 -c 1 -f -o $O/tc_layer_rank${rk}_$R $CMD > $O/ncu_tc_$rk.log 2>&1
