@@ -205,12 +205,12 @@ __global__ void svd_large_init(const float* __restrict__ A, int m, int n, double
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl[b] = LargeCtl{0, 0, 0, 0};
 }
 
-__global__ void __launch_bounds__(kSvdThreads) svd_large_round(double* G, double* J, LargeCtl* ctl, int k, int len, int round) {
-  const size_t b = blockIdx.y;
+// One Jacobi rotation of the row pair `pair` of round `round` of matrix b (whole CTA; every thread takes the same early exits).
+__device__ __forceinline__ void svd_large_rotate(double* G, double* J, LargeCtl* ctl, int k, int len, int round, int pair, size_t b) {
   if (ctl[b].done) return;
   const int n_even = k + (k & 1);
   int p, q;
-  rr_pair(round, blockIdx.x, n_even, p, q);
+  rr_pair(round, pair, n_even, p, q);
   if (q >= k) return;
   double* gp = G + b * k * len + (size_t)p * len;
   double* gq = G + b * k * len + (size_t)q * len;
@@ -262,6 +262,65 @@ __global__ void __launch_bounds__(kSvdThreads) svd_large_round(double* G, double
     const double x = jp[c], y = jq[c];
     jp[c] = cs * x - sn * y;
     jq[c] = sn * x + cs * y;
+  }
+}
+
+// fallback when a cooperative launch is not available: one launch per round
+__global__ void __launch_bounds__(kSvdThreads) svd_large_round(double* G, double* J, LargeCtl* ctl, int k, int len, int round) {
+  svd_large_rotate(G, J, ctl, k, len, round, (int)blockIdx.x, (size_t)blockIdx.y);
+}
+
+// Grid-wide barrier of a cooperative (fully co-resident) launch: arrival counter + generation, sense-reversing.
+__device__ __forceinline__ void svd_grid_barrier(unsigned int* bar, unsigned int n_cta) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    volatile unsigned int* gen_p = bar + 1;
+    const unsigned int gen = *gen_p;
+    if (atomicAdd(bar, 1u) == n_cta - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen_p == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ALL sweeps of ALL matrices in ONE cooperative launch (the per-round version needs (k-1) x 16 launches per call: 16 368 for the
+// 1024 x 4096 factors of an H = 1024 layer, most of them no-ops after convergence).  CTAs stride over the (pair, matrix) items of a
+// round, meet at a grid barrier between rounds (pairs of one round are disjoint, rounds are not), and leave as soon as every
+// matrix has converged.
+__global__ void __launch_bounds__(kSvdThreads) svd_large_persistent(double* G, double* J, LargeCtl* ctl, int k, int len, int batch, int max_sweeps,
+                                                                   unsigned int* gbar) {
+  const int n_even = k + (k & 1), pairs = n_even / 2, items = pairs * batch;
+  __shared__ int s_all_done;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int round = 0; round < n_even - 1; ++round) {
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        svd_large_rotate(G, J, ctl, k, len, round, item % pairs, (size_t)(item / pairs));
+        __syncthreads();   // the rotation's shared scratch is reused by the next item
+      }
+      svd_grid_barrier(gbar, gridDim.x);
+    }
+    if (blockIdx.x == 0)
+      for (int b = threadIdx.x; b < batch; b += kSvdThreads)
+        if (!ctl[b].done) {
+          ctl[b].sweeps += 1;
+          if (!ctl[b].changed) ctl[b].done = 1;
+          ctl[b].changed = 0;
+        }
+    svd_grid_barrier(gbar, gridDim.x);
+    if (threadIdx.x == 0) {
+      int all = 1;
+      for (int b = 0; b < batch; ++b) all &= ((volatile LargeCtl*)ctl)[b].done;
+      s_all_done = all;
+    }
+    __syncthreads();
+    if (s_all_done) break;
   }
 }
 
@@ -408,10 +467,32 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
   // Converged matrices turn the remaining launches into no-ops; a cyclic Jacobi on float32-exact
   // data needs ~8-12 sweeps, 16 leaves margin while bounding the launch count.
   const int max_sweeps = 16;
-  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    for (int r = 0; r < n_even - 1; ++r) svd_large_round<<<dim3(n_even / 2, batch), kSvdThreads, 0, stream>>>(G, J, ctl, k, len, r);
-    svd_large_sweep_end<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch);
+  bool persistent = false;
+  {
+    int dev = 0, coop = 0, n_sm = 0, per_sm = 0;
+    SVD_CUDA_TRY(cudaGetDevice(&dev));
+    SVD_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    SVD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    SVD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, svd_large_persistent, kSvdThreads, 0));
+    if (coop && per_sm > 0 && !getenv("SVDLSTM_SVD_PER_ROUND")) {
+      unsigned int* gbar = nullptr;
+      SVD_CUDA_TRY(cudaMallocAsync(&gbar, 2 * sizeof(unsigned int), stream));
+      SVD_CUDA_TRY(cudaMemsetAsync(gbar, 0, 2 * sizeof(unsigned int), stream));
+      const int items = (n_even / 2) * batch;
+      int grid = n_sm * per_sm;
+      if (grid > items) grid = items;
+      int k_ = k, len_ = len, batch_ = batch, ms_ = max_sweeps;
+      void* args[] = {&G, &J, &ctl, &k_, &len_, &batch_, &ms_, &gbar};
+      SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(svd_large_persistent), dim3((unsigned)grid), dim3(kSvdThreads), args, 0, stream));
+      SVD_CUDA_TRY(cudaFreeAsync(gbar, stream));
+      persistent = true;
+    }
   }
+  if (!persistent)
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+      for (int r = 0; r < n_even - 1; ++r) svd_large_round<<<dim3(n_even / 2, batch), kSvdThreads, 0, stream>>>(G, J, ctl, k, len, r);
+      svd_large_sweep_end<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch);
+    }
   svd_large_finalize<<<batch, kSvdThreads, 0, stream>>>(G, J, sig, rnk, ctl, m, n, U, S, Vt, sweeps);
   SVD_CUDA_TRY(cudaGetLastError());
   SVD_CUDA_TRY(cudaFreeAsync(G, stream));
