@@ -42,7 +42,6 @@ namespace {
 
 constexpr int kInStagesMax = 3;      // max input prefetch ring depth
 constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kTcThreads = 32 * (4 + kEpiWarps);
 constexpr int kMaxWSlots = 12;
 constexpr uint32_t kSlotBytes = 32768;   // preferred ring-slot size (two 16 KB chunks per hand-over); 16 KB when fewer than 4 would fit
