@@ -139,6 +139,7 @@ def build_workload(a, svdlstm):
     sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
     model = svdlstm.truncate_singular_model(sm, a.rank)
     model._singular_parent = sm
+    model._full_parent = full
     return layers, dense, model
 
 
@@ -409,6 +410,29 @@ def main():
             tf = flops_per_seq_step(D, a.hidden, a.layers, r) * B * T / (ms * 1e-3) / 1e12
             sweep["r%d" % r] = {"ms": round(ms, 3), "Mseqsteps_per_s": round(B * T / ms / 1e3, 1), "tflops": round(tf, 1),
                                 "frac_of_peak": round(tf / pk["bf16_tflops_sustained"], 4)}
+        if a.hidden <= 256:
+            # the uncompressed LSTM on the same engine (runs as the factorisation I . W): what the reference's speed-up plots divide by
+            fm = model._full_parent
+            for _ in range(2):
+                fm(x, engine=engine)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                fm(x, engine=engine)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            d_in, full_macs = D, 0
+            for _ in range(a.layers):
+                full_macs += d_in * 4 * a.hidden + a.hidden * 4 * a.hidden
+                d_in = a.hidden
+            tf = 2 * full_macs * B * T / (ms * 1e-3) / 1e12
+            sweep["full"] = {"ms": round(ms, 3), "Mseqsteps_per_s": round(B * T / ms / 1e3, 1), "tflops": round(tf, 1),
+                             "frac_of_peak": round(tf / pk["bf16_tflops_sustained"], 4),
+                             "note": "uncompressed LSTM (4(DH+H^2) MACs per layer-step) on the same tensor-core engine"}
+            for r in (8, 16, 32, 64, 128, 256):
+                sweep["r%d" % r]["speedup_vs_full"] = round(ms / sweep["r%d" % r]["ms"], 2)
         line["rank_sweep"] = sweep
     if e2e is not None:
         line["e2e"] = e2e

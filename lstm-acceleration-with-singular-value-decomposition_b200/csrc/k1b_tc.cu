@@ -1138,8 +1138,9 @@ __device__ __forceinline__ float block_right(const Block& b, int kk, int n) {
   if (rel >= b.ncols) return 0.f;
   return b.right[(size_t)kk * b.right_ld + rel];
 }
-__device__ __forceinline__ float block_left(const Block& b, int k, int j) {   // (L sigma)[k][j]
-  return b.left[(size_t)k * b.left_ld + j] * (b.scale ? b.scale[j] : 1.f);
+__device__ __forceinline__ float block_left(const Block& b, int k, int j) {   // (L sigma)[k][j]; a full (unfactored) matrix is I . W
+  const float l = b.left ? b.left[(size_t)k * b.left_ld + j] : (k == j ? 1.f : 0.f);
+  return l * (b.scale ? b.scale[j] : 1.f);
 }
 
 __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, Block bw_next, int x_r0, int rx, int H, int D,
@@ -1336,7 +1337,7 @@ static void tc_handoff_chain(const ModelDesc& md, int ns, bool out[kMaxLayers]) 
   for (int l = 0; l + 1 < md.n_layers; ++l) {
     const LayerDesc& A = md.layers[l];
     const LayerDesc& B = md.layers[l + 1];
-    if (off || A.n_blocks != 2 || B.n_blocks != 2 || B.blocks[0].left == nullptr) continue;
+    if (off || A.n_blocks != 2 || B.n_blocks != 2) continue;
     const bool no_s1w = l == 0 || out[l - 1];
     out[l] = round_up(A.blocks[1].rank, 8) + round_up(B.blocks[0].rank, 8) <= 128 * tc_s1u_tiles_max(ns, no_s1w);
   }
@@ -1347,7 +1348,8 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   if (L.n_blocks != 2) { *why = "only merged (non-split) cell forms run on the tensor-core engine"; return false; }
   const Block& bw = L.blocks[0];
   const Block& bu = L.blocks[1];
-  if (bu.left == nullptr || bw.left == nullptr) { *why = "full (unfactored) cells are not low-rank: use the FP32 engines"; return false; }
+  // (a full, unfactored cell runs as the "factorisation" I . W: its first contraction is an identity, exact in FP16 -- the baseline the
+  //  truncated models are compared with on the same engine; it pays one wasted H x H contraction per step)
   const int H = L.units;
   if (H % 128 != 0 || H > 128 * kMaxUB || (H > 512 && H != 1024)) { *why = "tensor-core engine needs units in {128, 256, 384, 512, 1024}"; return false; }
   if (H > 512 && ns != 32) { *why = "units above 512 run with 32-sequence tiles"; return false; }

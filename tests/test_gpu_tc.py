@@ -100,8 +100,11 @@ def test_tc_rejects_what_it_cannot_run():
     """No silent fallback: unsupported models / calls raise with the reason."""
     full, sm = _models(128, 1)
     x = torch.randn(4, 5, 16).cuda()
-    with pytest.raises((RuntimeError, ValueError), match="low-rank|FP32"):
-        full(x, engine="tc")                                      # unfactored cell
+    y_full = full(x, engine="tc")                                 # unfactored cell: runs as I . W (units <= 256)
+    assert float((y_full - full(x, engine="general")).abs().max()) < 2e-3
+    layers512, dense512 = svdlstm.synthetic_layers(16, 512, 1, seed=0)
+    with pytest.raises((RuntimeError, ValueError), match="ranks above 256"):
+        svdlstm.full_model_from_weights(layers512, dense512, return_sequences=True)(x, engine="tc")
     split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
     with pytest.raises((RuntimeError, ValueError), match="merged"):
         split(x, engine="tc")
@@ -303,3 +306,14 @@ def test_tc_mixed_ranks_and_wide_dense(oracle):
         m = svdlstm.truncate_singular_model(sm, ranks)      # (rank of the input factors, rank of the recurrent factors)
         x = np.random.default_rng(31).standard_normal((50, 6, 16)).astype(np.float32)
         _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc mixed ranks %s" % (ranks,))
+
+
+def test_tc_full_model_matches_oracle(oracle):
+    """The trained full (unfactored) LSTM on the tensor-core engine (as the factorisation I . W): the baseline the truncated
+    models are compared with at equal engine; 2 layers so the hand-off path carries h itself."""
+    layers, dense = svdlstm.synthetic_layers(16, 256, 2, seed=2)
+    full = svdlstm.full_model_from_weights(layers, dense, return_sequences=True)
+    x = np.random.default_rng(41).standard_normal((70, 9, 16)).astype(np.float32)
+    y = full.predict(x, engine="tc")
+    assert full.last_engine() == svdlstm.ENGINE_TC
+    _check(y, oracle_twin(oracle, full).predict(x), "tc full model H=256 L=2")
