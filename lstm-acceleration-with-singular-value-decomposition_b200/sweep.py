@@ -81,7 +81,7 @@ def build_rank_models(full_model, ranks: Sequence[int], form="reduced", merged_k
 
 
 def rank_sweep(full_model, X, ranks: Sequence[int], *, target=None, form="reduced", merged_kernel=True, engine=None,
-               gather_predictions=True, last_step_only=False, models=None, sse_over="kept"):
+               gather_predictions=True, last_step_only=False, models=None, sse_over="kept", target_engine=None):
     """Evaluate every rank-truncated model on this process's shard of X and reduce.
 
     X: (N, T, D) host or device array holding ALL sequences (each process slices its own shard), or, if
@@ -98,7 +98,7 @@ def rank_sweep(full_model, X, ranks: Sequence[int], *, target=None, form="reduce
     if models is None:
         _, models = build_rank_models(full_model, ranks, form=form, merged_kernel=merged_kernel)
     if target is None:
-        tgt = full_model(x_loc)
+        tgt = full_model(x_loc, engine=target_engine)   # default: the FP32 engines; "tc" compares like with like (truncation error only)
     else:
         tgt = C.dev_tensor(target(lo, hi) if callable(target) else target[lo:hi])
     tgt = tgt.reshape(tgt.shape[0], -1) if tgt.dim() > 1 else tgt.reshape(-1, 1)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--engine", default="tc")
     ap.add_argument("--form", default="singular")
+    ap.add_argument("--target-engine", default=None, help="engine for the full-model targets (default: FP32 engines)")
     a = ap.parse_args()
     lo_r, hi_r = (int(v) for v in a.ranks.split(":"))
     ranks = list(range(lo_r, hi_r + 1))
@@ -74,12 +75,12 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up: two ranks on a slice (kernel images, workspaces, NCCL communicator)
-    svdlstm.rank_sweep(full, Xc, ranks[:2], models=models[:2], engine=a.engine, last_step_only=True, sse_over="all")
+    svdlstm.rank_sweep(full, Xc, ranks[:2], models=models[:2], engine=a.engine, last_step_only=True, sse_over="all", target_engine=a.target_engine)
     barrier()
     l0 = svdlstm.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = svdlstm.rank_sweep(full, Xc, ranks, models=models, engine=a.engine, last_step_only=True, sse_over="all")
+    res = svdlstm.rank_sweep(full, Xc, ranks, models=models, engine=a.engine, last_step_only=True, sse_over="all", target_engine=a.target_engine)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -91,7 +92,7 @@ def main():
         sel = [r for r in (1, 2, 4, 8, 16, 32, 64, 128, 192, 256) if lo_r <= r <= hi_r]
         line = {"metric": "rank x sequence sweep (all ranks x sequences, RMSE vs full model)", "value": items * T / (ms * 1e-3),
                 "unit": "sequence-timesteps/s (summed over ranks)", "n_gpus": world, "seconds": ms * 1e-3, "scaling": "strong",
-                "items_rank_x_sequence": items, "sequences": N, "seq_len": T, "ranks": [lo_r, hi_r], "engine": a.engine, "form": a.form,
+                "items_rank_x_sequence": items, "sequences": N, "seq_len": T, "ranks": [lo_r, hi_r], "engine": a.engine, "target_engine": a.target_engine or "fp32", "form": a.form,
                 "gathered_bytes": int(res["preds"].numel() * 4) if res["preds"] is not None else 0,
                 "model_build_s": round(build_s, 3), "gpu_launches": svdlstm.launches() - l0,
                 "rmse_vs_full": {str(r): float(res["rmse"][r - lo_r]) for r in sel}, "data": "synthetic"}
