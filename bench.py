@@ -234,13 +234,37 @@ def batch1_table(svdlstm, torch):
         tm(svdlstm.truncate_singular_model(sm, r), "3F_r%d" % r)
         tm(svdlstm.make_LSTM_reduced_model(sm, rank=r), "2F_r%d" % r)
     tm(full, "full_general_engine", engine="general")
+    # True streaming (the reference's real-time setting, svd_acceleration_v3.py:151: one sample every 400 us): one call per chunk of
+    # `c` samples through Sequential.stream with the state carried on the device -- pinned host sample in, host prediction out.
+    import time
+    import numpy as np
+    streaming = {}
+    m8 = svdlstm.truncate_singular_model(sm, 8)
+    for label, model in (("full", full), ("3F_r8", m8)):
+        for c in (1, 16):
+            xin = torch.randn(1, c, 16).pin_memory()
+            yout = torch.empty(1, c, 1).pin_memory()
+            state = None
+            lat = []
+            for it in range(300):
+                t0 = time.perf_counter()
+                xd = xin.cuda(non_blocking=True)
+                y, state = model.stream(xd, state)
+                yout.copy_(y, non_blocking=True)
+                torch.cuda.synchronize()
+                lat.append(time.perf_counter() - t0)
+            lat = np.array(lat[50:]) * 1e6
+            streaming["%s_chunk%d" % (label, c)] = {"call_us_median": round(float(np.median(lat)), 1), "call_us_p99": round(float(np.percentile(lat, 99)), 1),
+                                                    "us_per_sample": round(float(np.median(lat)) / c, 1)}
+    out_streaming = {"how": "Sequential.stream per chunk: pinned H2D of the chunk, one launch with state in/out, D2H of the predictions, "
+                            "synchronize; wall clock of the Python call, 250 calls after 50 warm-ups", "calls": streaming}
     # algorithmic on-chip bytes/step of the 3-factor model at full rank: 28 140 B
     byt = 28140.0
     return {"unit": "us/timestep", "T": T, "model": "DROPBEAR 3x15 LSTM + Dense(1), batch 1", "us_per_step": out,
             "onchip_roofline": {"bytes_per_step_3F_r15": byt, "achieved_gbs": round(byt / (out["3F_r15"] * 1e-6) / 1e9, 2),
                                 "peak_gbs_1sm": 251.5, "frac": round(byt / (out["3F_r15"] * 1e-6) / 1e9 / 251.5, 4),
                                 "note": "peak = 128 B/clk x 1965 MHz, one SM (the latency chain uses one CTA)"},
-            "realtime_budget_us": 400.0}
+            "streaming": out_streaming, "realtime_budget_us": 400.0}
 
 
 def main():
