@@ -37,13 +37,18 @@ typedef struct svdlstm_model_s* svdlstm_handle;
 #define SVDLSTM_ZERO_OUTPUT_FOR_MASK  8   /* :418     */
 
 /* engines */
-#define SVDLSTM_ENGINE_AUTO     0   /* FP32: wavefront kernel when the model fits it, else general */
-#define SVDLSTM_ENGINE_GENERAL  1   /* FP32 CUDA-core batched persistent kernel (any shape)        */
-#define SVDLSTM_ENGINE_WAVEFRONT 2  /* FP32 register-resident warp-per-layer wavefront (H,D,r<=32) */
+#define SVDLSTM_ENGINE_AUTO     0   /* regime switch (north_star): the tensor-core engine when the call is dense enough for it
+                                       -- batch >= SVDLSTM_TC_MIN_BATCH, widest layer >= SVDLSTM_TC_MIN_UNITS, and the model /
+                                       call is one it supports -- else the FP32 choice below.  The environment variable
+                                       SVDLSTM_STRICT_FP32=1 turns AUTO into ENGINE_FP32 process-wide.                          */
+#define SVDLSTM_ENGINE_GENERAL  1   /* FP32 CUDA-core batched persistent kernel (any shape)                                    */
+#define SVDLSTM_ENGINE_WAVEFRONT 2  /* FP32 register-resident warp-per-layer wavefront (H,D,r<=32)                             */
 #define SVDLSTM_ENGINE_TC       3   /* tcgen05 tensor-core persistent kernel: FP16 operands, FP32 accumulate + cell state
-                                       (reduced precision; merged 3-/2-factor cells, units in {128..512, 1024}, ranks <= 256,
-                                       return_sequences, zero initial state, no mask) */
-#define SVDLSTM_ENGINE_TC_BF16  SVDLSTM_ENGINE_TC   /* first version of that engine used BF16 operands; alias kept */
+                                       (reduced precision; merged 3-/2-factor or full cells, units <= 512 or <= 1024 padded to
+                                       128-row tiles, ranks <= 256, return_sequences, no mask)                                 */
+#define SVDLSTM_ENGINE_FP32     4   /* strict FP32 (the 1e-5 parity path): wavefront when the model fits it, else general     */
+#define SVDLSTM_TC_MIN_BATCH    128
+#define SVDLSTM_TC_MIN_UNITS    64
 
 /* ---- model handle ------------------------------------------------------------------------
  * A handle describes a stack of L LSTM layers (+ optional Dense top), i.e. what the
@@ -103,7 +108,8 @@ int64_t svdlstm_count_weights(svdlstm_handle h);
  * old_versions/svd_classes.py:10,15,231.  A: batch x (m,n) row-major contiguous.
  * Outputs (k=min(m,n)): U batch x (m,k), S batch x (k) descending, Vt batch x (k,n).
  * Any of U/Vt may be NULL (values only).  sweeps (device int[batch], may be NULL) receives
- * the number of Jacobi sweeps used.  Internally float64.                                      */
+ * the number of Jacobi sweeps used, NEGATED when the matrix hit the sweep cap (40) without
+ * converging (its factors are then not orthogonal to working precision).  Internally float64. */
 int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int n, float* U, float* S,
                                float* Vt, int* sweeps, void* stream);
 

@@ -5,8 +5,8 @@ Drop-in for the reference's layer / builder API (code/svd_classes_v3.py) and dri
 (code/svd_acceleration_v3.py), Python host -> C-ABI (include/svdlstm.h) -> hand-written CUDA.
 There is no CPU fallback: the numpy oracle under oracle/ is test infrastructure only.
 """
-from ._cabi import (ENGINE_AUTO, ENGINE_GENERAL, ENGINE_TC, ENGINE_TC_BF16, ENGINE_WAVEFRONT, EXPORTS, LIB_PATH, lib,
-                    require_cuda)
+from ._cabi import (ENGINE_AUTO, ENGINE_FP32, ENGINE_GENERAL, ENGINE_TC, ENGINE_WAVEFRONT, EXPORTS, LIB_PATH, TC_MIN_BATCH,
+                    TC_MIN_UNITS, lib, require_cuda)
 from . import _cabi
 from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell, OrthogonalRegularizer,
                      PrunableTimeDistributed, ReducedLSTMCell, SingularLSTM, SingularLSTMCell, TimeDistributed,
@@ -17,6 +17,7 @@ from .metrics import (count_weights, full_weight_count, reduced_merged_weight_co
                       reference_rmse, rmse, signaltonoise, sweep_sse, weight_reduction_percent)
 from .rank_reduce import (LSTM_wrapper, get_model_singular_values, reduce_matrix_rank, reduce_two_step,
                           set_model_matrix_rank, sorted_sigma_indices)
+from .data import StandardScaler, preprocess, split_train_random
 from .sweep import build_rank_models, rank_sweep, shard_bounds
 from .weights_io import (load_model_weights_csv, load_model_weights_json, load_model_weights_npz, load_model_weights_zip,
                          save_model_weights_csv, save_model_weights_json, synthetic_layers)

@@ -25,8 +25,10 @@ ENGINE_AUTO = 0
 ENGINE_GENERAL = 1
 ENGINE_WAVEFRONT = 2
 ENGINE_TC = 3          # tcgen05 tensor-core engine: FP16 operands, FP32 accumulation / cell state (reduced precision)
-ENGINE_TC_BF16 = ENGINE_TC   # name of the first (BF16-operand) version of that engine; kept as an alias
-ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc": 3, "tc_f16": 3, "tc_bf16": 3, None: 0}
+ENGINE_FP32 = 4        # strict FP32: wavefront when the model fits it, else general (what "auto" was before the regime switch)
+TC_MIN_BATCH = 128     # "auto" picks the tensor-core engine from this batch size on (include/svdlstm.h)
+TC_MIN_UNITS = 64
+ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc": 3, "tc_f16": 3, "fp32": 4, None: 0}
 
 EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",

@@ -1,5 +1,6 @@
 // extern "C" surface of libsvdlstm.so: model handle, weight binding, forward dispatch.
 // See include/svdlstm.h for the contract and the reference interfaces each entry replaces.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -31,6 +32,7 @@ struct svdlstm_model_s {
   bool layer_set[kMaxLayers];
   ModelDesc* dev_md;        // device copy, re-uploaded when dirty
   ModelDesc* pinned_md;     // pinned staging so the upload is stream-ordered and async
+  cudaEvent_t md_event;     // recorded after every forward: the last reader of dev_md / pinned_md (whatever its stream)
   bool dirty;
   bool tc_dirty;
   TcState* tc;
@@ -68,6 +70,7 @@ int svdlstm_create(svdlstm_handle* out, int n_layers, int input_dim, const int* 
   }
   m->dev_md = nullptr;
   m->pinned_md = nullptr;
+  m->md_event = nullptr;
   m->dirty = true;
   m->tc_dirty = true;
   m->tc = nullptr;
@@ -81,6 +84,7 @@ void svdlstm_destroy(svdlstm_handle h) {
   if (!h) return;
   if (h->dev_md) cudaFree(h->dev_md);
   if (h->pinned_md) cudaFreeHost(h->pinned_md);
+  if (h->md_event) cudaEventDestroy(h->md_event);
   if (h->tc) tc_free(h->tc);
   delete h;
 }
@@ -229,8 +233,9 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
   if (h->dirty) {
     if (!h->dev_md) SVD_CUDA_TRY(cudaMalloc(&h->dev_md, sizeof(ModelDesc)));
     if (!h->pinned_md) SVD_CUDA_TRY(cudaMallocHost(&h->pinned_md, sizeof(ModelDesc)));
-    // the pinned staging copy may still be in flight from a previous upload on another stream
-    SVD_CUDA_TRY(cudaStreamSynchronize(stream));
+    // An earlier forward -- possibly on ANOTHER stream -- may still be reading dev_md, or its upload may still be reading the
+    // pinned staging copy: wait for the event recorded after that forward, not for the current stream.
+    if (h->md_event) SVD_CUDA_TRY(cudaEventSynchronize(h->md_event));
     memcpy(h->pinned_md, &h->md, sizeof(ModelDesc));
     SVD_CUDA_TRY(cudaMemcpyAsync(h->dev_md, h->pinned_md, sizeof(ModelDesc), cudaMemcpyHostToDevice, stream));
     h->dirty = false;
@@ -239,7 +244,17 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
   int launches = 0;
   int rc = 0;
   int used = engine;
-  if (engine == SVDLSTM_ENGINE_AUTO) used = wavefront_supported(h->md, a) ? SVDLSTM_ENGINE_WAVEFRONT : SVDLSTM_ENGINE_GENERAL;
+  if (engine == SVDLSTM_ENGINE_AUTO) {
+    // Regime switch: the thin contractions only fill 128-row x 32-sequence tensor-core tiles when batch x 4H is dense enough;
+    // below that the FP32 latency engines win and keep full precision.
+    static const bool strict = [] { const char* e = getenv("SVDLSTM_STRICT_FP32"); return e && e[0] && e[0] != '0'; }();
+    int max_units = 0;
+    for (int l = 0; l < h->md.n_layers; ++l) max_units = h->md.layers[l].units > max_units ? h->md.layers[l].units : max_units;
+    const char* why = "";
+    if (!strict && B >= SVDLSTM_TC_MIN_BATCH && max_units >= SVDLSTM_TC_MIN_UNITS && tc_supported(h->md, a, &why)) used = SVDLSTM_ENGINE_TC;
+    else used = SVDLSTM_ENGINE_FP32;
+  }
+  if (used == SVDLSTM_ENGINE_FP32) used = wavefront_supported(h->md, a) ? SVDLSTM_ENGINE_WAVEFRONT : SVDLSTM_ENGINE_GENERAL;
   switch (used) {
     case SVDLSTM_ENGINE_GENERAL:
       rc = run_general(h->md, h->dev_md, a, stream, &launches);
@@ -261,6 +276,10 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
     default:
       set_error("svdlstm_forward: unknown engine %d", engine);
       return -1;
+  }
+  if (rc == 0) {
+    if (!h->md_event) SVD_CUDA_TRY(cudaEventCreateWithFlags(&h->md_event, cudaEventDisableTiming));
+    SVD_CUDA_TRY(cudaEventRecord(h->md_event, stream));
   }
   h->last_launches = launches;
   h->last_engine = used;

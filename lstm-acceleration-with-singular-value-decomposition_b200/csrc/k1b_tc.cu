@@ -32,6 +32,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -287,7 +288,8 @@ struct TcLayerParams {
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
   float* y;                 // (B, T, n_dense) fused Dense-top output            (n_dense > 0)
   const float* dense_bias;
-  int H, Kin, T, B;
+  int H, Kin, T, B;         // H = units padded to a multiple of 128 (padded cells: zero weights, h = c = 0)
+  int Hu;                   // the layer's true units (state arrays and the packers index with it)
   int ns;                   // sequences per CTA tile (MMA N): 32 or 64
   int ru, rw;               // true ranks
   int ru_pad, rw_pad;       // multiples of 16: K extents of t_u / t_w inside the S2 contraction (rw_pad = 0 on layer 0)
@@ -513,7 +515,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
           float v[8];
           for (int m = 0; m < 8; ++m) {
             const int b = cta * NS + cc0 + 8 * j8 + m;
-            v[m] = b < p.B ? p.h0[(size_t)b * H + ub * 128 + row0] : 0.f;
+            v[m] = (b < p.B && ub * 128 + row0 < p.Hu) ? p.h0[(size_t)b * p.Hu + ub * 128 + row0] : 0.f;
           }
           sts128(sbase + sp.hbuf + act_offset(ub * 128 + row0, cc0 + 8 * j8, NS), pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]),
                  pack_f16(v[6], v[7]));
@@ -882,7 +884,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       for (int u = 0; u < NUB; ++u)
 #pragma unroll
         for (int n = 0; n < CPT; ++n)
-          if (b_first + n < p.B) cst[u][n] = p.c0[(size_t)(b_first + n) * H + u * 128 + row];
+          if (b_first + n < p.B && u * 128 + row < p.Hu) cst[u][n] = p.c0[(size_t)(b_first + n) * p.Hu + u * 128 + row];
     }
     // ---- epilogue-1 plan of this thread, one bit per 128-row tile (everything the time loop would otherwise re-derive) ----
     const int e1_rows_u = p.ru + p.n_dense;    // rows of S1u anyone needs
@@ -1078,8 +1080,8 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     if (STATE && p.h_n != nullptr) {   // return_state: h(T-1) as this engine holds it (FP16 between steps): read back this thread's own stores
       for (int u = 0; u < NUB; ++u)
         for (int n = 0; n < CPT; ++n)
-          if (b_first + n < p.B)
-            p.h_n[(size_t)(b_first + n) * H + u * 128 + row] =
+          if (b_first + n < p.B && u * 128 + row < p.Hu)
+            p.h_n[(size_t)(b_first + n) * p.Hu + u * 128 + row] =
                 __half2float(*reinterpret_cast<const __half*>(smem + sp.hbuf + act_offset(u * 128 + row, c0 + n, NS)));
     }
     if (STATE && p.c_n != nullptr) {   // return_state: c(T-1), float32 all along
@@ -1087,7 +1089,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       for (int u = 0; u < NUB; ++u)
 #pragma unroll
         for (int n = 0; n < CPT; ++n)
-          if (b_first + n < p.B) p.c_n[(size_t)(b_first + n) * H + u * 128 + row] = cst[u][n];
+          if (b_first + n < p.B && u * 128 + row < p.Hu) p.c_n[(size_t)(b_first + n) * p.Hu + u * 128 + row] = cst[u][n];
     }
   }
 
@@ -1143,7 +1145,9 @@ __device__ __forceinline__ float block_left(const Block& b, int k, int j) {   //
   return l * (b.scale ? b.scale[j] : 1.f);
 }
 
-__global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, Block bw_next, int x_r0, int rx, int H, int D,
+// H = padded units (multiple of 128: the kernel's row-tile granularity), Hu = the layer's true units, D = its true input width.
+// Padded cells have zero weights and zero bias: z = 0 -> i = f = o = 1/2, g = 0 -> c = h = 0 for all t, exactly.
+__global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block bw, Block bu, Block bw_next, int x_r0, int rx, int H, int Hu, int D,
                                     int ru_pad, const float* __restrict__ dense_k, int n_dense, int n_out, __half* __restrict__ img) {
   const PackChunk c = chunks[blockIdx.x];
   __half* out = img + c.byte_off / 2;
@@ -1153,24 +1157,29 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
     float v = 0.f;
     if (c.seg == 0) {
       const int j = c.r0 + row, kk = c.k0 + k;
-      if (j < bw.rank) v = block_left(bw, kk, j);
+      if (j < bw.rank && kk < D) v = block_left(bw, kk, j);
     } else if (c.seg == 1) {
       const int j = c.r0 + row, kk = c.k0 + k;
-      if (j < bu.rank) v = block_left(bu, kk, j);
-      else if (j - bu.rank < n_dense) v = dense_k[(size_t)kk * n_out + (j - bu.rank)];
-      else if (rx > 0 && j >= x_r0 && j - x_r0 < rx) v = block_left(bw_next, kk, j - x_r0);   // the next layer's (L_w sigma_w)^T rows
+      if (kk < Hu) {
+        if (j < bu.rank) v = block_left(bu, kk, j);
+        else if (j - bu.rank < n_dense) v = dense_k[(size_t)kk * n_out + (j - bu.rank)];
+        else if (rx > 0 && j >= x_r0 && j - x_r0 < rx) v = block_left(bw_next, kk, j - x_r0);   // the next layer's (L_w sigma_w)^T rows
+      }
     } else {
       const int gate = (c.g == 1) ? 2 : (c.g == 2) ? 1 : c.g;   // tile slots are ordered i, g(cell), f, o; Keras columns i, f, c, o
-      const int n = gate * H + c.ub * 128 + row;
+      const int unit = c.ub * 128 + row;
+      const int n = gate * Hu + unit;
       const int kk = c.k0 + k;
-      if (c.part == 0) {            // recurrent part: row kk of R_u
-        if (kk < bu.rank) v = block_right(bu, kk, n);
-      } else if (c.part == 2) {     // input part, layers >= 1: row kk of R_w
-        if (kk < bw.rank) v = block_right(bw, kk, n);
-      } else if (kk < D) {          // input part, layer 0: the dense D x 4H product W0 = (L_w sigma_w) R_w
-        float acc = 0.f;
-        for (int j = 0; j < bw.rank; ++j) acc = fmaf(block_left(bw, kk, j), block_right(bw, j, n), acc);
-        v = acc;
+      if (unit < Hu) {
+        if (c.part == 0) {            // recurrent part: row kk of R_u
+          if (kk < bu.rank) v = block_right(bu, kk, n);
+        } else if (c.part == 2) {     // input part, layers >= 1: row kk of R_w
+          if (kk < bw.rank) v = block_right(bw, kk, n);
+        } else if (kk < D) {          // input part, layer 0: the dense D x 4H product W0 = (L_w sigma_w) R_w
+          float acc = 0.f;
+          for (int j = 0; j < bw.rank; ++j) acc = fmaf(block_left(bw, kk, j), block_right(bw, j, n), acc);
+          v = acc;
+        }
       }
       if (gate != 2) v *= 0.5f;   // sigmoid gates: tanh(z/2) form
     }
@@ -1179,12 +1188,13 @@ __global__ void pack_wstream_kernel(const PackChunk* __restrict__ chunks, Block 
   }
 }
 
-__global__ void pack_bias_kernel(const float* __restrict__ bias, int H, float* __restrict__ img) {
+__global__ void pack_bias_kernel(const float* __restrict__ bias, int H, int Hu, float* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // [ub][slot][128], slots ordered i, g(cell), f, o
   if (idx >= 4 * H) return;
   const int ub = idx / 512, slot = (idx / 128) & 3, i = idx & 127;
   const int g = (slot == 1) ? 2 : (slot == 2) ? 1 : slot;
-  img[idx] = bias[g * H + ub * 128 + i] * (g != 2 ? 0.5f : 1.f);
+  const int unit = ub * 128 + i;
+  img[idx] = unit < Hu ? bias[g * Hu + unit] * (g != 2 ? 0.5f : 1.f) : 0.f;
 }
 
 // x (B,T,D) fp32 -> f16 activation tile images [cta][t] (K = Dpad16).  One block = one batch tile x TT steps:
@@ -1223,8 +1233,8 @@ __global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x
 }
 
 // last layer h tiles -> y (B,T,H) fp32 (only when the model has no Dense top; the Dense top is fused otherwise)
-__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int H, int ns, float* __restrict__ y) {
-  const uint32_t tile = act_tile_bytes(H, ns);
+__global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T, int Hpad, int H, int ns, float* __restrict__ y) {
+  const uint32_t tile = act_tile_bytes(Hpad, ns);
   const int cta = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int item = blockIdx.x * nw + warp; item < T * ns; item += gridDim.x * nw) {
@@ -1239,11 +1249,11 @@ __global__ void unpack_out_kernel(const uint8_t* __restrict__ img, int B, int T,
 // Dense / TimeDistributed(Dense) top from the last hidden-sequence image (only when it could not be fused into S1u):
 // y[b, t, o] = sum_k h[k][b] W[k][o] + bias[o].  One block per (step, tile): the 16-byte words of the tile (8 sequences of
 // one unit each) are read coalesced; thread (q, n-group) accumulates a quarter of the units for 8 sequences.
-__global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restrict__ img, int B, int T, int H, int ns,
+__global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restrict__ img, int B, int T, int Hpad, int H, int ns,
                                                         const float* __restrict__ dk, const float* __restrict__ db, int n_out,
                                                         float* __restrict__ y) {
   __shared__ float part[64][8][8];   // [k-slice (<= 64)][n-group][sequence in group]
-  const uint32_t tile = act_tile_bytes(H, ns);
+  const uint32_t tile = act_tile_bytes(Hpad, ns);
   const int cta = blockIdx.y, t = blockIdx.x;
   const int ngr = ns / 8, nks = 256 / ngr;          // n-groups, k-slices
   const int ng = threadIdx.x % ngr, ks = threadIdx.x / ngr;
@@ -1274,14 +1284,11 @@ __global__ void __launch_bounds__(256) dense_top_kernel(const uint8_t* __restric
   }
 }
 
-#include "k1c_pair.cuh"
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct TcPairState;
 struct TcLayerImg {
   PackChunk* chunks = nullptr;
   uint32_t* slots = nullptr;
@@ -1294,7 +1301,6 @@ struct TcState {
   TcLayerImg layers[kMaxLayers];
   int n_layers = 0;
   int ns = 0;   // tile width the images / plans were built for (the chunk order depends on resident vs streamed)
-  TcPairState* pair = nullptr;   // images of the paired-CTA kernel (k1c_pair.cuh), built on first use
 };
 
 // Per-device scratch shared by every handle: the FP16 image of x and the two ping-pong hidden-sequence images
@@ -1307,16 +1313,60 @@ struct TcWorkspace {
   size_t progress_elems = 0;
   uint8_t* xseq = nullptr;
   size_t xseq_bytes = 0;
-  cudaStream_t last_stream = nullptr;
-  bool used = false;
+  // Ordering across streams: every forward records `done` after its last launch and the next forward makes ITS stream wait on
+  // it (no stream handle is remembered -- the caller may have destroyed it).  `mu` serialises host threads sharing the device.
+  cudaEvent_t done = nullptr;
+  std::mutex mu;
 };
 static TcWorkspace g_tc_ws[16];
 
-#include "k1c_pair_host.cuh"
+// ---- 2-factor (ReducedLSTMCell) blocks on the tensor cores ---------------------------------------------------------------
+// z = [a | a C] with a = in . B  (svd_classes_v3.py:321-328).  C = inv(V1) V2 has entries in the hundreds on trained weights
+// (cond(V1) ~ 1e2): FP16 is the wrong container for it (5 % errors measured).  The SAME linear map is in . B' . Q^T with
+// [I | C] = P diag(s) Q^T (thin SVD, K2 on device), B' = B P diag(s): Q^T has orthonormal rows (entries <= 1) and B' is
+// as benign as the 3-factor (L sigma), so the block packs and runs exactly like a 3-factor one, at 3-factor accuracy.
+__global__ void tc_ident_right_kernel(Block b, int n, float* __restrict__ R) {   // R (rank x n) = [I | C]
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)b.rank * n; idx += stride) {
+    const int kk = (int)(idx / n), c = (int)(idx - (size_t)kk * n);
+    R[idx] = block_right(b, kk, b.out0 + c);
+  }
+}
+__global__ void tc_ident_left_kernel(Block b, int rows, const float* __restrict__ P, const float* __restrict__ S, float* __restrict__ out) {
+  // out (rows x r) = left (rows x r) . P (r x r) . diag(S)
+  const int r = b.rank;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)rows * r; idx += stride) {
+    const int i = (int)(idx / r), j = (int)(idx - (size_t)i * r);
+    double acc = 0.0;
+    for (int k = 0; k < r; ++k) acc += (double)block_left(b, i, k) * (double)P[(size_t)k * r + j];
+    out[idx] = (float)(acc * (double)S[j]);
+  }
+}
+
+static int tc_reorthogonalise(const Block& b, int rows, cudaStream_t stream, Block* out, std::vector<void*>& temps, int* launches) {
+  const int r = b.rank, n = b.rank + b.ncols;
+  float *R = nullptr, *P = nullptr, *S = nullptr, *Qt = nullptr, *Bp = nullptr;
+  SVD_CUDA_TRY(cudaMalloc(&R, sizeof(float) * r * n));
+  temps.push_back(R);
+  SVD_CUDA_TRY(cudaMalloc(&P, sizeof(float) * r * r));
+  temps.push_back(P);
+  SVD_CUDA_TRY(cudaMalloc(&S, sizeof(float) * r));
+  temps.push_back(S);
+  SVD_CUDA_TRY(cudaMalloc(&Qt, sizeof(float) * r * n));
+  temps.push_back(Qt);
+  SVD_CUDA_TRY(cudaMalloc(&Bp, sizeof(float) * rows * r));
+  temps.push_back(Bp);
+  tc_ident_right_kernel<<<imin(1184, (r * n + 255) / 256), 256, 0, stream>>>(b, n, R);
+  if (int rc = svdlstm_svd_jacobi_batched(R, 1, r, n, P, S, Qt, nullptr, stream)) return rc;
+  tc_ident_left_kernel<<<imin(1184, (rows * r + 127) / 128), 128, 0, stream>>>(b, rows, P, S, Bp);
+  *launches += 3;
+  *out = Block{Bp, nullptr, Qt, r, n, r, n, b.out0, 0, b.from_h, 0};
+  return 0;
+}
 
 void tc_free(TcState* s) {
   if (!s) return;
-  pair_free(s->pair);
   for (int l = 0; l < kMaxLayers; ++l) {
     if (s->layers[l].wimg) cudaFree(s->layers[l].wimg);
     if (s->layers[l].chunks) cudaFree(s->layers[l].chunks);
@@ -1350,14 +1400,18 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
   const Block& bu = L.blocks[1];
   // (a full, unfactored cell runs as the "factorisation" I . W: its first contraction is an identity, exact in FP16 -- the baseline the
   //  truncated models are compared with on the same engine; it pays one wasted H x H contraction per step)
-  const int H = L.units;
-  if (H % 128 != 0 || H > 128 * kMaxUB || (H > 512 && H != 1024)) { *why = "tensor-core engine needs units in {128, 256, 384, 512, 1024}"; return false; }
+  // units are padded to the 128-row tile of the MMAs (zero weights and bias: padded cells stay at h = c = 0 exactly), which is
+  // what lets the shipped 3 x 15 DROPBEAR model run on this engine too (its RMSE delta is part of north_star)
+  const int Hu = L.units;
+  const int H = round_up(Hu, 128);
+  if (H > 128 * kMaxUB || (H > 512 && H != 1024)) { *why = "tensor-core engine needs units <= 512, or 513..1024 (run as 1024)"; return false; }
   if (H > 512 && ns != 32) { *why = "units above 512 run with 32-sequence tiles"; return false; }
   if (bu.rank > 256 || bw.rank > 256) { *why = "ranks above 256 are not supported by the tensor-core engine"; return false; }
   const bool last = (l == md.n_layers - 1);
   p = TcLayerParams{};
   p.ns = ns;
   p.H = H;
+  p.Hu = Hu;
   p.ru = bu.rank;
   p.rw = bw.rank;
   p.ru_pad = round_up(bu.rank, 16);
@@ -1394,7 +1448,7 @@ static bool tc_layer_params(const ModelDesc& md, int l, int ns, TcLayerParams& p
     p.rw_pad = 0;
     p.rows_w = 0;
   } else {
-    p.Kin = md.layers[l - 1].units;
+    p.Kin = round_up(md.layers[l - 1].units, 128);
     p.kx = 0;
     p.rw_pad = round_up(bw.rank, 16);
     p.rows_w = round_up(bw.rank, 8);
@@ -1529,25 +1583,10 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     SVD_CUDA_TRY(cudaGetDevice(&dev0));
     SVD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev0));
   }
-  if (weights_dirty) {   // both image sets follow the weights; each is rebuilt when its path next runs
-    st->ns = 0;
-    if (st->pair) st->pair->built = false;
-  }
+  if (weights_dirty) st->ns = 0;   // the images follow the weights: rebuilt below
   const char* mode_env = getenv("SVDLSTM_TC_MODE");
-  {
-    // Paired-CTA kernel (k1c_pair.cuh): tiles of 128 sequences on two SMs, each streaming half of the weights.
-    const bool force_pair = mode_env && strcmp(mode_env, "pair") == 0;
-    if (force_pair) {
-      SVD_REQUIRE(pair_supported(md, &why), "tensor-core engine (SVDLSTM_TC_MODE=pair): %s", why);
-      SVD_REQUIRE(!(a.h0 || a.h_n || a.c_n), "tensor-core engine (SVDLSTM_TC_MODE=pair): initial_state / return_state are not supported by the paired kernel");
-      int dev0 = 0;
-      SVD_CUDA_TRY(cudaGetDevice(&dev0));
-      SVD_REQUIRE(dev0 >= 0 && dev0 < 16, "tensor-core engine: device ordinal %d out of range", dev0);
-      return run_tc_pair(md, &st->pair, weights_dirty, a, stream, n_sm, &g_tc_ws[dev0], launches);
-    }
-  }
   bool same_h = true;
-  for (int l = 1; l < L; ++l) same_h = same_h && md.layers[l].units == md.layers[0].units;
+  for (int l = 1; l < L; ++l) same_h = same_h && round_up(md.layers[l].units, 128) == round_up(md.layers[0].units, 128);
   bool ok64 = true;
   for (int l = 0; l < L; ++l) {
     TcLayerParams q;
@@ -1597,6 +1636,25 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   if (st->ns != ns) weights_dirty = true;
   if (weights_dirty) {
     st->ns = ns;
+    // effective factor blocks: 2-factor (ident) blocks are re-orthogonalised into 3-factor ones first (see tc_reorthogonalise)
+    Block eff[kMaxLayers][2];
+    std::vector<void*> temps;
+    struct TempGuard {
+      std::vector<void*>& t;
+      cudaStream_t s;
+      ~TempGuard() {
+        if (!t.empty()) cudaStreamSynchronize(s);   // the pack kernels read them
+        for (void* q : t) cudaFree(q);
+      }
+    } temp_guard{temps, stream};
+    for (int l = 0; l < L; ++l)
+      for (int j = 0; j < 2; ++j) {
+        eff[l][j] = md.layers[l].blocks[j];
+        if (eff[l][j].ident) {
+          const int rows = j == 0 ? md.layers[l].d_in : md.layers[l].units;
+          if (int rc = tc_reorthogonalise(md.layers[l].blocks[j], rows, stream, &eff[l][j], temps, &nl)) return rc;
+        }
+      }
     for (int l = 0; l < L; ++l) {
       TcLayerImg& li = st->layers[l];
       TcLayerParams p;
@@ -1664,11 +1722,11 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
       }
       SVD_REQUIRE((int)chunks.size() == p.n_chunks_w + p.n_chunks_u + p.n_chunks_2, "tensor-core engine: chunk table mismatch");
       const LayerDesc& Ld = md.layers[l];
-      const Block bw_next = l + 1 < L ? md.layers[l + 1].blocks[0] : Block{};
-      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, Ld.blocks[0], Ld.blocks[1], bw_next, p.x_r0, p.rx, p.H, Ld.d_in, p.ru_pad,
+      const Block bw_next = l + 1 < L ? eff[l + 1][0] : Block{};
+      pack_wstream_kernel<<<(unsigned)chunks.size(), 256, 0, stream>>>(li.chunks, eff[l][0], eff[l][1], bw_next, p.x_r0, p.rx, p.H, p.Hu, Ld.d_in, p.ru_pad,
                                                                        md.dense_kernel, p.n_dense, md.n_out,
                                                                        reinterpret_cast<__half*>(li.wimg));
-      pack_bias_kernel<<<(4 * p.H + 255) / 256, 256, 0, stream>>>(Ld.bias, p.H, li.bias);
+      pack_bias_kernel<<<(4 * p.H + 255) / 256, 256, 0, stream>>>(Ld.bias, p.H, p.Hu, li.bias);
       nl += 2;
       p.wimg = li.wimg;
       p.bias = li.bias;
@@ -1684,9 +1742,9 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   SVD_CUDA_TRY(cudaGetDevice(&dev));
   SVD_REQUIRE(dev >= 0 && dev < 16, "tensor-core engine: device ordinal %d out of range", dev);
   TcWorkspace* ws = &g_tc_ws[dev];
-  if (ws->used && ws->last_stream != stream) SVD_CUDA_TRY(cudaStreamSynchronize(ws->last_stream));
-  ws->used = true;
-  ws->last_stream = stream;
+  std::lock_guard<std::mutex> ws_lock(ws->mu);
+  if (ws->done == nullptr) SVD_CUDA_TRY(cudaEventCreateWithFlags(&ws->done, cudaEventDisableTiming));
+  else SVD_CUDA_TRY(cudaStreamWaitEvent(stream, ws->done, 0));   // the previous forward (any stream) owns the shared scratch until then
   const int Dpad = st->layers[0].prm.Kin;
   const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad, ns);
   if (ws->xseq_bytes < xbytes) {
@@ -1781,7 +1839,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     pp.n_tiles = n_cta;
     pp.progress = ws->progress;
     int lrc = -1;
-    switch ((md.layers[0].units / 128) * 2 + (ns == 64 ? 1 : 0)) {
+    switch ((st->layers[0].prm.H / 128) * 2 + (ns == 64 ? 1 : 0)) {
       case 2: lrc = tc_launch_pipe<1, 32>(pp, pipe_smem, stream); break;
       case 3: lrc = tc_launch_pipe<1, 64>(pp, pipe_smem, stream); break;
       case 4: lrc = tc_launch_pipe<2, 32>(pp, pipe_smem, stream); break;
@@ -1797,13 +1855,14 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   if (st->layers[L - 1].prm.store_h) {
     const uint8_t* last_seq = ws->seq[pipe ? L - 1 : ((L - 1) & 1)];
     if (md.n_out > 0)      // Dense top that did not fit the S1u tiles
-      dense_top_kernel<<<dim3((unsigned)T, (unsigned)n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, ns, md.dense_kernel,
-                                                                              md.dense_bias, md.n_out, a.y);
+      dense_top_kernel<<<dim3((unsigned)T, (unsigned)n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, st->layers[L - 1].prm.Hu, ns,
+                                                                              md.dense_kernel, md.dense_bias, md.n_out, a.y);
     else                   // no Dense top: the output is the last hidden sequence itself
-      unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, ns, a.y);
+      unpack_out_kernel<<<dim3(128, n_cta), 256, 0, stream>>>(last_seq, B, T, st->layers[L - 1].prm.H, st->layers[L - 1].prm.Hu, ns, a.y);
     ++nl;
   }
   SVD_CUDA_TRY(cudaGetLastError());
+  SVD_CUDA_TRY(cudaEventRecord(ws->done, stream));
   if (dbg_env) {   // debugging aid: dump the per-step timeline of CTA 0 (cycles relative to the step's first stamp)
     static long long host[kDbgPerLayer * kMaxLayers];
     SVD_CUDA_TRY(cudaStreamSynchronize(stream));

@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kSvdThreads) svd_small_kernel(const float* __r
     __syncthreads();
     if (!ch) break;
   }
-  if (tid == 0 && sweeps_out) sweeps_out[blockIdx.x] = sweep + 1;
+  // sweeps_out > 0: sweeps used (the last one found nothing to rotate); < 0: the cap was hit without converging
+  if (tid == 0 && sweeps_out) sweeps_out[blockIdx.x] = sweep < kMaxSweeps ? sweep + 1 : -kMaxSweeps;
   const size_t b = blockIdx.x;
   svd_finalize(G, J, sig, rnk, m, n, k, len, wide, U ? U + b * m * k : nullptr, S + b * k, Vt ? Vt + b * k * n : nullptr);
 }
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kSvdThreads) svd_large_finalize(const double* 
                                                                   int* sweeps_out) {
   const int k = min(m, n), len = max(m, n);
   const size_t b = blockIdx.x;
-  if (threadIdx.x == 0 && sweeps_out) sweeps_out[b] = ctl[b].sweeps;
+  if (threadIdx.x == 0 && sweeps_out) sweeps_out[b] = ctl[b].done ? ctl[b].sweeps : -ctl[b].sweeps;   // < 0: not converged
   svd_finalize(G + b * k * len, J + b * k * k, sigbuf + b * k, rnkbuf + b * k, m, n, k, len, m <= n, U ? U + b * m * k : nullptr,
                S + b * k, Vt ? Vt + b * k * n : nullptr);
 }
@@ -454,19 +455,29 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
     SVD_CUDA_TRY(cudaGetLastError());
     return 0;
   }
-  double *G = nullptr, *J = nullptr, *sig = nullptr;
-  int* rnk = nullptr;
-  LargeCtl* ctl = nullptr;
-  SVD_CUDA_TRY(cudaMallocAsync(&G, sizeof(double) * batch * k * len, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&J, sizeof(double) * batch * k * k, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&sig, sizeof(double) * batch * k, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&rnk, sizeof(int) * batch * k, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&ctl, sizeof(LargeCtl) * batch, stream));
+  // ONE stream-ordered scratch block (freed on every exit path by the guard below)
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t oG = 0, oJ = oG + up(sizeof(double) * batch * k * len), oS = oJ + up(sizeof(double) * batch * k * k),
+               oR = oS + up(sizeof(double) * batch * k), oC = oR + up(sizeof(int) * batch * k), oB = oC + up(sizeof(LargeCtl) * batch),
+               total = oB + 256;
+  uint8_t* scratch = nullptr;
+  SVD_CUDA_TRY(cudaMallocAsync(&scratch, total, stream));
+  struct Guard {
+    uint8_t* p;
+    cudaStream_t s;
+    ~Guard() { cudaFreeAsync(p, s); }
+  } guard{scratch, stream};
+  double* G = reinterpret_cast<double*>(scratch + oG);
+  double* J = reinterpret_cast<double*>(scratch + oJ);
+  double* sig = reinterpret_cast<double*>(scratch + oS);
+  int* rnk = reinterpret_cast<int*>(scratch + oR);
+  LargeCtl* ctl = reinterpret_cast<LargeCtl*>(scratch + oC);
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(scratch + oB);
   svd_large_init<<<dim3(296, batch), 256, 0, stream>>>(A, m, n, G, J, ctl);
   const int n_even = k + (k & 1);
-  // Converged matrices turn the remaining launches into no-ops; a cyclic Jacobi on float32-exact
-  // data needs ~8-12 sweeps, 16 leaves margin while bounding the launch count.
-  const int max_sweeps = 16;
+  // Same cap as the small path.  The persistent kernel leaves as soon as every matrix has converged (a cyclic Jacobi on
+  // float32-exact data needs ~8-12 sweeps), so the cap costs nothing; a matrix that hits it is reported through `sweeps` (< 0).
+  const int max_sweeps = kMaxSweeps;
   bool persistent = false;
   {
     int dev = 0, coop = 0, n_sm = 0, per_sm = 0;
@@ -475,8 +486,6 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
     SVD_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     SVD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, svd_large_persistent, kSvdThreads, 0));
     if (coop && per_sm > 0 && !getenv("SVDLSTM_SVD_PER_ROUND")) {
-      unsigned int* gbar = nullptr;
-      SVD_CUDA_TRY(cudaMallocAsync(&gbar, 2 * sizeof(unsigned int), stream));
       SVD_CUDA_TRY(cudaMemsetAsync(gbar, 0, 2 * sizeof(unsigned int), stream));
       const int items = (n_even / 2) * batch;
       int grid = n_sm * per_sm;
@@ -484,7 +493,6 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
       int k_ = k, len_ = len, batch_ = batch, ms_ = max_sweeps;
       void* args[] = {&G, &J, &ctl, &k_, &len_, &batch_, &ms_, &gbar};
       SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(svd_large_persistent), dim3((unsigned)grid), dim3(kSvdThreads), args, 0, stream));
-      SVD_CUDA_TRY(cudaFreeAsync(gbar, stream));
       persistent = true;
     }
   }
@@ -495,11 +503,6 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
     }
   svd_large_finalize<<<batch, kSvdThreads, 0, stream>>>(G, J, sig, rnk, ctl, m, n, U, S, Vt, sweeps);
   SVD_CUDA_TRY(cudaGetLastError());
-  SVD_CUDA_TRY(cudaFreeAsync(G, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(J, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(sig, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(rnk, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(ctl, stream));
   return 0;
 }
 

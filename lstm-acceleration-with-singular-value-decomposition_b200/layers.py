@@ -28,7 +28,8 @@ _default_engine = "auto"
 
 
 def set_default_engine(name: str) -> None:
-    """'auto' | 'general' | 'wavefront' | 'tc' -- engine used when a call does not name one."""
+    """'auto' | 'fp32' | 'general' | 'wavefront' | 'tc' -- engine used when a call does not name one.  'auto' is the regime
+    switch of include/svdlstm.h (tensor cores for dense batches, FP32 otherwise); 'fp32' never leaves full precision."""
     global _default_engine
     if name not in C.ENGINE_NAMES:
         raise ValueError("unknown engine %r" % (name,))
@@ -57,6 +58,9 @@ class Variable:
         self.name = name
         self.trainable = trainable
         self.regularizer = regularizer
+        # callables run after every in-place update: whoever bound this buffer into a device handle registers one, so that
+        # derived device state (the packed FP16 weight-stream images of the tensor-core engine) is rebuilt on the next forward
+        self._listeners = []
 
     @property
     def shape(self):
@@ -65,12 +69,21 @@ class Variable:
     def numpy(self) -> np.ndarray:
         return self.tensor.detach().cpu().numpy()
 
-    def assign(self, value) -> None:
+    def assign(self, value, notify: bool = True) -> None:
         v = C.dev_tensor(value, self.tensor.device)
         if tuple(v.shape) != tuple(self.tensor.shape):
             raise ValueError("Layer weight shape %s not compatible with provided weight shape %s"
                              % (tuple(self.tensor.shape), tuple(v.shape)))
         self.tensor.copy_(v)
+        if notify:
+            self.notify()
+
+    def notify(self) -> None:
+        alive = []
+        for fn in self._listeners:
+            if fn() is not False:       # a listener whose target died returns False and is dropped
+                alive.append(fn)
+        self._listeners = alive
 
     def __repr__(self):
         return "<Variable %s shape=%s>" % (self.name, self.shape)
@@ -125,12 +138,18 @@ class Handle:
         else:
             B, T = int(x.shape[0]), int(x.shape[1])
         n = self.n_out if self.n_out > 0 else self.units[-1]
-        if (not return_sequences and _engine_id(engine) == C.ENGINE_TC and not time_major and not go_backwards
-                and initial_state is None and mask is None and not want_state):
+        eid = _engine_id(engine)
+        if (not return_sequences and not time_major and not go_backwards and initial_state is None and mask is None and not want_state
+                and (eid == C.ENGINE_TC or (eid == C.ENGINE_AUTO and B >= C.TC_MIN_BATCH and max(self.units) >= C.TC_MIN_UNITS))):
             # The tensor-core kernel always produces the whole output sequence (the Dense top is fused into its S1 tiles, one
             # step behind); return_sequences=False (svd_classes_v3.py:428-431: last output only) is the last step of it.
-            y, _, _ = self.forward(x, return_sequences=True, engine=engine)
-            return y[:, -1].contiguous(), None, None
+            try:
+                y, _, _ = self.forward(x, return_sequences=True, engine="tc")
+                return y[:, -1].contiguous(), None, None
+            except ValueError:
+                if eid == C.ENGINE_TC:
+                    raise
+                engine = "fp32"     # "auto", and the tensor-core engine does not take this model: FP32 engines
         if return_sequences:
             y = torch.empty((T, B, n) if time_major else (B, T, n), dtype=torch.float32, device=dev)
         else:
@@ -331,7 +350,7 @@ class _CellBase:
                 raise ValueError("Layer weight shape %s not compatible with provided weight shape %s"
                                  % (v.shape, tuple(np.shape(w))))
         for v, w in zip(self._vars, weights):
-            v.assign(w)
+            v.assign(w, notify=False)
         self.rebind()
 
     def count_params(self):
@@ -344,10 +363,24 @@ class _CellBase:
 
     def _add(self, value, shape, name, trainable=False, regularizer=None) -> Variable:
         t = C.dev_tensor(value)
+        if isinstance(value, (torch.Tensor, Variable)):
+            # Every cell OWNS its buffers, as Keras variables do: the builders pass live tensors / views of the source model
+            # (its bias, slices of its factors), and an in-place set_weights on one model must never change another.
+            t = t.clone()
         if tuple(t.shape) != tuple(shape):
             raise ValueError("Layer weight shape %s not compatible with provided weight shape %s (weight %r of %s)"
                              % (tuple(shape), tuple(t.shape), name, self.name))
         v = Variable(t, name, trainable, regularizer)
+        import weakref
+        me = weakref.ref(self)
+
+        def _on_assign():     # Variable.assign outside set_weights (e.g. cell.kernel.assign(...)): re-announce the layer to its handles
+            c = me()
+            if c is None:
+                return False
+            c.rebind()
+            return True
+        v._listeners.append(_on_assign)
         self._vars.append(v)
         return v
 

@@ -24,9 +24,10 @@ from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell
 # --------------------------------------------------------------------------------------------------
 # device linear algebra wrappers (K2 / K2b)
 # --------------------------------------------------------------------------------------------------
-def svd_batched(A, compute_uv=True, return_sweeps=False):
+def svd_batched(A, compute_uv=True, return_sweeps=False, check_convergence=True):
     """Batched thin SVD on device.  A: (batch, m, n) or (m, n).  Returns (U, S, Vt) like
-    np.linalg.svd(full_matrices=False) -- U (..,m,k), S (..,k) descending, Vt (..,k,n)."""
+    np.linalg.svd(full_matrices=False) -- U (..,m,k), S (..,k) descending, Vt (..,k,n).  ``check_convergence`` reads the
+    per-matrix sweep counts back (one small D2H) and warns if a matrix hit the sweep cap (count reported negative)."""
     a = C.dev_tensor(A)
     squeeze = a.dim() == 2
     if squeeze:
@@ -39,10 +40,15 @@ def svd_batched(A, compute_uv=True, return_sweeps=False):
     S = torch.empty((batch, k), dtype=torch.float32, device=dev)
     U = torch.empty((batch, m, k), dtype=torch.float32, device=dev) if compute_uv else None
     Vt = torch.empty((batch, k, n), dtype=torch.float32, device=dev) if compute_uv else None
-    sw = torch.zeros(batch, dtype=torch.int32, device=dev) if return_sweeps else None
+    sw = torch.zeros(batch, dtype=torch.int32, device=dev)
     C.check(C.lib().svdlstm_svd_jacobi_batched(C.ptr(a), batch, m, n, C.ptr(U), C.ptr(S), C.ptr(Vt), C.ptr(sw),
                                                C.cur_stream()))
     C.add_launches(1)
+    if check_convergence:
+        bad = torch.nonzero(sw < 0).reshape(-1)
+        if bad.numel():
+            warnings.warn("svd_batched: Jacobi SVD hit the sweep cap without converging for matrix index %s of a (%d, %d, %d) "
+                          "batch; its factors are not orthogonal to working precision" % (bad.cpu().tolist(), batch, m, n))
     if squeeze:
         S = S[0]
         U = U[0] if U is not None else None
@@ -173,6 +179,19 @@ class Sequential:
             dense = self._dense()
             if dense is not None:
                 h.set_dense_top(dense.kernel.tensor, dense.bias.tensor)
+                import weakref
+                href = weakref.ref(h)
+
+                def _dense_changed(dense=dense):
+                    # Dense.set_weights / Variable.assign update the buffers in place; the tensor-core engine bakes the Dense
+                    # kernel into its FP16 weight-stream image, so the handle has to be told (marks that image stale)
+                    hh = href()
+                    if hh is None:
+                        return False
+                    hh.set_dense_top(dense.kernel.tensor, dense.bias.tensor)
+                    return True
+                dense.kernel._listeners.append(_dense_changed)
+                dense.bias._listeners.append(_dense_changed)
             self._fused = h
         return self._fused
 
@@ -210,11 +229,69 @@ class Sequential:
 
     def predict(self, X, batch_size=32, verbose=0, engine=None):
         """Keras ``model.predict`` (svd_acceleration_v3.py:148,151): host array in, host array out.
-        Sequences are independent, so the whole batch runs as one launch regardless of batch_size."""
-        return self.__call__(X, engine=engine).cpu().numpy()
+        Sequences are independent, so the whole batch runs as one launch regardless of batch_size.
+        Host input (numpy, or a torch CPU tensor -- pinned memory makes the copy asynchronous and full-speed) is staged through
+        the serving pipeline of ``predict_async``; a CUDA tensor skips the input copy."""
+        return np.array(self.predict_async(X, engine=engine).result())      # an owned copy (the pinned buffer is recycled)
+
+    def predict_async(self, X, engine=None):
+        """Enqueue one ``predict`` and return at once with a handle whose ``.result()`` blocks for the host array.
+
+        A serving loop keeps two requests in flight: the host->device copy of request i+1 (own copy stream, second device
+        buffer) overlaps the forward pass of request i, and each result is copied into one of two pinned host buffers on
+        the compute stream.  ``.result()`` returns a numpy VIEW of that pinned buffer, valid until the second-next request
+        of the same shape is issued (copy it to keep it longer)."""
+        dev = C.require_cuda()
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            y = self.__call__(X, engine=engine)
+            return _Pending(None, y, None)
+        xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float32)))
+        if xh.dtype != torch.float32 or not xh.is_contiguous():
+            xh = xh.to(torch.float32).contiguous()
+        if xh.dim() != 3:
+            raise ValueError("expected input of shape (batch, time, features)")
+        key = (tuple(xh.shape), dev.index)
+        st = getattr(self, "_serve", None)
+        if st is None or st["key"] != key:
+            st = {"key": key, "i": 0, "x_dev": [torch.empty(xh.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                  "y_host": [None, None], "copy_stream": torch.cuda.Stream(device=dev),
+                  "h2d_done": [torch.cuda.Event() for _ in range(2)], "x_free": [torch.cuda.Event() for _ in range(2)],
+                  "y_done": [torch.cuda.Event() for _ in range(2)]}
+            main = torch.cuda.current_stream(dev)
+            for e in st["x_free"]:
+                e.record(main)
+            self._serve = st
+        k = st["i"] & 1
+        st["i"] += 1
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["copy_stream"]):
+            st["copy_stream"].wait_event(st["x_free"][k])          # the forward that last read this buffer has finished
+            st["x_dev"][k].copy_(xh, non_blocking=True)
+            st["h2d_done"][k].record(st["copy_stream"])
+        main.wait_event(st["h2d_done"][k])
+        y = self.__call__(st["x_dev"][k], engine=engine)
+        st["x_free"][k].record(main)
+        if st["y_host"][k] is None or tuple(st["y_host"][k].shape) != tuple(y.shape):
+            st["y_host"][k] = torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory()
+        st["y_host"][k].copy_(y, non_blocking=True)
+        st["y_done"][k].record(main)
+        return _Pending(st["y_done"][k], None, st["y_host"][k])
 
     def last_engine(self):
         return self._fused.last_engine() if self._fused is not None else None
+
+
+class _Pending:
+    """Handle of one in-flight ``predict_async`` request."""
+
+    def __init__(self, event, y_dev, y_host):
+        self._event, self._y_dev, self._y_host = event, y_dev, y_host
+
+    def result(self) -> np.ndarray:
+        if self._y_host is None:
+            return self._y_dev.cpu().numpy()
+        self._event.synchronize()
+        return self._y_host.numpy()
 
 
 # --------------------------------------------------------------------------------------------------

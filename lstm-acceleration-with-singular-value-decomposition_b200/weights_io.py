@@ -17,21 +17,47 @@ import numpy as np
 GATES = ("i", "f", "c", "o")
 
 
+def _layer_key(name):
+    """lstm_9 < lstm_10: order layer directories by their numeric suffix (plain string sort gets this wrong)."""
+    digits = "".join(ch for ch in name if ch.isdigit())
+    return (int(digits) if digits else -1, name)
+
+
+def _assemble_layer(read, transposed):
+    """One layer from its 12 per-gate arrays.  ``read(fname) -> ndarray`` (any ndim: np.loadtxt returns 0-D / 1-D arrays
+    when units or input_dim is 1, in either orientation).  The shapes are fixed explicitly: units from the length of
+    b*.csv, the input width from the element count of W*.csv -- never from np.atleast_2d / .T guesses."""
+    bs = [np.asarray(read("b%s.csv" % g), np.float64).reshape(-1) for g in GATES]
+    H = int(bs[0].size)
+    if H < 1 or any(b.size != H for b in bs):
+        raise ValueError("per-gate bias files disagree on the number of units: %s" % [int(b.size) for b in bs])
+
+    def mat(fname, rows=None):
+        a = np.asarray(read(fname), np.float64)
+        if a.size % H:
+            raise ValueError("%s holds %d values, not a multiple of units=%d" % (fname, a.size, H))
+        d = a.size // H
+        if rows is not None and d != rows:
+            raise ValueError("%s: expected %d x %d values, found %d" % (fname, rows, H, a.size))
+        # file orientation: transposed = (units, d) row-major [the shipped fixture], else (d, units) [load_preprocess.py]
+        return a.reshape(H, d).T if transposed else a.reshape(d, H)
+
+    Ws = [mat("W%s.csv" % g) for g in GATES]
+    if any(w.shape != Ws[0].shape for w in Ws):
+        raise ValueError("per-gate W files disagree on the input width")
+    Us = [mat("U%s.csv" % g, rows=H) for g in GATES]
+    return (np.concatenate(Ws, 1).astype(np.float32), np.concatenate(Us, 1).astype(np.float32),
+            np.concatenate(bs).astype(np.float32))
+
+
 def load_model_weights_csv(path, layer_names=None, transposed=True):
     """-> ([(W (D,4H), U (H,4H), b (4H,)), ...], (dense_kernel (H,1), dense_bias (1,))) float32, Keras layout."""
     if layer_names is None:
-        layer_names = sorted(d for d in os.listdir(path) if d.startswith("lstm"))
+        layer_names = sorted((d for d in os.listdir(path) if d.startswith("lstm")), key=_layer_key)
     layers = []
     for name in layer_names:
         d = os.path.join(path, name)
-        Ws = [np.atleast_2d(np.loadtxt(os.path.join(d, "W%s.csv" % g), delimiter=",")) for g in GATES]
-        Us = [np.atleast_2d(np.loadtxt(os.path.join(d, "U%s.csv" % g), delimiter=",")) for g in GATES]
-        bs = [np.loadtxt(os.path.join(d, "b%s.csv" % g), delimiter=",").ravel() for g in GATES]
-        if transposed:
-            Ws = [w.T for w in Ws]
-            Us = [u.T for u in Us]
-        layers.append((np.concatenate(Ws, 1).astype(np.float32), np.concatenate(Us, 1).astype(np.float32),
-                       np.concatenate(bs).astype(np.float32)))
+        layers.append(_assemble_layer(lambda f, d=d: np.loadtxt(os.path.join(d, f), delimiter=","), transposed))
     dk = np.loadtxt(os.path.join(path, "dense_top", "weights.csv"), delimiter=",").reshape(-1, 1).astype(np.float32)
     db = np.loadtxt(os.path.join(path, "dense_top", "bias.csv"), delimiter=",").reshape(1).astype(np.float32)
     return layers, (dk, db)
@@ -132,17 +158,8 @@ def load_model_weights_zip(path, transposed=True):
             return np.loadtxt(io.StringIO(z.read(find(layer, fname)).decode("utf-8")), delimiter=",")
 
         layer_names = sorted({n.replace("\\", "/").split("/")[-2] for n in names
-                              if n.replace("\\", "/").split("/")[-2].startswith("lstm")})
-        layers = []
-        for name in layer_names:
-            Ws = [np.atleast_2d(read(name, "W%s.csv" % g)) for g in GATES]
-            Us = [np.atleast_2d(read(name, "U%s.csv" % g)) for g in GATES]
-            bs = [read(name, "b%s.csv" % g).ravel() for g in GATES]
-            if transposed:
-                Ws = [w.T for w in Ws]
-                Us = [u.T for u in Us]
-            layers.append((np.concatenate(Ws, 1).astype(np.float32), np.concatenate(Us, 1).astype(np.float32),
-                           np.concatenate(bs).astype(np.float32)))
+                              if n.replace("\\", "/").split("/")[-2].startswith("lstm")}, key=_layer_key)
+        layers = [_assemble_layer(lambda f, name=name: read(name, f), transposed) for name in layer_names]
         dk = read("dense_top", "weights.csv").reshape(-1, 1).astype(np.float32)
         db = read("dense_top", "bias.csv").reshape(1).astype(np.float32)
     return layers, (dk, db)

@@ -22,7 +22,7 @@ model = svdlstm.truncate_singular_model(sm, r) if form == "3F" else svdlstm.make
 x = torch.randn(B, T, 16, generator=torch.Generator().manual_seed(0)).cuda()
 y32 = model(x, engine="general")
 torch.cuda.synchronize()
-ytc = model(x, engine="tc_bf16")
+ytc = model(x, engine="tc")
 torch.cuda.synchronize()
 d = (ytc - y32).abs()
 print("H=%d L=%d r=%d B=%d T=%d %s" % (H, L, r, B, T, form))

@@ -20,12 +20,12 @@ x = torch.randn(B, T, 16, generator=torch.Generator().manual_seed(0)).cuda()
 for r in ranks:
     model = svdlstm.truncate_singular_model(sm, r)
     for _ in range(2):
-        y = model(x, engine="tc_bf16")
+        y = model(x, engine="tc")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        y = model(x, engine="tc_bf16")
+        y = model(x, engine="tc")
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
@@ -36,5 +36,5 @@ for r in ranks:
         d = H
     tf = 2 * macs * B * T / (ms * 1e-3) / 1e12
     ysub = model(x[:64, :64], engine="general")
-    err = (model(x[:64, :64], engine="tc_bf16") - ysub).abs().max().item()
+    err = (model(x[:64, :64], engine="tc") - ysub).abs().max().item()
     print("rank %3d: %.3f ms/step  %.2f M seq-steps/s  %.1f TFLOP/s (algorithmic)  max|tc-fp32| %.2e" % (r, ms, B * T / ms / 1e3, tf, err))

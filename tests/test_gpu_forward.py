@@ -198,3 +198,50 @@ def test_batch_permutation_and_padding_properties(full):
         assert torch.equal(full(x[perm], engine=engine), y[perm])
         assert torch.equal(full(x[:5], engine=engine), y[:5])
         assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("rank", [8, 32, 128, 256])
+def test_fp32_parity_at_c3_shape(oracle, rank):
+    """BASELINE configs[2] model (L=2, H=256, D=16) on the FP32 general engine vs the float64 oracle on the same weights,
+    <= 1e-5 relative (+2e-6 abs): 3-factor and 2-factor forms at the swept ranks, on a subsample of sequences/steps the
+    oracle finishes in seconds.  (The full-size run, T=1024, is in test_gpu_tc.py::test_tc_full_c3_size_properties.)"""
+    layers, dense = svdlstm.synthetic_layers(16, 256, 2, seed=0)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    x = np.random.default_rng(50 + rank).standard_normal((6, 96, 16)).astype(np.float32)
+    tm = svdlstm.truncate_singular_model(sm, rank)
+    assert_parity(tm.predict(x, engine="general"), oracle_twin(oracle, tm).predict(x), "C3 3F r=%d" % rank)
+    rm = svdlstm.make_LSTM_reduced_model(sm, rank=rank)
+    assert_parity(rm.predict(x, engine="general"), oracle_twin(oracle, rm).predict(x), "C3 2F r=%d" % rank,
+                  ref32=oracle_twin(oracle, rm, np.float32).predict(x), extra_atol=cond_slack(rm))
+    if rank == 256:     # full rank: both factored forms reproduce the unfactored model
+        assert_parity(full.predict(x, engine="general"), oracle_twin(oracle, full).predict(x), "C3 full")
+        assert np.max(np.abs(tm.predict(x, engine="general") - full.predict(x, engine="general"))) < 2e-5
+
+
+def test_fp32_parity_at_c5_shape(oracle):
+    """BASELINE configs[4] model (L=3, H=1024, rank 128) on the FP32 general engine vs the float64 oracle, <= 1e-5."""
+    layers, dense = svdlstm.synthetic_layers(16, 1024, 3, seed=0)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    tm = svdlstm.truncate_singular_model(sm, 128)
+    x = np.random.default_rng(60).standard_normal((3, 24, 16)).astype(np.float32)
+    assert_parity(tm.predict(x, engine="general"), oracle_twin(oracle, tm).predict(x), "C5 3F r=128")
+
+
+def test_derived_models_own_their_weights(oracle, full, x_small):
+    """builders hand live tensors / views of the source model to the new cells; every cell must own its buffers
+    (Keras variables are independent): set_weights on a derived model leaves the source -- and its siblings -- untouched."""
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    t8, t4 = svdlstm.truncate_singular_model(sm, 8), svdlstm.truncate_singular_model(sm, 4)
+    rm = svdlstm.make_LSTM_reduced_model(sm, rank=8)
+    snap = {id(mo): ([w.copy() for w in mo.get_weights()], mo.predict(x_small)) for mo in (full, sm, t4, rm)}
+    for layer in t8.layers:
+        layer.set_weights([w * 0.5 + 0.01 for w in layer.get_weights()])
+    sm.layers[0].set_weights([w + 0.125 for w in sm.layers[0].get_weights()])
+    for mo in (full, t4, rm):
+        w0, y0 = snap[id(mo)]
+        for a, b in zip(w0, mo.get_weights()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(mo.predict(x_small), y0)
+    assert not np.array_equal(sm.predict(x_small), snap[id(sm)][1])

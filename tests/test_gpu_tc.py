@@ -14,7 +14,10 @@ import torch
 import svdlstm
 from helpers import oracle_twin
 
+import os
+
 pytestmark = pytest.mark.gpu
+GOLDEN_W = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dropbear_weights.npz")
 
 
 def _models(H, L, seed=0):
@@ -58,7 +61,9 @@ def test_tc_streamed_matches_oracle(oracle, rank):
 
 def test_tc_reduced_form_and_rmse_delta(oracle):
     """2-factor (ReducedLSTMCell) weights on the tensor-core engine, and the RMSE delta vs the FP32 engine that
-    bench.py reports.  C = inv(V1) V2 has large entries, so FP16 rounding is amplified: looser bound, stated."""
+    bench.py reports.  C = inv(V1) V2 has entries in the hundreds -- FP16 is the wrong container for it (5 % errors in round 1)
+    -- so the engine runs the block as its exact 3-factor equivalent in . (B P s) . Q^T with [I | C] = P s Q^T (K2 on
+    device): the 2-factor form now meets the SAME bar as the 3-factor one (2e-3 relative + 2e-4)."""
     _, sm = _models(128, 2)
     x = torch.randn(64, 40, 16, generator=torch.Generator().manual_seed(3)).cuda()
     m3 = svdlstm.truncate_singular_model(sm, 32)
@@ -69,7 +74,14 @@ def test_tc_reduced_form_and_rmse_delta(oracle):
     assert rmse_delta < 5e-4 * max(scale, 1.0), rmse_delta
     m2 = svdlstm.make_LSTM_reduced_model(sm, rank=32)
     y2 = m2.predict(x.cpu().numpy(), engine="tc")
-    _check(y2, oracle_twin(oracle, m2).predict(x.cpu().numpy()), "tc 2-factor r=32", rel=5e-2, abs_=2e-3)
+    _check(y2, oracle_twin(oracle, m2).predict(x.cpu().numpy()), "tc 2-factor r=32")
+    # the shipped DROPBEAR model's 2-factor form (cond(V1) up to 136, max|C| ~ 650) at every rank, units padded 15 -> 128
+    layers, dense = svdlstm.load_model_weights_npz(GOLDEN_W)
+    dsm = svdlstm.make_LSTM_singular_model(svdlstm.full_model_from_weights(layers, dense), merged_kernel=True, return_sequences=True)
+    xd = np.random.default_rng(4).standard_normal((40, 60, 16)).astype(np.float32)
+    for r in (15, 8, 3):
+        md = svdlstm.make_LSTM_reduced_model(dsm, rank=r)
+        _check(md.predict(xd, engine="tc"), oracle_twin(oracle, md).predict(xd), "tc DROPBEAR 2-factor r=%d" % r)
 
 
 def test_tc_batch_properties_full_tile_count():
@@ -108,11 +120,9 @@ def test_tc_rejects_what_it_cannot_run():
     split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
     with pytest.raises((RuntimeError, ValueError), match="merged"):
         split(x, engine="tc")
-    layers, dense = svdlstm.synthetic_layers(16, 64, 1, seed=0)   # units not a multiple of 128
-    sm64 = svdlstm.make_LSTM_singular_model(svdlstm.full_model_from_weights(layers, dense), merged_kernel=True,
-                                            return_sequences=True)
-    with pytest.raises((RuntimeError, ValueError), match="units"):
-        sm64(x, engine="tc")
+    layers, dense = svdlstm.synthetic_layers(16, 1100, 1, seed=0)   # more than 1024 units
+    with pytest.raises((RuntimeError, ValueError), match="units|ranks"):
+        svdlstm.full_model_from_weights(layers, dense, return_sequences=True)(x, engine="tc")
 
 
 def test_tc_launch_shapes_agree(monkeypatch):
@@ -148,11 +158,11 @@ def test_tc_three_layers_pipelined_and_large_batch_fallback(oracle):
     _check(yb[idx.cuda()].cpu().numpy(), oracle_twin(oracle, m).predict(xb[idx.cuda()].cpu().numpy()), "tc large batch (per-layer launches)")
 
 
-def test_tc_full_c3_size_properties():
+def test_tc_full_c3_size_properties(oracle):
     """BASELINE configs[2] at full size (B=4096, T=1024, H=256, L=2, rank 128 -> all layers in one pipelined launch,
     64-sequence tiles, streamed weights).  Size-independent properties: (a) a sequence's output does not depend on the
     batch it travels in -- rows taken from the big run equal the same rows run as a small batch (different tile, column,
-    launch shape) to FP32 rounding of the Dense sum; (b) against the FP32 engine over all 1024 steps the error stays
+    launch shape) to FP32 rounding of the Dense sum; (b) against the float64 oracle over all 1024 steps the error stays
     at the reduced-precision level and does not grow with time; (c) the run is deterministic."""
     _, sm = _models(256, 2)
     m = svdlstm.truncate_singular_model(sm, 128)
@@ -162,54 +172,16 @@ def test_tc_full_c3_size_properties():
     idx = torch.tensor([0, 1, 63, 64, 65, 2047, 2048, 4032, 4095]).cuda()
     y_small = m(x[idx].contiguous(), engine="tc")
     assert float((y_small - y[idx]).abs().max()) < 2e-6
-    y32 = m(x[idx].contiguous(), engine="general")
-    err = (y[idx] - y32).abs()
-    scale = float(y32.abs().max())
+    # (b) against the float64 ORACLE (not another CUDA engine) on the same weights, all 1024 steps of the sampled sequences
+    y_or = torch.from_numpy(oracle_twin(oracle, m).predict(x[idx].cpu().numpy())).float()
+    err = (y[idx].cpu() - y_or).abs()
+    scale = float(y_or.abs().max())
     assert float(err.max()) < 2e-3 * scale + 2e-4
     assert float(err[:, -128:].max()) < 2.0 * float(err[:, :512].max()) + 1e-4     # no drift over the sequence
+    # ... and the FP32 general engine at this full-size shape holds the 1e-5 bar against the same oracle
+    from helpers import assert_parity
+    assert_parity(m(x[idx].contiguous(), engine="general").cpu().numpy(), y_or.double().numpy(), "C3 rank 128 general engine, T=1024")
     assert torch.equal(m(x, engine="tc"), y)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# paired-CTA kernel (csrc/k1c_pair.cuh, tcgen05 cta_group::2): opt-in with SVDLSTM_TC_MODE=pair
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.fixture
-def pair_mode(monkeypatch):
-    monkeypatch.setenv("SVDLSTM_TC_MODE", "pair")
-    monkeypatch.setenv("SVDLSTM_PAIR_DEBUG", "1")   # a protocol bug is reported as an error instead of hanging the GPU
-    yield
-    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
-
-
-@pytest.mark.parametrize("L,rank,B,T", [(1, 128, 128, 6), (2, 128, 300, 9), (2, 64, 128, 5), (2, 40, 200, 7), (2, 256, 130, 5), (3, 128, 128, 5)])
-def test_tc_pair_matches_oracle_and_single_cta(oracle, monkeypatch, L, rank, B, T):
-    """Two CTAs per 128-sequence tile, M=256 N=128 pair MMAs, h / t_u exchanged through distributed shared memory
-    (st.async + tx-counted mbarriers), the next layer's t_w handed over instead of h.  Same arithmetic as the
-    single-CTA kernel (identical FP16 operands, identical K order): results must be BIT-IDENTICAL to it whenever
-    the Dense top is fused in both (ranks < 256), and within the engine's tolerance of the float64 oracle."""
-    _, sm = _models(256, L)
-    m = svdlstm.truncate_singular_model(sm, rank)
-    x = np.random.default_rng(7).standard_normal((B, T, 16)).astype(np.float32)
-    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
-    y_single = m.predict(x, engine="tc")
-    monkeypatch.setenv("SVDLSTM_TC_MODE", "pair")
-    monkeypatch.setenv("SVDLSTM_PAIR_DEBUG", "1")
-    y_pair = m.predict(x, engine="tc")
-    y_pair2 = m.predict(x, engine="tc")
-    monkeypatch.delenv("SVDLSTM_TC_MODE", raising=False)
-    assert np.array_equal(y_pair, y_pair2), "paired kernel is not deterministic"
-    if rank < 256:
-        assert np.array_equal(y_pair, y_single), "paired kernel differs from the single-CTA kernel: max %.3e" % np.abs(y_pair - y_single).max()
-    _check(y_pair, oracle_twin(oracle, m).predict(x), "tc pair L=%d r=%d" % (L, rank))
-
-
-def test_tc_pair_rejects_unsupported(pair_mode):
-    """The paired kernel needs H in {256, 512} and a Dense top; anything else is an error, never a silent fallback."""
-    _, sm = _models(128, 2)
-    m = svdlstm.truncate_singular_model(sm, 32)
-    x = np.zeros((4, 3, 16), np.float32)
-    with pytest.raises((ValueError, RuntimeError)):
-        m.predict(x, engine="tc")
 
 
 def test_tc_units_1024_matches_oracle(oracle):
@@ -317,3 +289,73 @@ def test_tc_full_model_matches_oracle(oracle):
     y = full.predict(x, engine="tc")
     assert full.last_engine() == svdlstm.ENGINE_TC
     _check(y, oracle_twin(oracle, full).predict(x), "tc full model H=256 L=2")
+
+
+def test_tc_dropbear_model_padded_units(oracle):
+    """J2: the shipped 3 x 15 DROPBEAR model on the tensor-core engine.  Units are padded 15 -> 128 with zero weights (padded
+    cells stay at h = c = 0 exactly), layers run pipelined.  Full model, 3-factor ranks and return_state round trip."""
+    layers, dense = svdlstm.load_model_weights_npz(GOLDEN_W)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    x = np.random.default_rng(21).standard_normal((70, 200, 16)).astype(np.float32)
+    y_or = oracle_twin(oracle, full).predict(x)
+    _check(full.predict(x, engine="tc"), y_or, "tc DROPBEAR full")
+    assert full.last_engine() == svdlstm.ENGINE_TC
+    for r in (15, 10, 4, 1):
+        m = svdlstm.truncate_singular_model(sm, r)
+        _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc DROPBEAR 3F r=%d" % r)
+    # chunked == unchunked with the state carried (state arrays are (B, 15): the true units)
+    m = svdlstm.truncate_singular_model(sm, 8)
+    xd = torch.from_numpy(x).cuda()
+    y_all = m(xd, engine="tc")
+    ya, st = m.stream(xd[:, :77], None, engine="tc")
+    assert tuple(st[0][0].shape) == (70, 15)
+    yb, _ = m.stream(xd[:, 77:], st, engine="tc")
+    assert torch.equal(torch.cat([ya, yb], 1), y_all)
+
+
+def test_auto_engine_regime_switch(monkeypatch):
+    """north_star: "switches to tensor-core tiles only when batch x 4H makes the thin contraction genuinely dense".
+    engine=None / "auto": batch >= 128 and units >= 64 on a supported model -> tcgen05 engine; small batches, small models,
+    unsupported forms and engine="fp32" -> FP32 engines.  This is what rmodel.predict(X) (svd_acceleration_v3.py:150-151) runs."""
+    _, sm = _models(256, 2)
+    m = svdlstm.truncate_singular_model(sm, 128)
+    xb = torch.randn(4096, 8, 16, generator=torch.Generator().manual_seed(30)).cuda()
+    y = m.predict(xb.cpu().numpy())                     # no engine argument, host array in / out
+    assert m.last_engine() == svdlstm.ENGINE_TC
+    y32 = m.predict(xb.cpu().numpy(), engine="fp32")
+    assert m.last_engine() == svdlstm.ENGINE_GENERAL
+    assert float(np.abs(y - y32).max()) < 2e-3 * float(np.abs(y32).max()) + 2e-4
+    m(xb[:64])
+    assert m.last_engine() == svdlstm.ENGINE_GENERAL      # 64 sequences: not dense enough
+    r2 = svdlstm.make_LSTM_reduced_model(sm, rank=64)       # the reference's own timed object: a 2-factor model
+    r2(xb)
+    assert r2.last_engine() == svdlstm.ENGINE_TC
+    split = svdlstm.make_LSTM_singular_model(_models(256, 1)[0], merged_kernel=False, return_sequences=True)
+    split(xb[:256])
+    assert split.last_engine() == svdlstm.ENGINE_GENERAL  # split cells are an FP32-engine form
+    layers, dense = svdlstm.load_model_weights_npz(GOLDEN_W)
+    small = svdlstm.full_model_from_weights(layers, dense)
+    small(xb[:512])
+    assert small.last_engine() in (svdlstm.ENGINE_WAVEFRONT, svdlstm.ENGINE_GENERAL)   # 15 units: latency regime
+    # return_sequences=False (the reference builders' default) also takes the fast path: last step of the sequence
+    mlast = svdlstm.truncate_singular_model(svdlstm.make_LSTM_singular_model(_models(256, 2)[0], merged_kernel=True), 32)
+    ylast = mlast(xb)
+    assert tuple(ylast.shape) == (4096, 1) and mlast.last_engine() == svdlstm.ENGINE_TC
+
+
+def test_tc_sees_dense_and_variable_updates(oracle):
+    """the engine bakes the Dense kernel and the factors into FP16 images.  In-place updates through
+    Dense.set_weights / TimeDistributed.set_weights / Variable.assign must invalidate them."""
+    _, sm = _models(128, 2)
+    m = svdlstm.truncate_singular_model(sm, 16)
+    x = np.random.default_rng(40).standard_normal((40, 10, 16)).astype(np.float32)
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "before update")
+    dk, db = m.layers[-1].get_weights()
+    m.layers[-1].set_weights([dk * -1.7, db + 0.3])
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "after Dense.set_weights")
+    cell = m.layers[0].cell
+    cell.recurrent_kernel.assign(cell.recurrent_kernel.numpy() * 0.5)      # sigma_u through Variable.assign
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "after Variable.assign")
+    m.layers[-1].layer.bias.assign(np.array([1.25], np.float32))
+    _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "after Dense bias assign")

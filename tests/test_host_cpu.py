@@ -136,3 +136,78 @@ def test_weights_json_roundtrip_and_zip(tmp_path, dropbear_weights):
         for (W, U, b), (Wz, Uz, bz) in zip(layers, lz):
             assert np.array_equal(W, Wz) and np.array_equal(U, Uz) and np.array_equal(b, bz)
         assert np.allclose(np.asarray(dense[1]).reshape(-1), dz[1])
+
+
+@pytest.mark.parametrize("D,H", [(1, 5), (3, 1), (1, 1), (4, 6)])
+@pytest.mark.parametrize("transposed", [True, False])
+def test_csv_roundtrip_degenerate_shapes_and_layer_order(tmp_path, D, H, transposed):
+    """np.loadtxt returns 0-D / 1-D arrays when units or input_dim is 1 (the reference's own v2 builders use
+    InputLayer([None, 1])); shapes must come from the bias length, in both orientations.  Twelve layers check that
+    lstm_9 sorts before lstm_10 (numeric suffix, not string order)."""
+    rng = np.random.default_rng(D * 10 + H)
+    n_layers = 12
+    layers = []
+    d = D
+    for _ in range(n_layers):
+        layers.append((rng.standard_normal((d, 4 * H)).astype(np.float32), rng.standard_normal((H, 4 * H)).astype(np.float32),
+                       rng.standard_normal(4 * H).astype(np.float32)))
+        d = H
+    dense = (rng.standard_normal((H, 1)).astype(np.float32), rng.standard_normal(1).astype(np.float32))
+    pth = str(tmp_path / "w")
+    svdlstm.save_model_weights_csv(layers, dense, pth, transposed=transposed)
+    l2, d2 = svdlstm.load_model_weights_csv(pth, transposed=transposed)
+    assert len(l2) == n_layers
+    for (W, U, b), (W2, U2, b2) in zip(layers, l2):
+        assert W2.shape == W.shape and U2.shape == U.shape and b2.shape == b.shape
+        assert np.allclose(W, W2, rtol=1e-6) and np.allclose(U, U2, rtol=1e-6) and np.allclose(b, b2, rtol=1e-6)
+    assert np.allclose(dense[0], d2[0], rtol=1e-6) and np.allclose(dense[1], d2[1], rtol=1e-6)
+
+
+def test_preprocess_and_split_train_random_follow_the_reference_recipe():
+    """svd_acceleration_v3.py:24-87 on a synthetic recording (the real data_6_with_FFT.json is not shipped): NaN forward fill,
+    1.5 s settle cut, Fourier resampling, standardisation, 16-wide framing, the 30.7 s split and the reference's
+    (t, t_test, t_train) return order; split_train_random windows + the target one frame past each window."""
+    from scipy import signal
+    rng = np.random.default_rng(0)
+    acc_t = np.sort(rng.uniform(0, 40.0, 40000))
+    acc = np.sin(40 * acc_t) + 0.1 * rng.standard_normal(acc_t.size)
+    pin_t = np.linspace(0, 40.0, 900)
+    pin = 0.1 + 0.05 * np.sin(0.7 * pin_t)
+    pin[[0, 5, 6, 400]] = np.nan
+    data = {"acceleration_data": acc.tolist(), "time_acceleration_data": acc_t.tolist(),
+            "measured_pin_location": pin.tolist(), "measured_pin_location_tt": pin_t.tolist()}
+    period = 2e-3
+    (X, X_tr, X_te), (y, y_tr, y_te), (t, t_te, t_tr), pin_scaler, acc_scaler = svdlstm.preprocess(period, data=data)
+    # straight restatement of the recipe
+    p = pin.copy()
+    for i in range(len(p)):
+        if math.isnan(p[i]):
+            p[i] = p[i - 1]
+    p, pt = p[pin_t > 1.5], pin_t[pin_t > 1.5] - 1.5
+    a, at = acc[acc_t > 1.5], acc_t[acc_t > 1.5] - 1.5
+    num = int((at[-1] - at[0]) / period)
+    ra, rt = signal.resample(a, num, at)
+    rp = np.interp(rt, pt, p)
+    an = (ra - ra.mean()) / ra.std()
+    pn = ((rp - rp.mean()) / rp.std()).astype(np.float32)
+    n = an.size // 16
+    assert X.shape == (1, n, 16) and y.shape == (n,) and t.shape == (n,)
+    assert np.allclose(X[0], an[:n * 16].reshape(n, 16), atol=1e-12)
+    assert np.array_equal(y, pn[:n * 16].reshape(n, 16).T[0]) and y.dtype == np.float32
+    assert np.allclose(t, rt[:n * 16].reshape(n, 16).T[0])
+    assert X_tr.shape[1] == int((t < 30.7).sum()) and X_te.shape[1] == int((t > 30.7).sum())
+    assert np.array_equal(t_tr, t[t < 30.7]) and np.array_equal(t_te, t[t > 30.7]) and np.array_equal(y_te, y[t > 30.7])
+    assert np.allclose(pin_scaler.inverse_transform(y.reshape(-1, 1)).ravel(), rp[:n * 16:16], atol=1e-6)
+    assert np.allclose(acc_scaler.inverse_transform(X[0].reshape(-1, 1)).ravel(), ra[:n * 16], atol=1e-9)
+    Xm, ym = svdlstm.split_train_random(X_tr, y_tr, 64, 200, rng=3)
+    assert Xm.shape == (64, 200, 16) and ym.shape == (64,)
+    starts = np.random.default_rng(3).integers(0, X_tr.shape[1] - 200, size=64)
+    for i in (0, 17, 63):
+        assert np.array_equal(Xm[i], X_tr[0, starts[i]:starts[i] + 200]) and ym[i] == y_tr[starts[i] + 200]
+    np.random.seed(5)
+    Xg, yg = svdlstm.split_train_random(X_tr, y_tr, 8, 50)          # global-state draw, like the reference's randint
+    np.random.seed(5)
+    ref_idx = [np.random.randint(0, X_tr.shape[1] - 50) for _ in range(8)]
+    assert Xg.shape == (8, 50, 16) and all(0 <= s < X_tr.shape[1] - 50 for s in ref_idx)
+    with pytest.raises(ValueError):
+        svdlstm.split_train_random(X_tr[:, :100], y_tr[:100], 4, 200)
