@@ -145,6 +145,33 @@ int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items, double* ou
 int svdlstm_sweep_sse(const float* pred, const float* target, int n_ranks, int64_t n, double* sse,
                       void* stream);
 
+/* ---- real-time batch-1 stream -------------------------------------------------------------------
+ * The reference's deployment setting: a stateful LSTM (svd_classes_v3.py:421-426) fed one frame every
+ * 400-500 us (train_full_model_v4.py:14-16), i.e. `model.predict` called per sample
+ * (svd_acceleration_v3.py:151).  svdlstm_stream_open launches ONE persistent kernel for the handle's
+ * model (it must fit the wavefront engine: units, input_dim, ranks <= 32; input_dim <= 30; <= 15
+ * outputs); afterwards a sample costs no CUDA call at all: svdlstm_stream_step writes the input_dim
+ * floats of x_t (HOST pointer) into a ring in host-mapped pinned memory, the kernel polls it, runs all
+ * layers + the Dense top from registers and writes y_t back into host memory, where the call picks it
+ * up (blocking; y_t is a HOST pointer to n_out -- or units_last -- floats).  State (h, c) persists
+ * between calls.  The kernel parks its state and leaves after idle_ms (<= 0: 50 ms) without a sample
+ * -- a forgotten stream can neither pin an SM nor stall a cudaDeviceSynchronize for long -- and the
+ * next step relaunches it transparently; the same happens after the handle's weights are re-bound.
+ * One caller thread per stream.
+ *   svdlstm_stream_run   feeds n samples paced at period_us (0 = back to back) from native code and
+ *                        records the per-sample latency (write of x_t -> y_t visible) in latency_us
+ *                        (may be NULL): the measurement loop of bench.py, free of interpreter overhead.
+ *   svdlstm_stream_reset sets the state (NULL, NULL = zeros; else [layer][units] arrays, host or device).
+ *   svdlstm_stream_state reads the state back the same way.                                          */
+typedef struct svdlstm_stream_s* svdlstm_stream;
+int svdlstm_stream_open(svdlstm_handle h, int idle_ms, svdlstm_stream* out);
+int svdlstm_stream_step(svdlstm_stream s, const float* x_t, float* y_t);
+int svdlstm_stream_run(svdlstm_stream s, const float* x, int n, double period_us, float* y, float* latency_us);
+int svdlstm_stream_reset(svdlstm_stream s, const float* h0, const float* c0);
+int svdlstm_stream_state(svdlstm_stream s, float* h_n, float* c_n);
+int svdlstm_stream_launches(svdlstm_stream s);
+int svdlstm_stream_close(svdlstm_stream s);
+
 const char* svdlstm_last_error(void);
 const char* svdlstm_version(void);
 

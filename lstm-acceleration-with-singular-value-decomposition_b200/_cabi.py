@@ -35,7 +35,8 @@ EXPORTS = [
     "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
     "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_svd_jacobi_batched",
     "svdlstm_reduce_factors", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
-    "svdlstm_version",
+    "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
+    "svdlstm_stream_state", "svdlstm_stream_launches", "svdlstm_stream_close",
 ]
 
 
@@ -88,6 +89,20 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_penalties.restype = ci
     L.svdlstm_sweep_sse.argtypes = [vp, vp, ci, ctypes.c_int64, vp, vp]
     L.svdlstm_sweep_sse.restype = ci
+    L.svdlstm_stream_open.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    L.svdlstm_stream_open.restype = ci
+    L.svdlstm_stream_step.argtypes = [vp, vp, vp]
+    L.svdlstm_stream_step.restype = ci
+    L.svdlstm_stream_run.argtypes = [vp, vp, ci, ctypes.c_double, vp, vp]
+    L.svdlstm_stream_run.restype = ci
+    L.svdlstm_stream_reset.argtypes = [vp, vp, vp]
+    L.svdlstm_stream_reset.restype = ci
+    L.svdlstm_stream_state.argtypes = [vp, vp, vp]
+    L.svdlstm_stream_state.restype = ci
+    L.svdlstm_stream_launches.argtypes = [vp]
+    L.svdlstm_stream_launches.restype = ci
+    L.svdlstm_stream_close.argtypes = [vp]
+    L.svdlstm_stream_close.restype = ci
     L.svdlstm_last_error.argtypes = []
     L.svdlstm_last_error.restype = ctypes.c_char_p
     L.svdlstm_version.argtypes = []

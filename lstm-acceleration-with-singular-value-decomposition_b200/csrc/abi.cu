@@ -27,19 +27,22 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 using namespace svdlstm;
 
-struct svdlstm_model_s {
-  ModelDesc md;             // host copy (device pointers inside)
-  bool layer_set[kMaxLayers];
-  ModelDesc* dev_md;        // device copy, re-uploaded when dirty
-  ModelDesc* pinned_md;     // pinned staging so the upload is stream-ordered and async
-  cudaEvent_t md_event;     // recorded after every forward: the last reader of dev_md / pinned_md (whatever its stream)
-  bool dirty;
-  bool tc_dirty;
-  TcState* tc;
-  int last_launches;
-  int last_engine;
-  int64_t n_weights[kMaxLayers];
-};
+namespace svdlstm {
+// Device copy of the model description, re-uploaded (stream-ordered, through a pinned staging copy) when weights were re-bound.
+int upload_model_desc(svdlstm_model_s* h, cudaStream_t stream) {
+  if (!h->dirty) return 0;
+  if (!h->dev_md) SVD_CUDA_TRY(cudaMalloc(&h->dev_md, sizeof(ModelDesc)));
+  if (!h->pinned_md) SVD_CUDA_TRY(cudaMallocHost(&h->pinned_md, sizeof(ModelDesc)));
+  // An earlier forward -- possibly on ANOTHER stream -- may still be reading dev_md, or its upload may still be reading the
+  // pinned staging copy: wait for the event recorded after that forward, not for the current stream.
+  if (h->md_event) SVD_CUDA_TRY(cudaEventSynchronize(h->md_event));
+  memcpy(h->pinned_md, &h->md, sizeof(ModelDesc));
+  SVD_CUDA_TRY(cudaMemcpyAsync(h->dev_md, h->pinned_md, sizeof(ModelDesc), cudaMemcpyHostToDevice, stream));
+  h->dirty = false;
+  ++h->md_version;
+  return 0;
+}
+}  // namespace svdlstm
 
 extern "C" {
 
@@ -71,6 +74,7 @@ int svdlstm_create(svdlstm_handle* out, int n_layers, int input_dim, const int* 
   m->dev_md = nullptr;
   m->pinned_md = nullptr;
   m->md_event = nullptr;
+  m->md_version = 0;
   m->dirty = true;
   m->tc_dirty = true;
   m->tc = nullptr;
@@ -230,16 +234,7 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
     return -2;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (h->dirty) {
-    if (!h->dev_md) SVD_CUDA_TRY(cudaMalloc(&h->dev_md, sizeof(ModelDesc)));
-    if (!h->pinned_md) SVD_CUDA_TRY(cudaMallocHost(&h->pinned_md, sizeof(ModelDesc)));
-    // An earlier forward -- possibly on ANOTHER stream -- may still be reading dev_md, or its upload may still be reading the
-    // pinned staging copy: wait for the event recorded after that forward, not for the current stream.
-    if (h->md_event) SVD_CUDA_TRY(cudaEventSynchronize(h->md_event));
-    memcpy(h->pinned_md, &h->md, sizeof(ModelDesc));
-    SVD_CUDA_TRY(cudaMemcpyAsync(h->dev_md, h->pinned_md, sizeof(ModelDesc), cudaMemcpyHostToDevice, stream));
-    h->dirty = false;
-  }
+  if (int e = upload_model_desc(h, stream)) return e;
   ForwardArgs a{x, y, h0, c0, h_n, c_n, mask, B, T, flags};
   int launches = 0;
   int rc = 0;

@@ -65,6 +65,8 @@ struct ModelDesc {
   LayerDesc layers[kMaxLayers];
 };
 
+struct TcState;  // packed FP16 weight-stream images owned by the handle (k1b_tc.cu)
+
 struct ForwardArgs {
   const float* x;
   float* y;
@@ -76,14 +78,62 @@ struct ForwardArgs {
   int B, T, flags;
 };
 
+// ---- real-time stream (k1_wavefront.cu <STREAM>, stream.cu): rings in host-mapped pinned memory -------------------------------
+// Sample s travels in slot s % kStreamSlots tagged s+1.  A tag is only trusted together with the data of its OWN 64-byte line
+// (the PCIe root complex reads / writes a cache line atomically; x86 stores become visible in program order), so the input
+// slot carries the tag in both of its lines.
+constexpr int kStreamSlots = 64;
+struct StreamSlotIn { uint32_t w[32]; };    // line A = [tag, x0..x14], line B = [tag, x15..x29]
+struct StreamSlotOut { uint32_t w[16]; };   // [tag, y0..y14]
+struct StreamCtl {
+  volatile uint32_t stop;          // host -> device: leave at the next poll
+  uint32_t pad0[15];
+  volatile uint32_t exited;        // device -> host: generation of the launch that has left (written last)
+  volatile uint32_t exit_reason;   // 1 = stop, 2 = idle
+  volatile uint32_t consumed;      // samples consumed by all launches so far
+  uint32_t pad1[13];
+};
+struct StreamArgs {
+  StreamSlotIn* in;
+  StreamSlotOut* out;
+  StreamCtl* ctl;
+  uint32_t first_seq;              // samples consumed before this launch (state was parked after them)
+  uint32_t generation;
+  unsigned long long idle_ns;      // leave after this long without a sample
+};
+
+}  // namespace svdlstm
+
+// the opaque handle of include/svdlstm.h
+struct svdlstm_model_s {
+  svdlstm::ModelDesc md;             // host copy (device pointers inside)
+  bool layer_set[svdlstm::kMaxLayers];
+  svdlstm::ModelDesc* dev_md;        // device copy, re-uploaded when dirty
+  svdlstm::ModelDesc* pinned_md;     // pinned staging so the upload is stream-ordered and async
+  cudaEvent_t md_event;              // recorded after every forward: the last reader of dev_md / pinned_md (whatever its stream)
+  unsigned long long md_version;     // bumped by every upload (a running real-time stream notices re-bound weights)
+  bool dirty;
+  bool tc_dirty;
+  struct svdlstm::TcState* tc;
+  int last_launches;
+  int last_engine;
+  int64_t n_weights[svdlstm::kMaxLayers];
+};
+
+namespace svdlstm {
+
+int upload_model_desc(svdlstm_model_s* h, cudaStream_t stream);
+
 // engines (k1_*.cu); each returns 0 / error code and the number of kernels it launched
 int run_general(const ModelDesc& host_md, const ModelDesc* dev_md, const ForwardArgs& a,
                 cudaStream_t stream, int* launches);
 bool wavefront_supported(const ModelDesc& md, const ForwardArgs& a);
 int run_wavefront(const ModelDesc& host_md, const ModelDesc* dev_md, const ForwardArgs& a,
                   cudaStream_t stream, int* launches);
+bool stream_supported(const ModelDesc& md, const char** why);
+int launch_wavefront_stream(const ModelDesc& md, const ModelDesc* dev_md, float* state_h, float* state_c, const StreamArgs& sa,
+                            cudaStream_t stream);
 bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why);
-struct TcState;  // packed bf16 weights owned by the handle
 int run_tc(const ModelDesc& host_md, TcState** state, bool weights_dirty, const ForwardArgs& a,
                 cudaStream_t stream, int* launches);
 void tc_free(TcState* s);

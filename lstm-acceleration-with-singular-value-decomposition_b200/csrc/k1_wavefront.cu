@@ -154,8 +154,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // Template shape (max over layers, zero padded): KIN4 float4s of stage-1 input, MP stage-1 columns
 // per lane, K4 float4s of stage-2 contraction, G gates per lane (2: two lanes per unit, 4: one).
-template <int KIN4, int MP, int K4, int G>
-__global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a) {
+//
+// STREAM = true is the real-time service (svd_classes_v3.py:421-426 `stateful`, driven at the reference's one-sample-every-400-us
+// setting, train_full_model_v4.py:14-16): ONE persistent CTA that never returns to the host between samples.  Its loader warp
+// polls a ring in host-mapped pinned memory for the next sample, the layer warps run that step one after the other (sub-tick l =
+// layer l: the prediction of sample s must not wait for sample s+L, so the wavefront is NOT used across samples), and the
+// output warp writes the prediction straight into host-mapped memory.  No launch, no memcpy, no stream synchronisation per
+// sample; state (h, c) stays in registers / shared memory and is parked in device memory when the kernel leaves (host `stop`,
+// or no sample for `idle_ns`: a forgotten stream must never pin an SM -- or block a cudaDeviceSynchronize -- for ever).
+template <int KIN4, int MP, int K4, int G, bool STREAM = false>
+__global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a, StreamArgs sa) {
   extern __shared__ __align__(16) float smem[];
   __shared__ WfPlan pl;
   const ModelDesc& md = *mdp;
@@ -224,7 +232,10 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
       for (int n = tid; n < 4 * H; n += nthr) smem[w.off_bias + n] = Ld.bias[n];
       // initial h into slot 1 (= slot of timestep -1)
       if (a.h0 != nullptr)
-        for (int j = tid; j < H; j += nthr) smem[w.off_vh + w.S1 + j] = a.h0[soff + (size_t)b * H + j];
+        for (int j = tid; j < H; j += nthr) {
+          smem[w.off_vh + w.S1 + j] = a.h0[soff + (size_t)b * H + j];
+          if (STREAM) smem[w.off_vh + j] = a.h0[soff + (size_t)b * H + j];   // a resumed stream may start on an odd step
+        }
       soff += (size_t)B * H;
     }
     if (md.n_out > 0) {
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   const float* xrow_base = a.x;
   const int off_x = pl.off_x, xstride = pl.xstride;
   // loader prologue: prefetch the first kPrefetch steps
-  if (role == 0) {
+  if (!STREAM && role == 0) {
     for (int s = 0; s < kPrefetch; ++s) {
       if (s < T && lane < D) {
         const int t = backwards ? (T - 1 - s) : s;
@@ -324,21 +335,9 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   const float dense_w = (role == L + 1 && n_out > 0 && lane < HL) ? smem[off_dense + lane] : 0.f;
   const float dense_b = (n_out > 0) ? smem[off_dense + 32] : 0.f;
 
-  for (int tick = 0; tick < n_ticks; ++tick) {
-    if (role == 0) {
-      // ---- loader: x for step tick+kPrefetch -------------------------------------------------
-      const int s = tick + kPrefetch;
-      if (s < T && lane < D) {
-        const int t = backwards ? (T - 1 - s) : s;
-        const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
-        cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
-      }
-      cp_async_commit();
-      cp_async_wait<kPrefetch - 2>();   // everything up to step tick+1 has landed before the barrier
-    } else if (is_layer) {
-      const int step = tick - lyr;
-      if (step >= 0 && step < T) {
-        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? (step % kXRing) : (step & 1)) * vin_sb;
+  // one step of the layer this warp owns: `step` selects the double-buffered h slots, `xslot` the x ring slot (layer 0)
+  auto layer_step = [&](const int step, const int xslot) {
+        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? xslot : (step & 1)) * vin_sb;
         const unsigned ha = vh_addr + (unsigned)((step + 1) & 1) * vh_sb;       // h_l(step-1)
         const unsigned ho = vh_addr + (unsigned)(step & 1) * vh_sb + 4u * (unsigned)j;
         // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
@@ -424,18 +423,18 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
         c_state = fmaf(fg, c_state, ig * gg);
         h_last = og * fast_tanh(c_state);
         if (sub == 0 && j < H) sts32(ho, h_last);
-      }
-    } else if (role == L + 1) {
-      // ---- output stage ----------------------------------------------------------------------
-      const int step = tick - L;
-      if (step >= 0 && step < T) {
+  };
+  auto output_step = [&](const int step) {
         const float* hv = &smem[out_vh_off + (step & 1) * out_vh_stride];
         if (n_out > 0) {
           float v = (lane < HL) ? hv[lane] * dense_w : 0.f;
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
           v += dense_b;
-          if (ret_seq) {
+          if constexpr (STREAM) {
+            // [tag, y] in one 64-byte line of host memory, one store instruction: the host sees the tag only with the value
+            if (lane < 2) sa.out[(uint32_t)step % kStreamSlots].w[lane] = lane == 0 ? (uint32_t)step + 1u : __float_as_uint(v);
+          } else if (ret_seq) {
             if (lane == 0) smem[off_y + (step % kYRing)] = v;
             if ((step % kYRing) == kYRing - 1 || step == T - 1) {
               __syncwarp();
@@ -449,6 +448,8 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
           } else if (step == T - 1 && lane == 0) {
             a.y[b] = v;
           }
+        } else if constexpr (STREAM) {
+          if (lane < 16) sa.out[(uint32_t)step % kStreamSlots].w[lane] = lane == 0 ? (uint32_t)step + 1u : (lane - 1 < HL ? __float_as_uint(hv[lane - 1]) : 0u);
         } else if (ret_seq || step == T - 1) {
           if (lane < HL) {
             size_t yi;
@@ -457,9 +458,84 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
             a.y[yi] = hv[lane];
           }
         }
+  };
+
+  if constexpr (!STREAM) {
+    for (int tick = 0; tick < n_ticks; ++tick) {
+      if (role == 0) {
+        // ---- loader: x for step tick+kPrefetch -------------------------------------------------
+        const int s = tick + kPrefetch;
+        if (s < T && lane < D) {
+          const int t = backwards ? (T - 1 - s) : s;
+          const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
+          cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
+        }
+        cp_async_commit();
+        cp_async_wait<kPrefetch - 2>();   // everything up to step tick+1 has landed before the barrier
+      } else if (is_layer) {
+        const int step = tick - lyr;
+        if (step >= 0 && step < T) layer_step(step, step % kXRing);
+      } else if (role == L + 1) {
+        const int step = tick - L;
+        if (step >= 0 && step < T) output_step(step);
       }
+      __syncthreads();
     }
+  } else {
+    // ======================= real-time service loop =============================================
+    __shared__ int s_exit;
+    if (tid == 0) s_exit = 0;
     __syncthreads();
+    uint32_t seq = sa.first_seq;     // samples consumed so far (by every launch of this stream)
+    while (true) {
+      if (role == 0) {
+        // ---- poll the host-mapped input ring for sample `seq` (tag seq+1 in BOTH 64-byte lines of its slot) ----
+        const uint32_t want = (seq & 0x7fffffffu) + 1u;
+        const volatile uint32_t* slot = sa.in[seq % kStreamSlots].w;
+        unsigned long long t0 = 0;
+        uint32_t v = 0;
+        int polls = 0, reason = 0;
+        while (true) {
+          v = slot[lane];                          // ONE 128-byte read over PCIe per poll
+          const uint32_t tag_a = __shfl_sync(0xffffffffu, v, 0), tag_b = __shfl_sync(0xffffffffu, v, 16);
+          if (tag_a == want && tag_b == want) break;
+          if ((++polls & 7) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            int r = 0;
+            if (lane == 0) {
+              if (sa.ctl->stop != 0u) r = 1;
+              else if (now - t0 > sa.idle_ns) r = 2;
+            }
+            reason = __shfl_sync(0xffffffffu, r, 0);
+            if (reason) break;
+          }
+        }
+        if (reason) {
+          if (lane == 0) s_exit = reason;
+        } else {
+          // line A = [tag, x0..x14], line B = [tag, x15..x29]
+          const int xi = lane < 16 ? lane - 1 : lane - 2;
+          if (lane != 0 && lane != 16 && xi < D) smem[off_x + xi] = __uint_as_float(v);
+        }
+      }
+      __syncthreads();
+      if (s_exit) break;
+      const int step = (int)(seq & 0x7fffffffu);
+      for (int sub = 0; sub <= L; ++sub) {
+        if (is_layer && lyr == sub) layer_step(step, 0);
+        else if (role == L + 1 && sub == L) output_step(step);
+        __syncthreads();
+      }
+      ++seq;
+    }
+    if (tid == 0) {
+      sa.ctl->consumed = seq;
+      sa.ctl->exit_reason = (uint32_t)s_exit;
+      __threadfence_system();
+      sa.ctl->exited = sa.generation;
+    }
   }
 
   // ---------------- final state ----------------------------------------------------------------
@@ -495,34 +571,35 @@ inline bool wf_shape(const WfPlan& pl, WfShape& s) {
   return s.mp * s.kin4 * 8 + s.g * s.k4 * 4 <= 200;
 }
 
-typedef void (*WfKernel)(const ModelDesc*, ForwardArgs);
+typedef void (*WfKernel)(const ModelDesc*, ForwardArgs, StreamArgs);
 
-template <int KIN4, int MP, int K4>
+template <int KIN4, int MP, int K4, bool STREAM>
 WfKernel wf_pick_g(int g) {
-  if (g == 2) return lstm_wavefront_kernel<KIN4, MP, K4, 2>;
-  if constexpr (MP * KIN4 * 8 + 4 * K4 * 4 <= 200) return lstm_wavefront_kernel<KIN4, MP, K4, 4>;
+  if (g == 2) return lstm_wavefront_kernel<KIN4, MP, K4, 2, STREAM>;
+  if constexpr (MP * KIN4 * 8 + 4 * K4 * 4 <= 200) return lstm_wavefront_kernel<KIN4, MP, K4, 4, STREAM>;
   return nullptr;
 }
-template <int KIN4, int MP>
+template <int KIN4, int MP, bool STREAM>
 WfKernel wf_pick_k(int k4, int g) {
   switch (k4) {
-    case 2: return wf_pick_g<KIN4, MP, 2>(g);
-    case 4: return wf_pick_g<KIN4, MP, 4>(g);
-    case 8: return wf_pick_g<KIN4, MP, 8>(g);
+    case 2: return wf_pick_g<KIN4, MP, 2, STREAM>(g);
+    case 4: return wf_pick_g<KIN4, MP, 4, STREAM>(g);
+    case 8: return wf_pick_g<KIN4, MP, 8, STREAM>(g);
     default:
-      if constexpr (MP * KIN4 * 8 + 2 * 16 * 4 <= 200) return wf_pick_g<KIN4, MP, 16>(g);
+      if constexpr (MP * KIN4 * 8 + 2 * 16 * 4 <= 200) return wf_pick_g<KIN4, MP, 16, STREAM>(g);
       return nullptr;
   }
 }
-template <int KIN4>
+template <int KIN4, bool STREAM>
 WfKernel wf_pick_mp(int mp, int k4, int g) {
   switch (mp) {
-    case 1: return wf_pick_k<KIN4, 1>(k4, g);
-    case 2: return wf_pick_k<KIN4, 2>(k4, g);
-    default: return wf_pick_k<KIN4, 4>(k4, g);
+    case 1: return wf_pick_k<KIN4, 1, STREAM>(k4, g);
+    case 2: return wf_pick_k<KIN4, 2, STREAM>(k4, g);
+    default: return wf_pick_k<KIN4, 4, STREAM>(k4, g);
   }
 }
-inline WfKernel wf_pick(const WfShape& s) { return s.kin4 == 4 ? wf_pick_mp<4>(s.mp, s.k4, s.g) : wf_pick_mp<8>(s.mp, s.k4, s.g); }
+template <bool STREAM = false>
+inline WfKernel wf_pick(const WfShape& s) { return s.kin4 == 4 ? wf_pick_mp<4, STREAM>(s.mp, s.k4, s.g) : wf_pick_mp<8, STREAM>(s.mp, s.k4, s.g); }
 
 }  // namespace
 
@@ -543,9 +620,32 @@ int run_wavefront(const ModelDesc& md, const ModelDesc* dev_md, const ForwardArg
   const size_t smem = (size_t)pl.total_floats * sizeof(float);
   SVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = 32 * (md.n_layers + 2);
-  kern<<<a.B, threads, smem, stream>>>(dev_md, a);
+  kern<<<a.B, threads, smem, stream>>>(dev_md, a, StreamArgs{});
   SVD_CUDA_TRY(cudaGetLastError());
   *launches = 1;
+  return 0;
+}
+
+// The real-time service kernel (one persistent CTA): see stream.cu for the host half of the protocol.
+bool stream_supported(const ModelDesc& md, const char** why) {
+  ForwardArgs a{};
+  if (!wavefront_supported(md, a)) { *why = "the real-time stream runs on the wavefront engine: units, input_dim, ranks <= 32, <= 6 layers, n_out <= 1"; return false; }
+  if (md.input_dim > 30) { *why = "the real-time stream carries at most 30 input features per sample (one 128-byte ring slot)"; return false; }
+  if (md.n_out == 0 && md.layers[md.n_layers - 1].units > 15) { *why = "the real-time stream returns at most 15 values per sample (one 64-byte ring slot)"; return false; }
+  return true;
+}
+
+int launch_wavefront_stream(const ModelDesc& md, const ModelDesc* dev_md, float* state_h, float* state_c, const StreamArgs& sa, cudaStream_t stream) {
+  WfPlan pl;
+  SVD_REQUIRE(wf_make_plan(md, pl), "real-time stream: model does not fit the wavefront engine");
+  WfShape sh;
+  WfKernel kern = wf_shape(pl, sh) ? wf_pick<true>(sh) : nullptr;
+  SVD_REQUIRE(kern != nullptr, "real-time stream: factor shapes exceed the register-resident budget");
+  const size_t smem = (size_t)pl.total_floats * sizeof(float);
+  SVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ForwardArgs a{nullptr, nullptr, state_h, state_c, state_h, state_c, nullptr, 1, 1, SVDLSTM_RETURN_SEQUENCES};
+  kern<<<1, 32 * (md.n_layers + 2), smem, stream>>>(dev_md, a, sa);
+  SVD_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

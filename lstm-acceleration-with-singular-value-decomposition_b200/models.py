@@ -277,8 +277,105 @@ class Sequential:
         st["y_done"][k].record(main)
         return _Pending(st["y_done"][k], None, st["y_host"][k])
 
+    def open_stream(self, idle_ms=50):
+        """Real-time batch-1 service (the reference's deployment: ``model.predict`` per 16-sample frame every 400-500 us on a
+        stateful LSTM; svd_classes_v3.py:421-426, train_full_model_v4.py:14-16).  Launches ONE persistent kernel and returns a
+        ``RealtimeStream``; each ``step(x_t)`` then costs no CUDA call (host-mapped rings, see include/svdlstm.h)."""
+        self.build()
+        if not self._fusable():
+            raise ValueError("open_stream() needs a stack of LSTM layers (+ Dense top) that runs as one fused handle")
+        return RealtimeStream(self._fused_handle(), idle_ms)
+
     def last_engine(self):
         return self._fused.last_engine() if self._fused is not None else None
+
+
+class RealtimeStream:
+    """Handle of one persistent real-time kernel (C-ABI ``svdlstm_stream_*``).  ``step`` = one sample in, one prediction out,
+    state carried on the device; ``run`` feeds a whole series paced at ``period_us`` from native code and returns the
+    per-sample latencies.  Use as a context manager or call ``close()``."""
+
+    def __init__(self, handle: Handle, idle_ms=50):
+        import ctypes
+        self._handle = handle        # keeps the weights alive
+        self._s = ctypes.c_void_p()
+        C.require_cuda()
+        C.check(C.lib().svdlstm_stream_open(handle.raw, int(idle_ms), ctypes.byref(self._s)))
+        self.input_dim = handle.input_dim
+        self.n_out = handle.n_out if handle.n_out > 0 else handle.units[-1]
+        self._x = np.zeros(self.input_dim, np.float32)
+        self._y = np.zeros(self.n_out, np.float32)
+        self._launches_seen = 0
+
+    def step(self, x_t) -> np.ndarray:
+        np.copyto(self._x, np.asarray(x_t, np.float32).reshape(-1))
+        C.check(C.lib().svdlstm_stream_step(self._s, self._x.ctypes.data, self._y.ctypes.data))
+        self._count_launches()
+        return self._y.copy()
+
+    def run(self, X, period_us=0.0):
+        """X (n, input_dim) host array -> (Y (n, n_out), latency_us (n,)): every sample is written when it is due
+        (i * period_us after the first) and its latency is the time until its prediction is visible on the host."""
+        X = np.ascontiguousarray(np.asarray(X, np.float32).reshape(-1, self.input_dim))
+        n = int(X.shape[0])
+        Y = np.empty((n, self.n_out), np.float32)
+        lat = np.empty(n, np.float32)
+        C.check(C.lib().svdlstm_stream_run(self._s, X.ctypes.data, n, float(period_us), Y.ctypes.data, lat.ctypes.data))
+        self._count_launches()
+        return Y, lat
+
+    def reset_states(self, states=None):
+        """Zero state, or (hs, cs): one (units,) / (1, units) array per layer each (``SingularLSTM.reset_states`` semantics)."""
+        if states is None:
+            C.check(C.lib().svdlstm_stream_reset(self._s, None, None))
+            return
+        hs, cs = states
+        h = np.ascontiguousarray(np.concatenate([np.asarray(_host(a), np.float32).reshape(-1) for a in hs]))
+        c = np.ascontiguousarray(np.concatenate([np.asarray(_host(a), np.float32).reshape(-1) for a in cs]))
+        if h.size != sum(self._handle.units) or c.size != h.size:
+            raise ValueError("state needs one (units,) vector per layer for h and for c")
+        C.check(C.lib().svdlstm_stream_reset(self._s, h.ctypes.data, c.ctypes.data))
+
+    def states(self):
+        tot = sum(self._handle.units)
+        h, c = np.empty(tot, np.float32), np.empty(tot, np.float32)
+        C.check(C.lib().svdlstm_stream_state(self._s, h.ctypes.data, c.ctypes.data))
+        hs, cs, off = [], [], 0
+        for u in self._handle.units:
+            hs.append(h[off:off + u].copy())
+            cs.append(c[off:off + u].copy())
+            off += u
+        return hs, cs
+
+    def kernel_launches(self) -> int:
+        """How many times the persistent kernel has been (re)launched: 1 for an uninterrupted stream."""
+        return int(C.lib().svdlstm_stream_launches(self._s))
+
+    def _count_launches(self):
+        n = self.kernel_launches()
+        C.add_launches(n - self._launches_seen)
+        self._launches_seen = n
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s.value:
+            C.check(C.lib().svdlstm_stream_close(self._s))
+            self._s.value = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _host(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
 
 
 class _Pending:

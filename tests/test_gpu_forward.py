@@ -245,3 +245,52 @@ def test_derived_models_own_their_weights(oracle, full, x_small):
             assert np.array_equal(a, b)
         assert np.array_equal(mo.predict(x_small), y0)
     assert not np.array_equal(sm.predict(x_small), snap[id(sm)][1])
+
+
+def test_realtime_stream_matches_oracle_and_survives_idle(oracle, full):
+    """the persistent real-time kernel fed through host-mapped rings.  One sample per call, state on the
+    device: the per-sample outputs equal the whole-sequence run (FP32 1e-5 bar vs the float64 oracle); an idle gap longer than
+    idle_ms parks the state and the next sample relaunches the kernel without losing it; reset_states / states round-trip;
+    a weight update is picked up."""
+    import time
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    for label, model in (("full", full), ("3F r8", svdlstm.truncate_singular_model(sm, 8)), ("2F r8", svdlstm.make_LSTM_reduced_model(sm, rank=8)),
+                         ("split 3F", svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True))):
+        x = np.random.default_rng(70).standard_normal((1, 300, 16)).astype(np.float32)
+        y_ref = oracle_twin(oracle, model).predict(x)[0]
+        with model.open_stream(idle_ms=20) as st:
+            ys = [st.step(x[0, t]) for t in range(100)]
+            assert st.kernel_launches() == 1
+            time.sleep(0.08)                                   # > idle_ms: the kernel parks its state and leaves
+            ys += [st.step(x[0, t]) for t in range(100, 150)]
+            assert st.kernel_launches() == 2
+            Y, lat = st.run(x[0, 150:], period_us=50.0)         # native paced loop
+            assert lat.shape == (150,) and float(np.median(lat)) < 200.0
+            hs, cs = st.states()
+            got = np.concatenate([np.stack(ys), Y])
+            extra = dict(ref32=oracle_twin(oracle, model, np.float32).predict(x)[0], extra_atol=cond_slack(model)) if "2F" in label else {}
+            assert_parity(got, y_ref, "real-time stream " + label, **extra)
+            # state round trip: restart from the state after 300 samples, replay the last 20 from the state after 280
+            st.reset_states(None)
+            for t in range(280):
+                st.step(x[0, t])
+            tail = np.stack([st.step(x[0, t]) for t in range(280, 300)])
+            assert np.array_equal(tail, got[280:300])
+            hs2, cs2 = st.states()
+            assert all(np.array_equal(a, b) for a, b in zip(hs + cs, hs2 + cs2))
+            st.reset_states((hs, cs))
+            assert all(np.array_equal(a, b) for a, b in zip(hs + cs, sum(st.states(), [])))
+    # weights re-bound under a live stream
+    m = svdlstm.truncate_singular_model(sm, 8)
+    x = np.random.default_rng(71).standard_normal((1, 40, 16)).astype(np.float32)
+    with m.open_stream() as st:
+        a = np.stack([st.step(x[0, t]) for t in range(20)])
+        dk, db = m.layers[-1].get_weights()
+        m.layers[-1].set_weights([dk * 2.0, db])
+        st.reset_states(None)
+        b = np.stack([st.step(x[0, t]) for t in range(20)])
+        assert np.allclose(b - db, 2.0 * (a - db), rtol=1e-5, atol=1e-6)
+    big, _ = None, None
+    layers, dense = svdlstm.synthetic_layers(16, 64, 1, seed=0)
+    with pytest.raises((ValueError, RuntimeError), match="wavefront"):
+        svdlstm.full_model_from_weights(layers, dense).open_stream()
