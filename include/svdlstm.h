@@ -123,6 +123,18 @@ int svdlstm_reduce_factors(const float* U_r, int ldu, const float* S_r, const fl
                            int m, int r, int n, float* B, float* C, float* pivot_ratio,
                            void* stream);
 
+/* The same for a batch of matrices (every factor of a model, or of a whole rank sweep) in ONE launch.  */
+typedef struct {
+  const float* U_r;
+  const float* S_r;
+  const float* V_r;
+  float* B;
+  float* C;
+  float* pivot_ratio;
+  int32_t ldu, ldv, m, r, n;
+} svdlstm_reduce_item;
+int svdlstm_reduce_factors_batched(const svdlstm_reduce_item* items, int n_items, void* stream);
+
 /* ---- fused Hoyer + orthogonality penalties ----------------------------------------------------
  * One launch evaluates every regulariser of a model: HoyerRegularizer.__call__
  * (svd_classes_v3.py:460-462) on sigma vectors and keras OrthogonalRegularizer(mode='rows')

@@ -12,7 +12,7 @@ from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell
                      PrunableTimeDistributed, ReducedLSTMCell, SingularLSTM, SingularLSTMCell, TimeDistributed,
                      Variable, evaluate_penalties, get_default_engine, set_default_engine)
 from .models import (RealtimeStream, Sequential, full_model_from_weights, make_LSTM_reduced_model, make_LSTM_singular_model,
-                     make_split_LSTM_singular_model, reduce_factors, svd_batched, truncate_singular_model)
+                     make_split_LSTM_singular_model, reduce_factors, reduce_factors_batched, svd_batched, truncate_singular_model)
 from .metrics import (count_weights, full_weight_count, reduced_merged_weight_count, reduced_split_weight_count,
                       reference_rmse, rmse, signaltonoise, sweep_sse, weight_reduction_percent)
 from .rank_reduce import (LSTM_wrapper, get_model_singular_values, reduce_matrix_rank, reduce_two_step,

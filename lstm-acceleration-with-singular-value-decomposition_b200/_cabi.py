@@ -34,7 +34,7 @@ EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",
     "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
     "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_svd_jacobi_batched",
-    "svdlstm_reduce_factors", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
+    "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
     "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
     "svdlstm_stream_state", "svdlstm_stream_launches", "svdlstm_stream_close",
 ]
@@ -43,6 +43,12 @@ EXPORTS = [
 class PenaltyItem(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
                 ("ld", ctypes.c_int32), ("gram", ctypes.c_int32), ("columns", ctypes.c_int32)]
+
+
+class ReduceItem(ctypes.Structure):
+    _fields_ = [("U_r", ctypes.c_void_p), ("S_r", ctypes.c_void_p), ("V_r", ctypes.c_void_p), ("B", ctypes.c_void_p),
+                ("C", ctypes.c_void_p), ("pivot_ratio", ctypes.c_void_p), ("ldu", ctypes.c_int32), ("ldv", ctypes.c_int32),
+                ("m", ctypes.c_int32), ("r", ctypes.c_int32), ("n", ctypes.c_int32)]
 
 
 _lib = None
@@ -85,6 +91,8 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_svd_jacobi_batched.restype = ci
     L.svdlstm_reduce_factors.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
     L.svdlstm_reduce_factors.restype = ci
+    L.svdlstm_reduce_factors_batched.argtypes = [ctypes.POINTER(ReduceItem), ci, vp]
+    L.svdlstm_reduce_factors_batched.restype = ci
     L.svdlstm_penalties.argtypes = [ctypes.POINTER(PenaltyItem), ci, vp, vp]
     L.svdlstm_penalties.restype = ci
     L.svdlstm_sweep_sse.argtypes = [vp, vp, ci, ctypes.c_int64, vp, vp]

@@ -12,6 +12,8 @@
 // holds for the smallest sigma too.
 //   small path : one CTA per matrix, G and J in shared memory, a warp per pair;
 //   large path : G, J in global (L2-resident) scratch, one launch per round, a CTA per pair.
+#include <vector>
+
 #include "common.cuh"
 
 namespace svdlstm {
@@ -345,96 +347,169 @@ __global__ void __launch_bounds__(kSvdThreads) svd_large_finalize(const double* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b: B = (U_r * S_r) V1 ; C = V1^-1 V2 by Gauss-Jordan with partial pivoting on [V1 | V2] (float64)
+// K2b: B = (U_r * S_r) V1 ; C = V1^-1 V2  for a BATCH of matrices in ONE launch (float64 inside).
+//   CTA kinds (blockIdx.x order: all inverse CTAs first, so that a tile CTA that waits for an inverse can never keep
+//   that inverse's CTA from being scheduled):
+//     inverse  one CTA per item: in-place Gauss-Jordan inversion of V1 (r x r) with partial pivoting, in shared memory
+//              when r <= 158, else in the item's L2-resident scratch; publishes inv + the pivot ratio, then a flag;
+//     C tile   64 columns of C = inv . V2 (waits for the item's flag);
+//     B tile   64 rows of B = (U_r * S_r) . V1 (independent of the inverse).
+//   Round 1 issued 2 + 4 r launches per matrix (514 for one rank-128 factor; ~5e5 for a 2-factor rank sweep).
 // ------------------------------------------------------------------------------------------------
-__global__ void rf_init(const float* __restrict__ V, int ldv, int r, int n, double* M) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)r * n; idx += stride) {
-    const int i = idx / n, c = idx - (size_t)i * n;
-    M[idx] = (double)V[(size_t)i * ldv + c];
-  }
-}
+constexpr int kRfThreads = 256;
+constexpr int kRfTile = 64;
+constexpr int kRfSmemRank = 158;   // r*r doubles + bookkeeping <= 200 KB
 
-// B[i][c] = sum_k U[i][k] S[k] V[k][c], c < r   (uses the ORIGINAL V, before elimination)
-__global__ void rf_make_B(const float* __restrict__ Ur, int ldu, const float* __restrict__ Sr, const float* __restrict__ V, int ldv,
-                          int m, int r, float* B) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)m * r; idx += stride) {
-    const int i = idx / r, c = idx - (size_t)i * r;
-    double acc = 0.0;
-    for (int k = 0; k < r; ++k) acc += ((double)Ur[(size_t)i * ldu + k] * (double)Sr[k]) * (double)V[(size_t)k * ldv + c];
-    B[idx] = (float)acc;
-  }
-}
-
-struct RfCtl {
-  int pivot_row;
-  int pad;
-  double pivot_val;
-  double min_abs, max_abs;
+struct RfItem {   // device copy of svdlstm_reduce_item + scratch
+  const float* U;
+  const float* S;
+  const float* V;
+  float* B;
+  float* C;
+  float* pivot_ratio;
+  double* inv;        // r x r
+  unsigned int* flag;
+  int ldu, ldv, m, r, n;
+};
+struct RfTile {
+  int item;
+  int kind;   // 1: C tile (first column c0), 2: B tile (first row c0)
+  int c0;
 };
 
-__global__ void __launch_bounds__(256) rf_find_pivot(const double* M, int r, int n, int step, RfCtl* ctl) {
-  __shared__ double sv[256];
-  __shared__ int si[256];
-  double best = -1.0;
-  int bi = step;
-  for (int i = step + threadIdx.x; i < r; i += 256) {
-    const double v = fabs(M[(size_t)i * n + step]);
-    if (v > best) { best = v; bi = i; }
+__device__ void rf_invert(const RfItem& it, double* A /* r x r, shared or global */, int* perm /* r, shared */) {
+  const int r = it.r, tid = threadIdx.x;
+  __shared__ double s_val[kRfThreads / 32];
+  __shared__ int s_idx[kRfThreads / 32];
+  __shared__ double s_piv, s_min, s_max;
+  __shared__ int s_prow;
+  for (int idx = tid; idx < r * r; idx += kRfThreads) {
+    const int i = idx / r, c = idx - i * r;
+    A[idx] = (double)it.V[(size_t)i * it.ldv + c];
   }
-  sv[threadIdx.x] = best;
-  si[threadIdx.x] = bi;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      const double o = sv[threadIdx.x + s];
-      const int oi = si[threadIdx.x + s];
-      if (o > sv[threadIdx.x] || (o == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = o; si[threadIdx.x] = oi; }
+  for (int k = 0; k < r; ++k) {
+    // ---- pivot: largest |A[i][k]|, i >= k (ties: smallest row) ----
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < r; i += kRfThreads) {
+      const double v = fabs(A[(size_t)i * r + k]);
+      if (v > best) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kRfThreads / 32; ++w)
+        if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+      s_prow = bi;
+      s_piv = A[(size_t)bi * r + k];
+      perm[k] = bi;
+      if (k == 0) { s_min = best; s_max = best; }
+      else { s_min = fmin(s_min, best); s_max = fmax(s_max, best); }
+    }
+    __syncthreads();
+    const int pr = s_prow;
+    const double inv_p = 1.0 / s_piv;
+    // ---- swap rows k <-> pr, scale the pivot row; its column-k entry becomes 1/pivot (the in-place inverse) ----
+    for (int c = tid; c < r; c += kRfThreads) {
+      const double a = A[(size_t)k * r + c], b2 = A[(size_t)pr * r + c];
+      A[(size_t)pr * r + c] = a;                                  // (pr == k: harmless)
+      A[(size_t)k * r + c] = (c == k ? 1.0 : b2) * inv_p;
+    }
+    __syncthreads();
+    // ---- eliminate column k from every other row ----
+    for (int i = tid >> 5; i < r; i += kRfThreads / 32) {
+      if (i == k) continue;
+      const double f = A[(size_t)i * r + k];
+      __syncwarp();
+      if (f != 0.0)
+        for (int c = tid & 31; c < r; c += 32) {
+          const double pk = A[(size_t)k * r + c];
+          A[(size_t)i * r + c] = (c == k ? 0.0 : A[(size_t)i * r + c]) - f * pk;
+        }
+      __syncwarp();
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    ctl->pivot_row = si[0];
-    ctl->pivot_val = M[(size_t)si[0] * n + step];
-    const double a = sv[0];
-    if (step == 0) { ctl->min_abs = a; ctl->max_abs = a; }
-    else { ctl->min_abs = fmin(ctl->min_abs, a); ctl->max_abs = fmax(ctl->max_abs, a); }
+  // ---- undo the row interchanges as column interchanges, last first ----
+  for (int k = r - 1; k >= 0; --k) {
+    const int pr = perm[k];
+    if (pr != k)
+      for (int i = tid; i < r; i += kRfThreads) {
+        const double a = A[(size_t)i * r + k];
+        A[(size_t)i * r + k] = A[(size_t)i * r + pr];
+        A[(size_t)i * r + pr] = a;
+      }
+    __syncthreads();
+  }
+  if (A != it.inv)
+    for (int idx = tid; idx < r * r; idx += kRfThreads) it.inv[idx] = A[idx];
+  if (tid == 0 && it.pivot_ratio) *it.pivot_ratio = (float)(s_max > 0 ? s_min / s_max : 0.0);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicExch(it.flag, 1u);
   }
 }
 
-// swap rows step<->pivot, scale pivot row, stash multipliers: split in two launches to avoid races
-__global__ void rf_swap_scale(double* M, int r, int n, int step, const RfCtl* ctl, double* mult) {
-  const int pr = ctl->pivot_row;
-  const double inv = 1.0 / ctl->pivot_val;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < (size_t)n; c += stride) {
-    const double a = M[(size_t)step * n + c];
-    const double b = M[(size_t)pr * n + c];
-    M[(size_t)pr * n + c] = a;          // (pr == step: harmless)
-    M[(size_t)step * n + c] = b * inv;
+__global__ void __launch_bounds__(kRfThreads) rf_batched_kernel(const RfItem* __restrict__ items, int n_items, const RfTile* __restrict__ tiles) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < n_items) {
+    const RfItem it = items[blockIdx.x];
+    double* A = it.r <= kRfSmemRank ? reinterpret_cast<double*>(rf_smem) : it.inv;
+    int* perm = reinterpret_cast<int*>(rf_smem + (it.r <= kRfSmemRank ? sizeof(double) * it.r * it.r : 0));
+    rf_invert(it, A, perm);
+    return;
   }
-}
-__global__ void rf_stash_mult(const double* M, int r, int n, int step, double* mult) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < r) mult[i] = (i == step) ? 0.0 : M[(size_t)i * n + step];
-}
-__global__ void rf_eliminate(double* M, int r, int n, int step, const double* mult) {
-  const int i = blockIdx.y;
-  const double f = mult[i];
-  if (f == 0.0) return;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < (size_t)n; c += stride)
-    M[(size_t)i * n + c] -= f * M[(size_t)step * n + c];
-}
-__global__ void rf_write_C(const double* M, int r, int n, float* C, const RfCtl* ctl, float* pivot_ratio) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int nc = n - r;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)r * nc; idx += stride) {
-    const int i = idx / nc, c = idx - (size_t)i * nc;
-    C[idx] = (float)M[(size_t)i * n + r + c];
+  const RfTile tl = tiles[blockIdx.x - n_items];
+  const RfItem it = items[tl.item];
+  const int r = it.r;
+  float* tile = reinterpret_cast<float*>(rf_smem);
+  if (tl.kind == 2) {
+    // B rows [c0, c0+64): stage (U * S) rows, then thread = output column
+    const int rows = min(kRfTile, it.m - tl.c0);
+    for (int idx = tid; idx < rows * r; idx += kRfThreads) {
+      const int i = idx / r, k = idx - i * r;
+      tile[idx] = it.U[(size_t)(tl.c0 + i) * it.ldu + k] * it.S[k];
+    }
+    __syncthreads();
+    for (int c = tid; c < r; c += kRfThreads)
+      for (int i = 0; i < rows; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < r; ++k) acc += (double)tile[i * r + k] * (double)it.V[(size_t)k * it.ldv + c];
+        it.B[(size_t)(tl.c0 + i) * r + c] = (float)acc;
+      }
+    return;
   }
-  if (pivot_ratio && blockIdx.x == 0 && threadIdx.x == 0) *pivot_ratio = (float)(ctl->max_abs > 0 ? ctl->min_abs / ctl->max_abs : 0.0);
+  // C columns [c0, c0+64) of the n - r columns of V2
+  const int nc = it.n - r, cols = min(kRfTile, nc - tl.c0);
+  for (int idx = tid; idx < r * kRfTile; idx += kRfThreads) {
+    const int k = idx / kRfTile, c = idx - k * kRfTile;
+    tile[idx] = c < cols ? it.V[(size_t)k * it.ldv + r + tl.c0 + c] : 0.f;
+  }
+  if (tid == 0) {
+    const long long t0 = clock64();
+    while (atomicAdd(it.flag, 0u) == 0u)
+      if (clock64() - t0 > 20000000000LL) __trap();   // a protocol bug must surface as an error, never as a hang
+    __threadfence();
+  }
+  __syncthreads();
+  const int c = tid % kRfTile, g = tid / kRfTile;     // 4 row groups
+  if (c < cols)
+    for (int i = g; i < r; i += kRfThreads / kRfTile) {
+      const double* row = it.inv + (size_t)i * r;
+      double acc = 0.0;
+      for (int k = 0; k < r; ++k) acc += __ldcg(row + k) * (double)tile[k * kRfTile + c];
+      it.C[(size_t)i * nc + tl.c0 + c] = (float)acc;
+    }
 }
 
 }  // namespace
@@ -506,31 +581,59 @@ extern "C" int svdlstm_svd_jacobi_batched(const float* A, int batch, int m, int 
   return 0;
 }
 
+extern "C" int svdlstm_reduce_factors_batched(const svdlstm_reduce_item* items, int n_items, void* stream_) {
+  SVD_REQUIRE(items != nullptr && n_items >= 1, "svdlstm_reduce_factors_batched: null / empty item list");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::vector<RfItem> hit((size_t)n_items);
+  std::vector<RfTile> tiles;
+  size_t inv_doubles = 0;
+  int max_r = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const svdlstm_reduce_item& s = items[i];
+    SVD_REQUIRE(s.U_r && s.S_r && s.V_r && s.B, "svdlstm_reduce_factors: null argument (item %d)", i);
+    SVD_REQUIRE(s.m >= 1 && s.r >= 1 && s.n >= s.r, "svdlstm_reduce_factors: need m>=1, 1<=r<=n (m=%d r=%d n=%d, item %d)", s.m, s.r, s.n, i);
+    SVD_REQUIRE(s.C != nullptr || s.n == s.r, "svdlstm_reduce_factors: null C (item %d)", i);
+    SVD_REQUIRE(s.r <= 1024, "svdlstm_reduce_factors: rank %d above 1024 (item %d)", s.r, i);
+    hit[i] = RfItem{s.U_r, s.S_r, s.V_r, s.B, s.C, s.pivot_ratio, nullptr, nullptr, s.ldu, s.ldv, s.m, s.r, s.n};
+    inv_doubles += (size_t)s.r * s.r;
+    max_r = s.r > max_r ? s.r : max_r;
+    for (int c0 = 0; c0 < s.n - s.r; c0 += kRfTile) tiles.push_back(RfTile{i, 1, c0});
+    for (int r0 = 0; r0 < s.m; r0 += kRfTile) tiles.push_back(RfTile{i, 2, r0});
+  }
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t o_inv = 0, o_flag = o_inv + up(sizeof(double) * inv_doubles), o_items = o_flag + up(sizeof(unsigned) * n_items),
+               o_tiles = o_items + up(sizeof(RfItem) * n_items), total = o_tiles + up(sizeof(RfTile) * (tiles.size() + 1));
+  uint8_t* scratch = nullptr;
+  SVD_CUDA_TRY(cudaMallocAsync(&scratch, total, stream));
+  struct Guard {
+    uint8_t* p;
+    cudaStream_t s;
+    ~Guard() { cudaFreeAsync(p, s); }
+  } guard{scratch, stream};
+  size_t off = 0;
+  for (int i = 0; i < n_items; ++i) {
+    hit[i].inv = reinterpret_cast<double*>(scratch + o_inv) + off;
+    hit[i].flag = reinterpret_cast<unsigned*>(scratch + o_flag) + i;
+    off += (size_t)hit[i].r * hit[i].r;
+  }
+  SVD_CUDA_TRY(cudaMemsetAsync(scratch + o_flag, 0, sizeof(unsigned) * n_items, stream));
+  // pageable sources: the runtime stages them before the call returns
+  SVD_CUDA_TRY(cudaMemcpyAsync(scratch + o_items, hit.data(), sizeof(RfItem) * n_items, cudaMemcpyHostToDevice, stream));
+  if (!tiles.empty()) SVD_CUDA_TRY(cudaMemcpyAsync(scratch + o_tiles, tiles.data(), sizeof(RfTile) * tiles.size(), cudaMemcpyHostToDevice, stream));
+  size_t smem = sizeof(float) * (size_t)kRfTile * max_r;                                          // tile CTAs
+  const int rs = max_r <= kRfSmemRank ? max_r : kRfSmemRank;
+  const size_t inv_smem = sizeof(double) * (size_t)rs * rs + sizeof(int) * (size_t)max_r + 16;    // inverse CTAs
+  if (inv_smem > smem) smem = inv_smem;
+  SVD_REQUIRE(smem <= 227 * 1024, "svdlstm_reduce_factors: rank %d needs %zu bytes of shared memory", max_r, smem);
+  SVD_CUDA_TRY(cudaFuncSetAttribute(rf_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rf_batched_kernel<<<(unsigned)(n_items + tiles.size()), kRfThreads, smem, stream>>>(reinterpret_cast<const RfItem*>(scratch + o_items), n_items,
+                                                                                       reinterpret_cast<const RfTile*>(scratch + o_tiles));
+  SVD_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int svdlstm_reduce_factors(const float* U_r, int ldu, const float* S_r, const float* V_r, int ldv, int m, int r, int n,
                                       float* B, float* C, float* pivot_ratio, void* stream_) {
-  SVD_REQUIRE(U_r && S_r && V_r && B, "svdlstm_reduce_factors: null argument");
-  SVD_REQUIRE(m >= 1 && r >= 1 && n >= r, "svdlstm_reduce_factors: need m>=1, 1<=r<=n (m=%d r=%d n=%d)", m, r, n);
-  SVD_REQUIRE(C != nullptr || n == r, "svdlstm_reduce_factors: null C");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  double *M = nullptr, *mult = nullptr;
-  RfCtl* ctl = nullptr;
-  SVD_CUDA_TRY(cudaMallocAsync(&M, sizeof(double) * r * n, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&mult, sizeof(double) * r, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&ctl, sizeof(RfCtl), stream));
-  const int gx = (int)(((size_t)r * n + 255) / 256 < 1184 ? ((size_t)r * n + 255) / 256 : 1184);
-  rf_init<<<gx, 256, 0, stream>>>(V_r, ldv, r, n, M);
-  rf_make_B<<<(int)(((size_t)m * r + 127) / 128 < 1184 ? ((size_t)m * r + 127) / 128 : 1184), 128, 0, stream>>>(U_r, ldu, S_r, V_r, ldv, m, r, B);
-  const int gc = (n + 255) / 256;
-  for (int step = 0; step < r; ++step) {
-    rf_find_pivot<<<1, 256, 0, stream>>>(M, r, n, step, ctl);
-    rf_swap_scale<<<gc, 256, 0, stream>>>(M, r, n, step, ctl, mult);
-    rf_stash_mult<<<(r + 127) / 128, 128, 0, stream>>>(M, r, n, step, mult);
-    rf_eliminate<<<dim3(gc, r), 256, 0, stream>>>(M, r, n, step, mult);
-  }
-  if (n > r || pivot_ratio) rf_write_C<<<gx, 256, 0, stream>>>(M, r, n, C, ctl, pivot_ratio);
-  SVD_CUDA_TRY(cudaGetLastError());
-  SVD_CUDA_TRY(cudaFreeAsync(M, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(mult, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(ctl, stream));
-  return 0;
+  svdlstm_reduce_item it{U_r, S_r, V_r, B, C, pivot_ratio, ldu, ldv, m, r, n};
+  return svdlstm_reduce_factors_batched(&it, 1, stream_);
 }

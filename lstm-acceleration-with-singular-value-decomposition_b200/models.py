@@ -59,24 +59,40 @@ def svd_batched(A, compute_uv=True, return_sweeps=False, check_convergence=True)
     return out
 
 
+def reduce_factors_batched(triples):
+    """[(U_r (m,r), S_r (r,), V_r (r,n)), ...] -> [(B (m,r), C (r,n-r), pivot_ratio (1,)), ...] from ONE launch of K2b:
+    B = (U_r * S_r) @ V1, C = inv(V1) @ V2 with V_r = [V1 | V2] (svd_classes_v3.py:622-626, 656-660)."""
+    import ctypes
+    items = (C.ReduceItem * len(triples))()
+    keep, outs = [], []
+    for i, (U_r, S_r, V_r) in enumerate(triples):
+        U_r = C.dev_tensor(U_r)
+        S_r = C.dev_tensor(S_r).reshape(-1)
+        V_r = C.dev_tensor(V_r)
+        m, r = int(U_r.shape[0]), int(U_r.shape[1])
+        n = int(V_r.shape[1])
+        if int(V_r.shape[0]) != r or int(S_r.numel()) != r:
+            raise ValueError("reduce_factors: inconsistent ranks")
+        if r == 0:
+            raise ValueError("reduce_factors: every singular value was pruned (rank 0)")
+        if U_r.stride(1) != 1 or V_r.stride(1) != 1:
+            U_r, V_r = U_r.contiguous(), V_r.contiguous()
+        dev = U_r.device
+        B = torch.empty((m, r), dtype=torch.float32, device=dev)
+        Cm = torch.empty((r, n - r), dtype=torch.float32, device=dev)
+        pr = torch.zeros(1, dtype=torch.float32, device=dev)
+        items[i] = C.ReduceItem(U_r.data_ptr(), S_r.data_ptr(), V_r.data_ptr(), B.data_ptr(), Cm.data_ptr() if Cm.numel() else None,
+                                pr.data_ptr(), U_r.stride(0), V_r.stride(0), m, r, n)
+        keep.append((U_r, S_r, V_r))
+        outs.append((B, Cm, pr))
+    C.check(C.lib().svdlstm_reduce_factors_batched(items, len(triples), C.cur_stream()))
+    C.add_launches(1)
+    return outs
+
+
 def reduce_factors(U_r, S_r, V_r, return_pivot_ratio=False):
     """B = (U_r * S_r) @ V1, C = inv(V1) @ V2 with V_r = [V1 | V2] (svd_classes_v3.py:622-626)."""
-    U_r = C.dev_tensor(U_r)
-    S_r = C.dev_tensor(S_r).reshape(-1)
-    V_r = C.dev_tensor(V_r)
-    m, r = int(U_r.shape[0]), int(U_r.shape[1])
-    n = int(V_r.shape[1])
-    if int(V_r.shape[0]) != r or int(S_r.numel()) != r:
-        raise ValueError("reduce_factors: inconsistent ranks")
-    if r == 0:
-        raise ValueError("reduce_factors: every singular value was pruned (rank 0)")
-    dev = U_r.device
-    B = torch.empty((m, r), dtype=torch.float32, device=dev)
-    Cm = torch.empty((r, n - r), dtype=torch.float32, device=dev)
-    pr = torch.zeros(1, dtype=torch.float32, device=dev)
-    C.check(C.lib().svdlstm_reduce_factors(C.ptr(U_r), U_r.stride(0), C.ptr(S_r), C.ptr(V_r), V_r.stride(0), m, r, n,
-                                           C.ptr(B), C.ptr(Cm) if Cm.numel() else None, C.ptr(pr), C.cur_stream()))
-    C.add_launches(2 + 4 * r)
+    B, Cm, pr = reduce_factors_batched([(U_r, S_r, V_r)])[0]
     if return_pivot_ratio:
         return B, Cm, pr
     return B, Cm
@@ -484,32 +500,29 @@ def make_LSTM_singular_model(model, hoyer=None, orthogonal=None, merged_kernel=T
     return smodel
 
 
-def _reduce_one(U, S, V, cutoff, rank, use_abs=False, where=""):
-    """svd_classes_v3.py:618-627.  Threshold keep = S > cutoff (drops negative sigma regardless of
+def _select_factors(U, S, V, cutoff, rank, use_abs=False, where=""):
+    """svd_classes_v3.py:618-621.  Threshold keep = S > cutoff (drops negative sigma regardless of
     magnitude, as the reference does; ``use_abs`` opts into |S| > cutoff) or explicit top-``rank``."""
     S = S.reshape(-1)
     if rank is not None:
-        keep_idx = torch.arange(min(int(rank), S.numel()), device=S.device)
-    else:
-        s_host = S.cpu()
-        keep = (s_host.abs() if use_abs else s_host) > cutoff
-        keep_idx = torch.nonzero(keep).reshape(-1).to(S.device)
+        r = min(int(rank), S.numel())
+        if r < 1:
+            raise ValueError("make_LSTM_reduced_model: rank must be >= 1")
+        return U[:, :r], S[:r], V[:r]                 # leading factors: strided views, no gather
+    s_host = S.cpu()
+    keep = (s_host.abs() if use_abs else s_host) > cutoff
+    keep_idx = torch.nonzero(keep).reshape(-1).to(S.device)
     if keep_idx.numel() == 0:
         raise ValueError("make_LSTM_reduced_model: cutoff removed every singular value of %s" % where)
-    U_r = U.index_select(1, keep_idx).contiguous()
-    V_r = V.index_select(0, keep_idx).contiguous()
-    S_r = S.index_select(0, keep_idx).contiguous()
-    B, Cm, pr = reduce_factors(U_r, S_r, V_r, return_pivot_ratio=True)
-    return [B, Cm], pr
+    return U.index_select(1, keep_idx).contiguous(), S.index_select(0, keep_idx).contiguous(), V.index_select(0, keep_idx).contiguous()
 
 
 def make_LSTM_reduced_model(model, cutoff=.05, merged_kernel=True, *, rank=None, use_abs=False, check_condition=True):
     """svd_classes_v3.py:604-676.  From a model of SingularLSTMCells build the 2-factor model.
     ``rank=`` (keyword-only extension) keeps the top-``rank`` factors of every matrix instead of
-    thresholding.  Output layers always return sequences + TimeDistributed(Dense) (:630,:665,:670)."""
-    rmodel = Sequential()
-    rmodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
-    pivots = []
+    thresholding.  Output layers always return sequences + TimeDistributed(Dense) (:630,:665,:670).
+    Every (B, C) pair of the model comes out of ONE K2b launch."""
+    names, triples, plan = [], [], []
     for li, layer in enumerate(model.layers[:-1]):
         cell = layer.cell
         if not isinstance(cell, SingularLSTMCell):
@@ -517,31 +530,38 @@ def make_LSTM_reduced_model(model, cutoff=.05, merged_kernel=True, *, rank=None,
         if bool(cell.merged_kernel) != bool(merged_kernel):
             raise ValueError("merged_kernel=%s but layer %d holds a %s SingularLSTMCell"
                              % (merged_kernel, li, "merged" if cell.merged_kernel else "split"))
-        units = layer.units
         w_s, u_s, w_l, w_r, u_l, u_r, b = [v.tensor for v in cell.weights]
         if merged_kernel:
-            wu = []
-            for nm, mat in (("W", [w_l, w_s, w_r]), ("U", [u_l, u_s, u_r])):
-                f, pr = _reduce_one(mat[0], mat[1], mat[2], cutoff, rank, use_abs, "layer %d %s" % (li, nm))
-                wu.append(f)
-                pivots.append(("layer %d %s" % (li, nm), pr))
-            rcell = ReducedLSTMCell(units, w=wu[0], u=wu[1], b=b)
+            for nm, mat in (("W", (w_l, w_s, w_r)), ("U", (u_l, u_s, u_r))):
+                names.append("layer %d %s" % (li, nm))
+                triples.append(_select_factors(mat[0], mat[1], mat[2], cutoff, rank, use_abs, names[-1]))
         else:
-            w, u = [], []
             w_l4, w_s4, w_r4 = (torch.chunk(a, 4, dim=1) for a in (w_l, w_s, w_r))
             u_l4, u_s4, u_r4 = (torch.chunk(a, 4, dim=1) for a in (u_l, u_s, u_r))
             for g in range(4):
-                fw, pw = _reduce_one(w_l4[g], w_s4[g], w_r4[g], cutoff, rank, use_abs, "layer %d W gate %d" % (li, g))
-                fu, pu = _reduce_one(u_l4[g], u_s4[g], u_r4[g], cutoff, rank, use_abs, "layer %d U gate %d" % (li, g))
-                w.append(fw); u.append(fu)
-                pivots += [("layer %d W gate %d" % (li, g), pw), ("layer %d U gate %d" % (li, g), pu)]
+                names.append("layer %d W gate %d" % (li, g))
+                triples.append(_select_factors(w_l4[g], w_s4[g], w_r4[g], cutoff, rank, use_abs, names[-1]))
+                names.append("layer %d U gate %d" % (li, g))
+                triples.append(_select_factors(u_l4[g], u_s4[g], u_r4[g], cutoff, rank, use_abs, names[-1]))
+        plan.append((layer.units, b))
+    outs = reduce_factors_batched(triples)
+    rmodel = Sequential()
+    rmodel.add(InputLayer(input_shape=[None, model.input_shape[-1]]))
+    per = 2 if merged_kernel else 8
+    for li, (units, b) in enumerate(plan):
+        o = outs[li * per:(li + 1) * per]
+        if merged_kernel:
+            rcell = ReducedLSTMCell(units, w=[o[0][0], o[0][1]], u=[o[1][0], o[1][1]], b=b)
+        else:
+            w = [[o[2 * g][0], o[2 * g][1]] for g in range(4)]
+            u = [[o[2 * g + 1][0], o[2 * g + 1][1]] for g in range(4)]
             rcell = ReducedLSTMCell(units, w=w, u=u, b=b, merged_kernel=False)
         rmodel.add(SingularLSTM(units, cell=rcell, return_sequences=True))
     _copy_dense_top(model, rmodel, True)
     rmodel.build()
-    if check_condition and pivots:
-        ratios = torch.cat([p for _, p in pivots]).cpu().numpy()
-        rmodel.pivot_ratios = {name: float(r) for (name, _), r in zip(pivots, ratios)}
+    if check_condition and outs:
+        ratios = torch.cat([o[2] for o in outs]).cpu().numpy()
+        rmodel.pivot_ratios = {name: float(r) for name, r in zip(names, ratios)}
         bad = [n for n, r in rmodel.pivot_ratios.items() if not (r > 1e-6)]
         if bad:
             warnings.warn("make_LSTM_reduced_model: V1 is (near-)singular for %s; the reference calls "
