@@ -135,6 +135,13 @@ typedef struct {
 } svdlstm_reduce_item;
 int svdlstm_reduce_factors_batched(const svdlstm_reduce_item* items, int n_items, void* stream);
 
+/* out (m,n; row stride ldo) = (A (m,k; lda) * diag(scale (k) or NULL)) . B (k,n; ldb) + bias (n) or NULL.
+ * The dense products of the path outside the recurrent kernels: the rank-truncated reconstruction
+ * A_r = (U * s_r) V with k = the kept rank (old_versions/svd_classes.py:9-12, 210-217) and a stand-alone
+ * Dense / TimeDistributed(Dense) layer (svd_classes_v3.py:532-539).                                     */
+int svdlstm_scaled_matmul(const float* A, int lda, const float* scale, const float* B, int ldb, const float* bias,
+                          int m, int k, int n, float* out, int ldo, void* stream);
+
 /* ---- fused Hoyer + orthogonality penalties ----------------------------------------------------
  * One launch evaluates every regulariser of a model: HoyerRegularizer.__call__
  * (svd_classes_v3.py:460-462) on sigma vectors and keras OrthogonalRegularizer(mode='rows')

@@ -34,7 +34,7 @@ EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",
     "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
     "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_svd_jacobi_batched",
-    "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
+    "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_scaled_matmul", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
     "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
     "svdlstm_stream_state", "svdlstm_stream_launches", "svdlstm_stream_close",
 ]
@@ -93,6 +93,8 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_reduce_factors.restype = ci
     L.svdlstm_reduce_factors_batched.argtypes = [ctypes.POINTER(ReduceItem), ci, vp]
     L.svdlstm_reduce_factors_batched.restype = ci
+    L.svdlstm_scaled_matmul.argtypes = [vp, ci, vp, vp, ci, vp, ci, ci, ci, vp, ci, vp]
+    L.svdlstm_scaled_matmul.restype = ci
     L.svdlstm_penalties.argtypes = [ctypes.POINTER(PenaltyItem), ci, vp, vp]
     L.svdlstm_penalties.restype = ci
     L.svdlstm_sweep_sse.argtypes = [vp, vp, ci, ctypes.c_int64, vp, vp]
@@ -164,6 +166,25 @@ def ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 
 def int_array(vals: Sequence[int]):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def scaled_matmul(A: torch.Tensor, B: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                  k: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = (A[:, :k] * scale[:k]) @ B[:k] + bias on device (K5; float32, row strides honoured, last dim contiguous)."""
+    if A.stride(-1) != 1:
+        A = A.contiguous()
+    if B.stride(-1) != 1:
+        B = B.contiguous()
+    m, n = int(A.shape[0]), int(B.shape[1])
+    k = int(A.shape[1]) if k is None else int(k)
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    if out.stride(-1) != 1:
+        raise ValueError("scaled_matmul: out must have a contiguous last dimension")
+    check(lib().svdlstm_scaled_matmul(ptr(A), A.stride(0), ptr(scale), ptr(B), B.stride(0), ptr(bias), m, k, n, ptr(out), out.stride(0),
+                                      cur_stream()))
+    add_launches(1)
+    return out
 
 
 def add_launches(n: int) -> None:

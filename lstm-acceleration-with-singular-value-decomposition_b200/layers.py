@@ -693,7 +693,7 @@ class LSTM(SingularLSTM):
 
 class Dense:
     """keras.layers.Dense (linear).  Inside a Sequential the Dense top is fused into the recurrent
-    kernel; called on its own it is a plain library GEMM."""
+    kernel; called on its own it runs through K5 (svdlstm_scaled_matmul)."""
 
     def __init__(self, units, name=None):
         self.units = int(units)
@@ -736,7 +736,9 @@ class Dense:
         x = C.dev_tensor(inputs)
         if not self.built:
             raise ValueError("Dense has no weights yet")
-        return x @ self.kernel.tensor + self.bias.tensor
+        lead = tuple(x.shape[:-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        return C.scaled_matmul(x2, self.kernel.tensor, bias=self.bias.tensor).reshape(lead + (self.units,))
 
     __call__ = call
 

@@ -6,7 +6,7 @@
     set_model_matrix_rank(model, index, rank)   :210-217  re-SVD one gate block, zero trailing sigma
     LSTM_wrapper(model, scaler).iterate_reduce_model(X, y, ...)   :139-182 / old_versions/svd_acceleration.py:61-88
                                        greedy "drop the globally smallest sigma, predict, RMSE" sweep
-All SVDs run through K2 (svd_batched); the tiny dense products use library GEMMs (plumbing).
+All SVDs run through K2 (svd_batched); the reconstruction (U * s_r) V runs through K5 (scaled_matmul).
 """
 from __future__ import annotations
 
@@ -20,9 +20,8 @@ from .models import reduce_factors, svd_batched
 def reduce_matrix_rank(a, rank):
     A = C.dev_tensor(a)
     u, s, v = svd_batched(A)
-    s = s.clone()
-    s[int(rank):] = 0
-    return ((u * s) @ v).cpu().numpy()
+    r = max(0, min(int(rank), int(s.numel())))
+    return C.scaled_matmul(u, v, scale=s.reshape(-1), k=r).cpu().numpy()      # (U * s_r) V on device (K5)
 
 
 def reduce_two_step(a, rank):
@@ -58,9 +57,8 @@ def set_model_matrix_rank(model, index, rank):
     var = (layer.cell.kernel, layer.cell.recurrent_kernel)[index[1]]
     blk = var.tensor[:, H * index[2]:H * (index[2] + 1)]
     u, s, v = svd_batched(blk.contiguous())
-    s = s.clone()
-    s[int(rank):] = 0
-    blk.copy_((u * s) @ v)
+    r = max(0, min(int(rank), int(s.numel())))
+    C.scaled_matmul(u, v, scale=s.reshape(-1), k=r, out=blk)                   # written in place into the gate block (strided view)
     layer.cell.rebind()
     return model
 

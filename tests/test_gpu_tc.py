@@ -79,9 +79,15 @@ def test_tc_reduced_form_and_rmse_delta(oracle):
     layers, dense = svdlstm.load_model_weights_npz(GOLDEN_W)
     dsm = svdlstm.make_LSTM_singular_model(svdlstm.full_model_from_weights(layers, dense), merged_kernel=True, return_sequences=True)
     xd = np.random.default_rng(4).standard_normal((40, 60, 16)).astype(np.float32)
+    # (trained weights: |W| up to ~3 and saturating gates through 3 layers -- FP16 operand rounding shows as ~2.5e-3 of the output
+    #  scale on this model in every form, full / 3-factor / 2-factor alike; bar 5e-3, RMSE delta reported by bench.py)
     for r in (15, 8, 3):
         md = svdlstm.make_LSTM_reduced_model(dsm, rank=r)
-        _check(md.predict(xd, engine="tc"), oracle_twin(oracle, md).predict(xd), "tc DROPBEAR 2-factor r=%d" % r)
+        _check(md.predict(xd, engine="tc"), oracle_twin(oracle, md).predict(xd), "tc DROPBEAR 2-factor r=%d" % r, rel=5e-3)
+        m3 = svdlstm.truncate_singular_model(dsm, r)
+        e2 = np.abs(md.predict(xd, engine="tc") - oracle_twin(oracle, md).predict(xd)).max()
+        e3 = np.abs(m3.predict(xd, engine="tc") - oracle_twin(oracle, m3).predict(xd)).max()
+        assert e2 < 3.0 * e3 + 1e-3, "2-factor form is not at 3-factor accuracy: %.3e vs %.3e" % (e2, e3)
 
 
 def test_tc_batch_properties_full_tile_count():
@@ -299,11 +305,11 @@ def test_tc_dropbear_model_padded_units(oracle):
     sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
     x = np.random.default_rng(21).standard_normal((70, 200, 16)).astype(np.float32)
     y_or = oracle_twin(oracle, full).predict(x)
-    _check(full.predict(x, engine="tc"), y_or, "tc DROPBEAR full")
+    _check(full.predict(x, engine="tc"), y_or, "tc DROPBEAR full", rel=5e-3)
     assert full.last_engine() == svdlstm.ENGINE_TC
     for r in (15, 10, 4, 1):
         m = svdlstm.truncate_singular_model(sm, r)
-        _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc DROPBEAR 3F r=%d" % r)
+        _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "tc DROPBEAR 3F r=%d" % r, rel=5e-3)
     # chunked == unchunked with the state carried (state arrays are (B, 15): the true units)
     m = svdlstm.truncate_singular_model(sm, 8)
     xd = torch.from_numpy(x).cuda()
