@@ -164,6 +164,30 @@ int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items, double* ou
 int svdlstm_sweep_sse(const float* pred, const float* target, int n_ranks, int64_t n, double* sse,
                       void* stream);
 
+/* ---- training step (Hoyer fine-tune) -------------------------------------------------------------
+ * Replaces smodel.compile(loss="mse", optimizer="adam") + smodel.fit(...) of the reference driver
+ * (svd_acceleration_v3.py:111-128) for models of SingularLSTMCells + Dense top.  Trainable tensors as in the
+ * reference: sigma_w / sigma_u always (svd_classes_v3.py:40,47), the factor matrices and the bias only where
+ * train_uv[layer] != 0 (:49-56,:102-112), the Dense top always.  The flat parameter / gradient vector is laid
+ * out per layer as [sigma_w | sigma_u | w_left | w_right | u_left | u_right | bias] (get_weights() order, :113),
+ * then [dense kernel | dense bias]; svdlstm_trainer_layout returns the 7 L + 3 start offsets.
+ *   gradients     forward with cache + back-propagation through time of the mean-squared error of one mini-batch
+ *                 (x (B,T,D); y_true (B,T,n) with return_sequences else (B,n); device pointers).  grad_out NULL =
+ *                 loss only (validation).  Deterministic: per-sequence partial gradients, summed in batch order.
+ *   regularizers  adds d penalty / d w and the penalty itself for HoyerRegularizer (kind 1, :455-462) and
+ *                 OrthogonalRegularizer(mode='rows') (kind 2, call sites :514,:573); tensor_index = 7 l + {0..5}.
+ *   adam          one Keras-Adam update IN PLACE in the caller's weight tensors.                                */
+typedef struct svdlstm_trainer_s* svdlstm_trainer;
+int svdlstm_trainer_create(svdlstm_handle h, const int* train_uv, svdlstm_trainer* out);
+void svdlstm_trainer_destroy(svdlstm_trainer t);
+int64_t svdlstm_trainer_num_params(svdlstm_trainer t);
+int svdlstm_trainer_layout(svdlstm_trainer t, int64_t* offsets);
+int svdlstm_trainer_gradients(svdlstm_trainer t, const float* x, const float* y_true, int B, int T, int return_sequences,
+                              float* grad_out, float* loss_out, void* stream);
+int svdlstm_trainer_regularizers(svdlstm_trainer t, const int* tensor_index, const int* kind, const float* coef, int n,
+                                 float* grad, float* loss, void* stream);
+int svdlstm_trainer_adam(svdlstm_trainer t, const float* grad, float lr, float beta1, float beta2, float eps, void* stream);
+
 /* ---- real-time batch-1 stream -------------------------------------------------------------------
  * The reference's deployment setting: a stateful LSTM (svd_classes_v3.py:421-426) fed one frame every
  * 400-500 us (train_full_model_v4.py:14-16), i.e. `model.predict` called per sample

@@ -18,6 +18,7 @@ from .metrics import (count_weights, full_weight_count, reduced_merged_weight_co
 from .rank_reduce import (LSTM_wrapper, get_model_singular_values, reduce_matrix_rank, reduce_two_step,
                           set_model_matrix_rank, sorted_sigma_indices)
 from .data import StandardScaler, preprocess, split_train_random
+from .training import History, Trainer
 from .sweep import build_rank_models, rank_sweep, shard_bounds
 from .weights_io import (load_model_weights_csv, load_model_weights_json, load_model_weights_npz, load_model_weights_zip,
                          save_model_weights_csv, save_model_weights_json, synthetic_layers)

@@ -37,6 +37,8 @@ EXPORTS = [
     "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_scaled_matmul", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
     "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
     "svdlstm_stream_state", "svdlstm_stream_launches", "svdlstm_stream_close",
+    "svdlstm_trainer_create", "svdlstm_trainer_destroy", "svdlstm_trainer_num_params", "svdlstm_trainer_layout",
+    "svdlstm_trainer_gradients", "svdlstm_trainer_regularizers", "svdlstm_trainer_adam",
 ]
 
 
@@ -113,6 +115,21 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_stream_launches.restype = ci
     L.svdlstm_stream_close.argtypes = [vp]
     L.svdlstm_stream_close.restype = ci
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    L.svdlstm_trainer_create.argtypes = [vp, cip, ctypes.POINTER(vp)]
+    L.svdlstm_trainer_create.restype = ci
+    L.svdlstm_trainer_destroy.argtypes = [vp]
+    L.svdlstm_trainer_destroy.restype = None
+    L.svdlstm_trainer_num_params.argtypes = [vp]
+    L.svdlstm_trainer_num_params.restype = ctypes.c_int64
+    L.svdlstm_trainer_layout.argtypes = [vp, i64p]
+    L.svdlstm_trainer_layout.restype = ci
+    L.svdlstm_trainer_gradients.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
+    L.svdlstm_trainer_gradients.restype = ci
+    L.svdlstm_trainer_regularizers.argtypes = [vp, cip, cip, ctypes.POINTER(ctypes.c_float), ci, vp, vp, vp]
+    L.svdlstm_trainer_regularizers.restype = ci
+    L.svdlstm_trainer_adam.argtypes = [vp, vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp]
+    L.svdlstm_trainer_adam.restype = ci
     L.svdlstm_last_error.argtypes = []
     L.svdlstm_last_error.restype = ctypes.c_char_p
     L.svdlstm_version.argtypes = []

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsvdlstm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["abi.cu", "stream.cu", "k1_general.cu", "k1_wavefront.cu", "k1b_tc.cu", "k2_svd.cu", "k3_penalties.cu", "k5_matmul.cu"]
+SOURCES = ["abi.cu", "stream.cu", "k1_general.cu", "k1_wavefront.cu", "k1b_tc.cu", "k2_svd.cu", "k3_penalties.cu", "k5_matmul.cu", "k6_train.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if os.environ.get("SVDLSTM_TC_TIMELINE_BUILD"):   # debug build (separate .so): per-step clock64 stamps inside the tensor-core kernel

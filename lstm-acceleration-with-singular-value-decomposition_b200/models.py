@@ -293,6 +293,46 @@ class Sequential:
         st["y_done"][k].record(main)
         return _Pending(st["y_done"][k], None, st["y_host"][k])
 
+    # ---- training (svd_acceleration_v3.py:111-128) ------------------------------------------------------------------------
+    def compile(self, loss="mse", optimizer="adam", learning_rate=None, **kwargs):
+        """keras ``model.compile``: only what the reference uses -- loss "mse", optimizer "adam" (Keras defaults:
+        learning_rate 1e-3, beta_1 0.9, beta_2 0.999, epsilon 1e-7; ``optimizer`` may also be a dict of those)."""
+        from .training import Trainer
+        if loss not in ("mse", "mean_squared_error"):
+            raise NotImplementedError("loss=%r: the reference trains with 'mse'" % (loss,))
+        hp = {}
+        if isinstance(optimizer, dict):
+            hp = {k: v for k, v in optimizer.items() if k in ("learning_rate", "beta_1", "beta_2", "epsilon")}
+        elif str(optimizer).lower() != "adam":
+            raise NotImplementedError("optimizer=%r: the reference trains with 'adam'" % (optimizer,))
+        if learning_rate is not None:
+            hp["learning_rate"] = learning_rate
+        self.build()
+        self._trainer = Trainer(self, **hp)
+
+    def fit(self, x=None, y=None, batch_size=32, epochs=1, verbose=0, validation_data=None, shuffle=True, **kwargs):
+        from .training import fit
+        return fit(self, x, y, batch_size=batch_size, epochs=epochs, validation_data=validation_data, shuffle=shuffle, verbose=verbose,
+                   seed=kwargs.get("seed"), steps_per_epoch=kwargs.get("steps_per_epoch"))
+
+    def evaluate(self, x=None, y=None, batch_size=256, verbose=0):
+        from .training import evaluate
+        return evaluate(self, x, y, batch_size=batch_size)
+
+    def train_on_batch(self, x, y):
+        if getattr(self, "_trainer", None) is None:
+            raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer, loss)`.")
+        self._trainer.loss_and_grad(x, y)
+        self._trainer.apply()
+        return float(self._trainer.loss[0])
+
+    def gradients(self, x, y, regularizers=True):
+        """(total loss, [d loss / d w for w in get_weights()]) of one batch -- the quantity `fit` feeds to Adam."""
+        if getattr(self, "_trainer", None) is None:
+            raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer, loss)`.")
+        self._trainer.loss_and_grad(x, y, with_regs=regularizers)
+        return float(self._trainer.loss[0]), self._trainer.grads_as_weights()
+
     def open_stream(self, idle_ms=50):
         """Real-time batch-1 service (the reference's deployment: ``model.predict`` per 16-sample frame every 400-500 us on a
         stateful LSTM; svd_classes_v3.py:421-426, train_full_model_v4.py:14-16).  Launches ONE persistent kernel and returns a

@@ -182,3 +182,16 @@ def test_greedy_sigma_sweep_oracle(oracle, dropbear_weights):
     assert rmse[0] < 1e-12 and rmse[-1] > rmse[1] > 0
     assert list(w[:3]) == [0.0, 2 * 15 - 2 * 14 - 1, (2 * 15 - 2 * 14 - 1) * 2] or w[2] in (2.0, 4.0)
     assert np.all(np.diff(w) > 0)
+
+
+def test_torch_ref_matches_numpy_oracle(oracle, dropbear_weights):
+    """The torch-autograd checker of the training step (oracle/svdlstm_torch_ref.py) is itself pinned: its forward pass equals
+    the numpy oracle's on the shipped model, merged and split."""
+    import svdlstm_torch_ref as R
+    layers, dense = dropbear_weights
+    ofull = oracle.model_from_weights(layers, dense, dtype=np.float64)
+    x = np.random.default_rng(3).standard_normal((3, 12, 16))
+    for merged in (True, False):
+        osm = oracle.make_LSTM_singular_model(ofull, merged_kernel=merged, return_sequences=True, svd_dtype=np.float64)
+        tm = R.TorchSingularModel([c.get_weights() for c in osm.cells], osm.dense, [c.units for c in osm.cells], merged, True)
+        assert np.max(np.abs(tm.forward(x).detach().numpy() - osm.predict(x))) < 1e-12
