@@ -103,17 +103,24 @@ def main():
                           ("tc_layer_rank32_%s" % R, "lstm_tc", "tc_pipe_rank32_%s.txt" % R), ("tc_pipe_c5_%s" % R, "lstm_tc", "tc_pipe_c5_%s.txt" % R),
                           ("b1_wavefront_%s" % R, "lstm_wavefront", "b1_wavefront_%s.txt" % R)]:
         rp = os.path.join(O, rep + ".ncu-rep")
-        if not os.path.exists(rp):
+        pre = os.path.join(O, rep + ".txt")          # condensed on the GPU box by profile_round.sh (the reports exceed gpurun's 64 MiB)
+        if os.path.exists(pre) and os.path.getsize(pre) > 200:
+            txt = open(pre).read()
+        elif os.path.exists(rp):
+            txt = subprocess.run([sys.executable, summ, rp, pat], capture_output=True, text=True).stdout
+        else:
             continue
-        txt = subprocess.run([sys.executable, summ, rp, pat], capture_output=True, text=True).stdout
+        hot = os.path.join(O, rep + ".hot.txt")
+        if os.path.exists(hot) and os.path.getsize(hot) > 50:
+            txt += "\n## hottest source lines (ncu --page source: warp stall samples per line, needs -lineinfo)\n" + open(hot).read()
         open(os.path.join(P, dst), "w").write("# %s\n" % stamp + txt)
         m = re.search(r"rank(\d+)", rep)
         if m:
             for key, metric in (("tensor_pipe_active_pct_rank_%s", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                                 ("tensor_pipe_elapsed_pct_rank_%s", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")):
-                v = raw_metric(rp, metric, pat)
-                if v is not None:
-                    traffic[key % m.group(1)] = v
+                mm = re.search(re.escape(metric) + r"\s+([0-9.]+)", txt)
+                if mm:
+                    traffic[key % m.group(1)] = float(mm.group(1))
     json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     # SASS opcode histogram of the shipped library
     lib = os.path.join(ROOT, "lstm-acceleration-with-singular-value-decomposition_b200", "libsvdlstm.so")
