@@ -18,6 +18,8 @@
 //
 // K4 is the device half of the RMSE of svd_acceleration_v3.py:187-190: per-rank sum of squared
 // errors, two-stage fixed-order float64 reduction (independent of GPU count => sweep determinism).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -30,8 +32,61 @@ constexpr int kTile = 32;
 constexpr int kSplitF = 256;   // features per Gram CTA
 constexpr int kPartDoubles = kTile * kTile + 2 * kTile;   // one parked partial: the tile + both row-norm blocks
 
+// ---- kind 2: 128 x 128 Gram tiles on the tensor cores (tcgen05, kind::tf32, FP32 accumulation in TMEM) -----------------------
+// The Gram matrix of the large factors (w_right / u_right of H = 1024: 128 x 4096, u_left: 1024 x 128, ...) is a SYRK:
+// 2 n^2 m FLOP, 1.3 GFLOP for the C5 factor set -- round 1 did it in float64 on the CUDA cores (0.37 ms).  Here every 128 x 128
+// tile of Y Y^T is accumulated by tcgen05.mma over K chunks of 32 features with the 3xTF32 split y = hi + lo
+// (hi = tf32(y), lo = tf32(y - hi)):  hi hi^T + hi lo^T + lo hi^T  recovers FP32-level accuracy (~2^-21 per product) from
+// TF32 operands.  Operands are staged by the CTA's own loads (coalesced 64-byte row segments -> K-major SWIZZLE_NONE core
+// matrices, hi and lo planes), double-buffered against the MMAs; the same pass accumulates the row norms of both blocks.
+// Split-K over the features, per-tile ticket, fixed-order combination as for kind 1 (FP32 parts, float64 final sums).
+constexpr int kTcTile = 128;            // rows of both operand blocks (MMA M = N = 128)
+constexpr int kTcKc = 32;               // features per staged chunk (4 MMAs of K = 8 per product)
+constexpr int kTcSplitF = 512;          // features per tensor-core Gram CTA
+constexpr int kTcPartFloats = kTcTile * kTcTile + 2 * kTcTile;       // parked partial: tile + squared norms of both row blocks
+constexpr uint32_t kTcPlane = kTcTile * kTcKc * 4;                    // bytes of one operand plane (hi or lo) of one chunk: 16 KB
+constexpr uint32_t kTcBuf = 4 * kTcPlane;                             // A hi, A lo, B hi, B lo
+constexpr uint32_t kTcSmem = 2 * kTcBuf + 64;                         // two buffers + barriers
+
+__device__ __forceinline__ uint32_t k3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k3_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ bool k3_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!k3_mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must surface as an error, never as a hang
+}
+__device__ __forceinline__ uint32_t k3_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// K-major SWIZZLE_NONE operand plane [128 rows x 32 k] of 4-byte elements: core matrix = 8 rows x 16 bytes;
+//   elem(row, k) at (row / 8) * 1024 + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4        LBO = 128 (next core along K), SBO = 1024
+__device__ __forceinline__ uint64_t k3_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+  const uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14);     // bit 46: sm_100 descriptor version
+  return ((uint64_t)hi << 32) | lo;
+}
+constexpr uint32_t k3_idesc_tf32() {
+  return (1u << 4)                       // D format F32
+         | (2u << 7) | (2u << 10)        // A, B format TF32
+         | (0u << 15) | (0u << 16)       // both K-major
+         | ((uint32_t)(kTcTile >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+}
+__device__ __forceinline__ void k3_umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(k3_idesc_tf32()), "r"(accumulate)
+      : "memory");
+}
+
 struct Work {
-  int item, kind, a, b;
+  int item, kind, a, b;   // kind 0: L1/L2 chunk a;  1: CUDA-core 32 x 32 Gram tile (a, b);  2: tensor-core 128 x 128 Gram tile (a, b)
   int split, n_splits;   // this CTA's feature range [split * kSplitF, ...) of n_splits
   int slot;              // split tiles: index of the tile's ticket / scratch block
   int base;              // split tiles: work index that receives the tile's result
@@ -56,6 +111,207 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
   return t;  // valid in thread 0
 }
 
+
+// One 128 x 128 tile (bi = wk.a <= bj = wk.b) of Y Y^T over the feature range of this split, rows mode.  Returns (off, fro) in
+// thread 0 when this CTA completes the tile (finish = true), else parks its part.
+__device__ void gram_tile_tc(const ItemDev& it, const Work& wk, unsigned char* dsm, unsigned int* ticket, double* scratch, const int* scratch_off,
+                             double* red, double& r0, double& r1, bool& finish, int& out_slot) {
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_nrm[2][kTcTile];
+  __shared__ bool s_tile_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = it.rows, F = it.cols;
+  const int i0 = wk.a * kTcTile, j0 = wk.b * kTcTile;
+  const bool diag = wk.a == wk.b;
+  const int kbeg = wk.split * kTcSplitF;
+  const int kend = kbeg + kTcSplitF < F ? kbeg + kTcSplitF : F;
+  const int n_chunks = (kend - kbeg + kTcKc - 1) / kTcKc;
+  const uint32_t sbase = k3_smem_u32(dsm);
+  const uint32_t bar0 = sbase + 2 * kTcBuf;      // two mbarriers: "the MMAs that read buffer b have completed"
+  if (tid == 0) {
+    k3_mbar_init(bar0, 1);
+    k3_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(k3_smem_u32(&s_tmem)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+
+  // loader geometry: warp w stages row groups {w, w + 8} (8 rows each); lane = (row in group, k quarter); 2 k halves of 16
+  const int lrow = lane & 7, kq = lane >> 3;
+  const bool vec_ok = (it.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(it.data) & 15) == 0);
+  double nacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // [operand A/B][row group of this warp]
+  auto stage = [&](int chunk, uint32_t buf) {
+    const int k0 = kbeg + chunk * kTcKc;
+#pragma unroll
+    for (int op = 0; op < 2; ++op) {
+      if (op == 1 && diag) break;
+      const int rbase = op == 0 ? i0 : j0;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int rg = warp + 8 * g;
+        const int row = rbase + rg * 8 + lrow;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          const int k = k0 + kh * 16 + kq * 4;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (row < R) {
+            const float* src = it.data + (size_t)row * it.ld + k;
+            if (vec_ok && k + 3 < kend) {
+              const float4 q4 = __ldg(reinterpret_cast<const float4*>(src));
+              v[0] = q4.x; v[1] = q4.y; v[2] = q4.z; v[3] = q4.w;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (k + u < kend) v[u] = __ldg(src + u);
+            }
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            hi[u] = k3_tf32(v[u]);
+            lo[u] = k3_tf32(v[u] - __uint_as_float(hi[u]));
+            nacc[op][g] += (double)v[u] * (double)v[u];
+          }
+          const uint32_t off = (uint32_t)rg * 1024u + (uint32_t)(kh * 4 + kq) * 128u + (uint32_t)lrow * 16u;
+          const uint32_t ph = sbase + buf * kTcBuf + (uint32_t)(2 * op) * kTcPlane + off;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ph), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ph + kTcPlane), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+      }
+    }
+  };
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint32_t buf = (uint32_t)c & 1u;
+    if (c >= 2) k3_mbar_wait(bar0 + 8u * buf, (uint32_t)((c >> 1) - 1) & 1u);   // the MMAs of chunk c-2 no longer read this buffer
+    stage(c, buf);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (warp == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = sbase + buf * kTcBuf, a_lo = a_hi + kTcPlane;
+        const uint32_t b_hi = diag ? a_hi : a_hi + 2 * kTcPlane, b_lo = b_hi + kTcPlane;
+#pragma unroll
+        for (int ks = 0; ks < kTcKc / 8; ++ks) {     // K = 8 per MMA = two core matrices = 256 bytes along K
+          const uint32_t o = (uint32_t)ks * 256u;
+          k3_umma_tf32(tmem, k3_desc(a_hi + o), k3_desc(b_hi + o), (c > 0 || ks > 0) ? 1u : 0u);
+          k3_umma_tf32(tmem, k3_desc(a_hi + o), k3_desc(b_lo + o), 1u);
+          k3_umma_tf32(tmem, k3_desc(a_lo + o), k3_desc(b_hi + o), 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8u * buf) : "memory");
+      }
+      __syncwarp();
+    }
+  }
+  // all MMAs complete: the last commit of each buffer
+  {
+    const int last = n_chunks - 1;
+    k3_mbar_wait(bar0 + 8u * ((uint32_t)last & 1u), (uint32_t)(last >> 1) & 1u);
+    if (n_chunks > 1) k3_mbar_wait(bar0 + 8u * ((uint32_t)(last - 1) & 1u), (uint32_t)((last - 1) >> 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // squared row norms of this split: reduce over the 4 k quarters, lanes 0..7 hold 8 rows
+#pragma unroll
+  for (int op = 0; op < 2; ++op)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      double v = nacc[op][g];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) s_nrm[op][(warp + 8 * g) * 8 + lane] = (float)v;
+    }
+  __syncthreads();
+  if (diag && tid < kTcTile) s_nrm[1][tid] = s_nrm[0][tid];
+  __syncthreads();
+  // accumulator tile -> registers: thread = row (TMEM lane quarter = warp % 4), 64 of the 128 columns (half = warp / 4)
+  const int q = warp & 3, half = warp >> 2;
+  const int trow = q * 32 + lane;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t r[16];
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64 + j * 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[j * 16 + u] = __uint_as_float(r[u]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  finish = true;
+  if (wk.n_splits > 1) {
+    float* mine = reinterpret_cast<float*>(scratch + (size_t)scratch_off[wk.slot]) + (size_t)wk.split * kTcPartFloats;
+#pragma unroll
+    for (int u = 0; u < 64; ++u) mine[(size_t)trow * kTcTile + half * 64 + u] = acc[u];
+    if (tid < kTcTile) {
+      mine[kTcTile * kTcTile + tid] = s_nrm[0][tid];
+      mine[kTcTile * kTcTile + kTcTile + tid] = s_nrm[1][tid];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_tile_last = (atomicAdd(ticket + 1 + wk.slot, 1u) == (unsigned int)wk.n_splits - 1u);
+    __syncthreads();
+    finish = s_tile_last;
+    if (finish) {
+      __threadfence();
+      const volatile float* parts = reinterpret_cast<const volatile float*>(scratch + (size_t)scratch_off[wk.slot]);
+#pragma unroll
+      for (int u = 0; u < 64; ++u) acc[u] = 0.f;
+      float na = 0.f, nb = 0.f;
+      for (int sp = 0; sp < wk.n_splits; ++sp) {       // fixed order: bit-reproducible
+        const volatile float* pp = parts + (size_t)sp * kTcPartFloats;
+#pragma unroll
+        for (int u = 0; u < 64; ++u) acc[u] += pp[(size_t)trow * kTcTile + half * 64 + u];
+        if (tid < kTcTile) {
+          na += pp[kTcTile * kTcTile + tid];
+          nb += pp[kTcTile * kTcTile + kTcTile + tid];
+        }
+      }
+      __syncthreads();
+      if (tid < kTcTile) {
+        s_nrm[0][tid] = na;
+        s_nrm[1][tid] = nb;
+      }
+      __syncthreads();
+      out_slot = wk.base;
+    }
+  }
+  if (!finish) return;
+  double off = 0.0, fro = 0.0;
+  const double mult = diag ? 1.0 : 2.0;
+  const int gi = i0 + trow;
+  const double ni = sqrt(fmax((double)s_nrm[0][trow], 1e-12));
+  if (gi < R) {
+#pragma unroll
+    for (int u = 0; u < 64; ++u) {
+      const int cj = half * 64 + u, gj = j0 + cj;
+      if (gj < R) {
+        const double p = (double)acc[u];
+        if (gi != gj) {
+          off += fabs(p) / (ni * sqrt(fmax((double)s_nrm[1][cj], 1e-12)));
+          fro += p * p;
+        } else {
+          fro += (p - 1.0) * (p - 1.0);
+        }
+      }
+    }
+  }
+  r0 = block_sum_256(off * mult, red);
+  r1 = block_sum_256(fro * mult, red);
+}
+
 __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restrict__ items, int n_items, const Work* __restrict__ work,
                                                         int n_work, double* partial /*n_work x 2, zeroed*/, unsigned int* ticket /*[0] + per split tile, zeroed*/,
                                                         double* scratch /*per split tile: n_splits x kPartDoubles*/, const int* __restrict__ scratch_off,
@@ -71,7 +327,12 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
   const Work wk = work[blockIdx.x];
   const ItemDev it = items[wk.item];
   double r0 = 0.0, r1 = 0.0;
-  if (wk.kind == 0) {
+  if (wk.kind == 2) {
+    extern __shared__ __align__(1024) unsigned char dsm[];
+    bool finish = true;
+    gram_tile_tc(it, wk, dsm, ticket, scratch, scratch_off, red, r0, r1, finish, out_slot);
+    if (!finish) out_slot = -1;
+  } else if (wk.kind == 0) {
     const size_t total = (size_t)it.rows * it.cols;
     const size_t beg = (size_t)wk.a * kChunk;
     const size_t end = beg + kChunk < total ? beg + kChunk : total;
@@ -190,7 +451,7 @@ __global__ void __launch_bounds__(256) penalties_kernel(const ItemDev* __restric
     double s[4] = {0, 0, 0, 0};
     for (int w = lane; w < d.n_work; w += 32) {
       const int gw = d.first_work + w;
-      const int kind = work[gw].kind;
+      const int kind = work[gw].kind == 0 ? 0 : 1;     // Gram tiles of either flavour report (off-diagonal sum, Frobenius sum)
       const volatile double* pp = partial + 2 * (size_t)gw;
       s[2 * kind] += pp[0];
       s[2 * kind + 1] += pp[1];
@@ -247,6 +508,7 @@ extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items,
   std::vector<Work> hw;
   std::vector<int> soff;          // per split tile: offset of its scratch block (doubles)
   size_t scratch_doubles = 0;
+  bool any_tc = false;
   for (int i = 0; i < n_items; ++i) {
     const svdlstm_penalty_item& s = items[i];
     SVD_REQUIRE(s.data && s.rows >= 1 && s.cols >= 1 && s.ld >= s.cols, "svdlstm_penalties: item %d has bad shape (%d,%d) ld=%d", i, s.rows, s.cols, s.ld);
@@ -254,7 +516,23 @@ extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items,
     const size_t total = (size_t)s.rows * s.cols;
     const int nchunks = (int)((total + kChunk - 1) / kChunk);
     for (int c = 0; c < nchunks; ++c) hw.push_back(Work{i, 0, c, 0, 0, 1, 0, 0});
-    if (s.gram) {
+    const bool tc = s.gram && !s.columns && s.rows >= 64 && s.cols >= 64 && !getenv("SVDLSTM_K3_NO_TC");
+    if (tc) {
+      any_tc = true;
+      const int nb = (s.rows + kTcTile - 1) / kTcTile;
+      const int nsp = (s.cols + kTcSplitF - 1) / kTcSplitF;
+      for (int a = 0; a < nb; ++a)
+        for (int b = a; b < nb; ++b) {
+          if (nsp <= 1) {
+            hw.push_back(Work{i, 2, a, b, 0, 1, 0, 0});
+          } else {
+            const int base = (int)hw.size(), slot = (int)soff.size();
+            soff.push_back((int)scratch_doubles);
+            scratch_doubles += ((size_t)nsp * kTcPartFloats + 1) / 2;
+            for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 2, a, b, sp, nsp, slot, base});
+          }
+        }
+    } else if (s.gram) {
       const int R = s.columns ? s.cols : s.rows;
       const int F = s.columns ? s.rows : s.cols;
       const int nb = (R + kTile - 1) / kTile;
@@ -293,7 +571,9 @@ extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items,
   // pageable -> device: the runtime stages these synchronously, so the vectors may die after the call
   SVD_CUDA_TRY(cudaMemcpyAsync(di, hi.data(), sizeof(ItemDev) * n_items, cudaMemcpyHostToDevice, stream));
   SVD_CUDA_TRY(cudaMemcpyAsync(dw, hw.data(), sizeof(Work) * n_work, cudaMemcpyHostToDevice, stream));
-  penalties_kernel<<<n_work, 256, 0, stream>>>(di, n_items, dw, n_work, partial, ticket, scratch, dsoff, out);
+  const size_t dyn_smem = any_tc ? kTcSmem : 0;
+  if (any_tc) SVD_CUDA_TRY(cudaFuncSetAttribute(penalties_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  penalties_kernel<<<n_work, 256, dyn_smem, stream>>>(di, n_items, dw, n_work, partial, ticket, scratch, dsoff, out);
   SVD_CUDA_TRY(cudaGetLastError());
   SVD_CUDA_TRY(cudaFreeAsync(di, stream));
   SVD_CUDA_TRY(cudaFreeAsync(dw, stream));

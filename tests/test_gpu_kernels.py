@@ -259,3 +259,29 @@ def test_svd_c5_size_matrix():
     assert float((Ud.reshape(1024, 1024).T @ Ud.reshape(1024, 1024) - eye).abs().max()) < 1e-5
     assert float((Vd.reshape(1024, 4096) @ Vd.reshape(1024, 4096).T - eye).abs().max()) < 1e-5
     print("SVD 1024x4096: %d sweeps, %.2f s" % (int(sw[0]), dt))
+
+
+def test_penalties_tensor_core_gram(oracle, monkeypatch):
+    """K3 kind 2: 128 x 128 Gram tiles on tcgen05 (kind::tf32, 3xTF32 split, FP32 accumulation in TMEM) for rows-mode items with
+    >= 64 rows and features -- the C5 factor shapes (128 x 4096 right factors: 8 feature splits; 1024 x 128 left factors: 36
+    tiles), ragged shapes, and orthonormal rows (penalty ~ 0).  Bars vs the float64 oracle: 2e-6 relative on the raw sums
+    (TF32-split products carry ~2^-21 each, signs random), absolute 1e-5 / 1e-6 where the true value is ~0."""
+    rng = np.random.default_rng(20)
+    q = np.linalg.qr(rng.standard_normal((256, 256)))[0].astype(np.float32)
+    items = [(rng.standard_normal((128, 4096)) / 64.0).astype(np.float32), (rng.standard_normal((1024, 128)) / 11.0).astype(np.float32),
+             rng.standard_normal((300, 700)).astype(np.float32), q, q[:100, :], rng.standard_normal((64, 64)).astype(np.float32),
+             rng.standard_normal((129, 65)).astype(np.float32)]
+    spec = [(a, True, False) for a in items]
+    raw = svdlstm.evaluate_penalties(spec)
+    assert np.array_equal(raw, svdlstm.evaluate_penalties(spec)), "tensor-core Gram tiles must be bit-reproducible"
+    for a, got in zip(items, raw):
+        ref = oracle.penalty_raw_sums(a, mode="rows")
+        assert math.isclose(got[0], ref[0], rel_tol=1e-6) and math.isclose(got[1], ref[1], rel_tol=1e-6)
+        assert math.isclose(got[2], ref[2], rel_tol=2e-6, abs_tol=1e-5 * a.shape[0]), (a.shape, got[2], ref[2])
+        assert math.isclose(got[3], ref[3], rel_tol=2e-6, abs_tol=1e-6), (a.shape, got[3], ref[3])
+    # (the CUDA-core float64 tiles remain for columns mode and small items; both flavours agree -- checked in a fresh process
+    #  because the switch is read per call)
+    monkeypatch.setenv("SVDLSTM_K3_NO_TC", "1")
+    raw64 = svdlstm.evaluate_penalties(spec)
+    monkeypatch.delenv("SVDLSTM_K3_NO_TC")
+    assert np.allclose(raw, raw64, rtol=2e-6, atol=1e-5)
