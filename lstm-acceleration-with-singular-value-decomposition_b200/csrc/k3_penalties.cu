@@ -20,6 +20,7 @@
 // errors, two-stage fixed-order float64 reduction (independent of GPU count => sweep determinism).
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -500,87 +501,121 @@ __global__ void __launch_bounds__(256) sse_final_kernel(const double* __restrict
 
 using namespace svdlstm;
 
-extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items, double* out, void* stream_) {
-  SVD_REQUIRE(items && out, "svdlstm_penalties: null argument");
-  SVD_REQUIRE(n_items >= 1 && n_items <= 4096, "svdlstm_penalties: n_items=%d not in [1,4096]", n_items);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  std::vector<ItemDev> hi(n_items);
-  std::vector<Work> hw;
-  std::vector<int> soff;          // per split tile: offset of its scratch block (doubles)
-  size_t scratch_doubles = 0;
-  bool any_tc = false;
-  for (int i = 0; i < n_items; ++i) {
-    const svdlstm_penalty_item& s = items[i];
-    SVD_REQUIRE(s.data && s.rows >= 1 && s.cols >= 1 && s.ld >= s.cols, "svdlstm_penalties: item %d has bad shape (%d,%d) ld=%d", i, s.rows, s.cols, s.ld);
-    hi[i] = ItemDev{s.data, s.rows, s.cols, s.ld, s.gram, s.columns, (int)hw.size(), 0};
-    const size_t total = (size_t)s.rows * s.cols;
-    const int nchunks = (int)((total + kChunk - 1) / kChunk);
-    for (int c = 0; c < nchunks; ++c) hw.push_back(Work{i, 0, c, 0, 0, 1, 0, 0});
-    const bool tc = s.gram && !s.columns && s.rows >= 64 && s.cols >= 64 && !getenv("SVDLSTM_K3_NO_TC");
-    if (tc) {
-      any_tc = true;
-      const int nb = (s.rows + kTcTile - 1) / kTcTile;
-      const int nsp = (s.cols + kTcSplitF - 1) / kTcSplitF;
-      for (int a = 0; a < nb; ++a)
-        for (int b = a; b < nb; ++b) {
-          if (nsp <= 1) {
-            hw.push_back(Work{i, 2, a, b, 0, 1, 0, 0});
-          } else {
-            const int base = (int)hw.size(), slot = (int)soff.size();
-            soff.push_back((int)scratch_doubles);
-            scratch_doubles += ((size_t)nsp * kTcPartFloats + 1) / 2;
-            for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 2, a, b, sp, nsp, slot, base});
-          }
-        }
-    } else if (s.gram) {
-      const int R = s.columns ? s.cols : s.rows;
-      const int F = s.columns ? s.rows : s.cols;
-      const int nb = (R + kTile - 1) / kTile;
-      const int nsp = (F + kSplitF - 1) / kSplitF;
-      for (int a = 0; a < nb; ++a)
-        for (int b = a; b < nb; ++b) {
-          if (nsp <= 1) {
-            hw.push_back(Work{i, 1, a, b, 0, 1, 0, 0});
-          } else {
-            const int base = (int)hw.size(), slot = (int)soff.size();
-            soff.push_back((int)scratch_doubles);
-            scratch_doubles += (size_t)nsp * kPartDoubles;
-            for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 1, a, b, sp, nsp, slot, base});
-          }
-        }
-    }
-    hi[i].n_work = (int)hw.size() - hi[i].first_work;
-  }
-  const int n_work = (int)hw.size();
+// The work list of a model does not change from one training step to the next (same tensors, same shapes): it is built and
+// uploaded once and kept per device; a repeated call costs two small memsets and the launch.
+struct K3Plan {
+  std::vector<svdlstm_penalty_item> key;
+  bool no_tc = false;
   ItemDev* di = nullptr;
   Work* dw = nullptr;
   double* partial = nullptr;
   unsigned int* ticket = nullptr;
   double* scratch = nullptr;
   int* dsoff = nullptr;
-  const size_t n_tick = 1 + soff.size();
-  SVD_CUDA_TRY(cudaMallocAsync(&di, sizeof(ItemDev) * n_items, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&dw, sizeof(Work) * n_work, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&partial, sizeof(double) * 2 * n_work, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&ticket, sizeof(unsigned int) * n_tick, stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(double) * (scratch_doubles ? scratch_doubles : 1), stream));
-  SVD_CUDA_TRY(cudaMallocAsync(&dsoff, sizeof(int) * (soff.size() ? soff.size() : 1), stream));
-  SVD_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int) * n_tick, stream));
-  SVD_CUDA_TRY(cudaMemsetAsync(partial, 0, sizeof(double) * 2 * n_work, stream));
-  if (!soff.empty()) SVD_CUDA_TRY(cudaMemcpyAsync(dsoff, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice, stream));
-  // pageable -> device: the runtime stages these synchronously, so the vectors may die after the call
-  SVD_CUDA_TRY(cudaMemcpyAsync(di, hi.data(), sizeof(ItemDev) * n_items, cudaMemcpyHostToDevice, stream));
-  SVD_CUDA_TRY(cudaMemcpyAsync(dw, hw.data(), sizeof(Work) * n_work, cudaMemcpyHostToDevice, stream));
-  const size_t dyn_smem = any_tc ? kTcSmem : 0;
-  if (any_tc) SVD_CUDA_TRY(cudaFuncSetAttribute(penalties_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  penalties_kernel<<<n_work, 256, dyn_smem, stream>>>(di, n_items, dw, n_work, partial, ticket, scratch, dsoff, out);
+  int n_work = 0;
+  size_t n_tick = 0;
+  bool any_tc = false;
+  cudaEvent_t done = nullptr;   // the last launch that used these buffers
+  void release() {
+    if (done) cudaEventSynchronize(done);
+    cudaFree(di); cudaFree(dw); cudaFree(partial); cudaFree(ticket); cudaFree(scratch); cudaFree(dsoff);
+    di = nullptr; dw = nullptr; partial = nullptr; ticket = nullptr; scratch = nullptr; dsoff = nullptr;
+    key.clear();
+  }
+};
+static K3Plan g_k3_plan[16];
+static std::mutex g_k3_mu;
+
+extern "C" int svdlstm_penalties(const svdlstm_penalty_item* items, int n_items, double* out, void* stream_) {
+  SVD_REQUIRE(items && out, "svdlstm_penalties: null argument");
+  SVD_REQUIRE(n_items >= 1 && n_items <= 4096, "svdlstm_penalties: n_items=%d not in [1,4096]", n_items);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0;
+  SVD_CUDA_TRY(cudaGetDevice(&dev));
+  SVD_REQUIRE(dev >= 0 && dev < 16, "svdlstm_penalties: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_k3_mu);
+  K3Plan& P = g_k3_plan[dev];
+  const bool no_tc = getenv("SVDLSTM_K3_NO_TC") != nullptr;
+  bool same = (int)P.key.size() == n_items && P.no_tc == no_tc;
+  for (int i = 0; same && i < n_items; ++i)
+    same = P.key[i].data == items[i].data && P.key[i].rows == items[i].rows && P.key[i].cols == items[i].cols && P.key[i].ld == items[i].ld &&
+           P.key[i].gram == items[i].gram && P.key[i].columns == items[i].columns;
+  if (!same) {
+    P.release();
+    std::vector<ItemDev> hi(n_items);
+    std::vector<Work> hw;
+    std::vector<int> soff;          // per split tile: offset of its scratch block (doubles)
+    size_t scratch_doubles = 0;
+    bool any_tc = false;
+    for (int i = 0; i < n_items; ++i) {
+      const svdlstm_penalty_item& s = items[i];
+      SVD_REQUIRE(s.data && s.rows >= 1 && s.cols >= 1 && s.ld >= s.cols, "svdlstm_penalties: item %d has bad shape (%d,%d) ld=%d", i, s.rows, s.cols, s.ld);
+      hi[i] = ItemDev{s.data, s.rows, s.cols, s.ld, s.gram, s.columns, (int)hw.size(), 0};
+      const size_t total = (size_t)s.rows * s.cols;
+      const int nchunks = (int)((total + kChunk - 1) / kChunk);
+      for (int c = 0; c < nchunks; ++c) hw.push_back(Work{i, 0, c, 0, 0, 1, 0, 0});
+      // tensor-core tiles for the GEMM-sized Gram matrices (rows mode); small items and columns mode stay on the float64 tiles
+      const bool tc = s.gram && !s.columns && s.rows >= 64 && s.cols >= 64 && (size_t)s.rows * s.rows * s.cols >= (size_t)1 << 21 && !no_tc;
+      if (tc) {
+        any_tc = true;
+        const int nb = (s.rows + kTcTile - 1) / kTcTile;
+        const int nsp = (s.cols + kTcSplitF - 1) / kTcSplitF;
+        for (int a = 0; a < nb; ++a)
+          for (int b = a; b < nb; ++b) {
+            if (nsp <= 1) {
+              hw.push_back(Work{i, 2, a, b, 0, 1, 0, 0});
+            } else {
+              const int base = (int)hw.size(), slot = (int)soff.size();
+              soff.push_back((int)scratch_doubles);
+              scratch_doubles += ((size_t)nsp * kTcPartFloats + 1) / 2;
+              for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 2, a, b, sp, nsp, slot, base});
+            }
+          }
+      } else if (s.gram) {
+        const int R = s.columns ? s.cols : s.rows;
+        const int F = s.columns ? s.rows : s.cols;
+        const int nb = (R + kTile - 1) / kTile;
+        const int nsp = (F + kSplitF - 1) / kSplitF;
+        for (int a = 0; a < nb; ++a)
+          for (int b = a; b < nb; ++b) {
+            if (nsp <= 1) {
+              hw.push_back(Work{i, 1, a, b, 0, 1, 0, 0});
+            } else {
+              const int base = (int)hw.size(), slot = (int)soff.size();
+              soff.push_back((int)scratch_doubles);
+              scratch_doubles += (size_t)nsp * kPartDoubles;
+              for (int sp = 0; sp < nsp; ++sp) hw.push_back(Work{i, 1, a, b, sp, nsp, slot, base});
+            }
+          }
+      }
+      hi[i].n_work = (int)hw.size() - hi[i].first_work;
+    }
+    P.n_work = (int)hw.size();
+    P.n_tick = 1 + soff.size();
+    P.any_tc = any_tc;
+    P.no_tc = no_tc;
+    SVD_CUDA_TRY(cudaMalloc(&P.di, sizeof(ItemDev) * n_items));
+    SVD_CUDA_TRY(cudaMalloc(&P.dw, sizeof(Work) * P.n_work));
+    SVD_CUDA_TRY(cudaMalloc(&P.partial, sizeof(double) * 2 * P.n_work));
+    SVD_CUDA_TRY(cudaMalloc(&P.ticket, sizeof(unsigned int) * P.n_tick));
+    SVD_CUDA_TRY(cudaMalloc(&P.scratch, sizeof(double) * (scratch_doubles ? scratch_doubles : 1)));
+    SVD_CUDA_TRY(cudaMalloc(&P.dsoff, sizeof(int) * (soff.size() ? soff.size() : 1)));
+    if (!P.done) SVD_CUDA_TRY(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+    // blocking copies from pageable memory: the host vectors die with this scope
+    if (!soff.empty()) SVD_CUDA_TRY(cudaMemcpy(P.dsoff, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice));
+    SVD_CUDA_TRY(cudaMemcpy(P.di, hi.data(), sizeof(ItemDev) * n_items, cudaMemcpyHostToDevice));
+    SVD_CUDA_TRY(cudaMemcpy(P.dw, hw.data(), sizeof(Work) * P.n_work, cudaMemcpyHostToDevice));
+    P.key.assign(items, items + n_items);
+  } else {
+    SVD_CUDA_TRY(cudaStreamWaitEvent(stream, P.done, 0));   // a previous call on another stream may still own the scratch
+  }
+  SVD_CUDA_TRY(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned int) * P.n_tick, stream));
+  SVD_CUDA_TRY(cudaMemsetAsync(P.partial, 0, sizeof(double) * 2 * P.n_work, stream));
+  const size_t dyn_smem = P.any_tc ? kTcSmem : 0;
+  if (P.any_tc) SVD_CUDA_TRY(cudaFuncSetAttribute(penalties_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  penalties_kernel<<<P.n_work, 256, dyn_smem, stream>>>(P.di, n_items, P.dw, P.n_work, P.partial, P.ticket, P.scratch, P.dsoff, out);
   SVD_CUDA_TRY(cudaGetLastError());
-  SVD_CUDA_TRY(cudaFreeAsync(di, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(dw, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(partial, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(ticket, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(scratch, stream));
-  SVD_CUDA_TRY(cudaFreeAsync(dsoff, stream));
+  SVD_CUDA_TRY(cudaEventRecord(P.done, stream));
   return 0;
 }
 
