@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--c4-sequences", type=int, default=65536)
     ap.add_argument("--c4-ranks", type=int, default=256)
     ap.add_argument("--sweep-iters", type=int, default=10)
+    ap.add_argument("--staging", default="wc", choices=["wc", "pinned"], help="host staging buffer of x: write-combined pinned (default) or plain pinned")
     a = ap.parse_args()
     if a.quick:
         a.batch, a.seq_len = 512, 64
@@ -453,7 +454,13 @@ def main():
     smodel = model._singular_parent
     B, T, D = a.batch, a.seq_len, 16
     gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, T, D, generator=gen).pin_memory()
+    x_src = torch.randn(B, T, D, generator=gen)
+    if a.staging == "wc":      # the user's input staging buffer: write-combined pinned memory (DMA reads are not snooped by the CPU caches)
+        x_host = svdlstm.pinned_empty((B, T, D), write_combined=True)
+        x_host.copy_(x_src)
+    else:
+        x_host = x_src.pin_memory()
+    del x_src
     x = x_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
     engine = None if a.engine == "auto" else a.engine     # None: the library's regime switch picks (what rmodel.predict(X) does)
@@ -528,7 +535,7 @@ def main():
                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(B * T * 4),
                "how": "Sequential.predict_async(pinned host x).result() per step, two requests in flight (H2D of step i+1 on a copy "
                       "stream overlaps the forward of step i); y lands in pinned host memory and is read on the host every step",
-               "numa": numa}
+               "numa": numa, "staging": "cudaHostAllocWriteCombined" if a.staging == "wc" else "pinned (cudaHostAlloc default)"}
         n_sync = max(3, a.steps // 3)
         model.predict(x_host, engine=engine)
         barrier()

@@ -22,6 +22,7 @@
 #ifndef SVDLSTM_H_
 #define SVDLSTM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -94,6 +95,12 @@ int svdlstm_set_dense_top(svdlstm_handle h, const float* kernel, const float* bi
 int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y,
                     const float* h0, const float* c0, float* h_n, float* c_n,
                     const uint8_t* mask, int flags, int engine, void* stream);
+
+/* Pinned (page-locked) host buffers for the inputs / outputs of predict(); write_combined != 0: cudaHostAllocWriteCombined
+ * (DMA reads are not snooped by the CPU caches -- faster host->device streams when several GPUs share a socket; slow for the
+ * CPU to read back, so for input staging only).                                                                           */
+int svdlstm_host_alloc(void** out, size_t bytes, int write_combined);
+int svdlstm_host_free(void* p);
 
 /* Number of kernels the last forward on this handle launched, and which engine ran. */
 int svdlstm_last_launches(svdlstm_handle h);

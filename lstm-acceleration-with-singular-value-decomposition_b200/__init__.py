@@ -6,7 +6,7 @@ Drop-in for the reference's layer / builder API (code/svd_classes_v3.py) and dri
 There is no CPU fallback: the numpy oracle under oracle/ is test infrastructure only.
 """
 from ._cabi import (ENGINE_AUTO, ENGINE_FP32, ENGINE_GENERAL, ENGINE_TC, ENGINE_WAVEFRONT, EXPORTS, LIB_PATH, TC_MIN_BATCH,
-                    TC_MIN_UNITS, lib, require_cuda)
+                    TC_MIN_UNITS, lib, pinned_empty, require_cuda)
 from . import _cabi
 from .layers import (Dense, Handle, HoyerRegularizer, InputLayer, LSTM, LSTMCell, OrthogonalRegularizer,
                      PrunableTimeDistributed, ReducedLSTMCell, SingularLSTM, SingularLSTMCell, TimeDistributed,

@@ -33,7 +33,7 @@ ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc": 3, "tc_f16": 3, "
 EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",
     "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
-    "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_svd_jacobi_batched",
+    "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_host_alloc", "svdlstm_host_free", "svdlstm_svd_jacobi_batched",
     "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_scaled_matmul", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
     "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
     "svdlstm_stream_state", "svdlstm_stream_launches", "svdlstm_stream_close",
@@ -87,6 +87,10 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_last_launches.restype = ci
     L.svdlstm_last_engine.argtypes = [vp]
     L.svdlstm_last_engine.restype = ci
+    L.svdlstm_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t, ci]
+    L.svdlstm_host_alloc.restype = ci
+    L.svdlstm_host_free.argtypes = [vp]
+    L.svdlstm_host_free.restype = ci
     L.svdlstm_count_weights.argtypes = [vp]
     L.svdlstm_count_weights.restype = ctypes.c_int64
     L.svdlstm_svd_jacobi_batched.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp]
@@ -202,6 +206,37 @@ def scaled_matmul(A: torch.Tensor, B: torch.Tensor, scale: Optional[torch.Tensor
                                       cur_stream()))
     add_launches(1)
     return out
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; freed when the last tensor viewing it dies."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.p = ctypes.c_void_p()
+        check(lib().svdlstm_host_alloc(ctypes.byref(self.p), nbytes, 1 if write_combined else 0))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.p.value:
+                lib().svdlstm_host_free(self.p)
+                self.p = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
+    """float32 CPU tensor in page-locked host memory (a staging buffer for ``predict`` / ``predict_async``).
+    ``write_combined=True`` -> cudaHostAllocWriteCombined: fill it once from the CPU, let the GPU read it."""
+    n = int(np.prod(shape))
+    blk = _PinnedBlock(max(4 * n, 4), write_combined)
+    buf = (ctypes.c_float * n).from_address(blk.p.value)
+    arr = np.ctypeslib.as_array(buf).reshape(shape)
+    t = torch.from_numpy(arr)
+    t._svdlstm_block = blk          # keeps the allocation alive as long as this tensor object
+    arr_owner = getattr(t, "_svdlstm_block")
+    assert arr_owner is blk
+    return t
 
 
 def add_launches(n: int) -> None:

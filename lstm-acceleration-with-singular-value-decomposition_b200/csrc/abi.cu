@@ -209,6 +209,19 @@ int svdlstm_set_dense_top(svdlstm_handle h, const float* kernel, const float* bi
   return 0;
 }
 
+/* Pinned host staging buffers for predict(): write_combined != 0 asks for cudaHostAllocWriteCombined memory -- not snooped
+ * by the CPU caches during DMA, which is what limits host->device throughput when several GPUs stream their inputs from one
+ * socket (slow for the CPU to READ, so only for buffers the host fills and the GPU consumes). */
+int svdlstm_host_alloc(void** out, size_t bytes, int write_combined) {
+  SVD_REQUIRE(out != nullptr && bytes > 0, "svdlstm_host_alloc: bad argument");
+  SVD_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return 0;
+}
+int svdlstm_host_free(void* p) {
+  if (p) SVD_CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
+
 int64_t svdlstm_count_weights(svdlstm_handle h) {
   if (!h) return -1;
   int64_t s = 0;
