@@ -306,10 +306,29 @@ def batch1_table(svdlstm, torch):
                             "synchronize; wall clock of the Python call, 250 calls after 50 warm-ups", "calls": streaming}
     # algorithmic on-chip bytes/step of the 3-factor model at full rank: 28 140 B
     byt = 28140.0
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("b1_wavefront", {})
+    except Exception:
+        ncu = {}
+    # Dependent chain of ONE layer-tick of the wavefront kernel (what bounds batch 1: weights are register-resident, so neither
+    # HBM nor the shared-memory port is), from the latencies of the microarchitecture guide: LDS 29, FFMA/FFMA2 4, MUFU ~20,
+    # SHFL ~25, STS->LDS hand-over ~35, CTA barrier ~40 cycles.
+    chain = {"lds_inputs": 29, "stage1_8_dependent_ffma2_plus_adds": 40, "p_through_smem_sts_syncwarp_lds": 35,
+             "stage2_8_dependent_ffma2_plus_adds": 40, "gate_ex2_rcp_fma": 52, "shuffle_gather": 25, "cell_update_fma": 8,
+             "tanh_c_ex2_rcp_fma": 52, "h_mul_sts": 14, "cta_barrier": 40}
+    floor_cycles = sum(chain.values())
+    floor_us = floor_cycles / 1965.0
     return {"unit": "us/timestep", "T": T, "model": "DROPBEAR 3x15 LSTM + Dense(1), batch 1", "us_per_step": out,
             "onchip_roofline": {"bytes_per_step_3F_r15": byt, "achieved_gbs": round(byt / (out["3F_r15"] * 1e-6) / 1e9, 2),
                                 "peak_gbs_1sm": 251.5, "frac": round(byt / (out["3F_r15"] * 1e-6) / 1e9 / 251.5, 4),
-                                "note": "peak = 128 B/clk x 1965 MHz, one SM (the latency chain uses one CTA)"},
+                                "ncu_shared_wavefronts_per_step": ncu.get("shared_wavefronts_per_step"),
+                                "ncu_shared_gbs": ncu.get("shared_gbs"), "ncu_source": ncu.get("source"),
+                                "note": "peak = 128 B/clk x 1965 MHz, one SM (the latency chain uses one CTA); achieved_gbs = ALGORITHMIC factor bytes / time "
+                                        "(the factors live in registers); ncu_* = the shared-memory traffic the kernel really generates (activations only)"},
+            "latency_floor": {"cycles": floor_cycles, "us": round(floor_us, 4), "measured_us": out["3F_r15"],
+                              "frac_of_floor": round(floor_us / out["3F_r15"], 3), "chain_cycles": chain,
+                              "note": "one layer-tick is one dependent chain (the L layers overlap as a wavefront); this, not a memory pipe, bounds batch 1"},
             "streaming": out_streaming, "realtime_budget_us": 400.0}
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns the raw captures of scripts/profile_round.sh (gpurun_out/, scratch) into the tracked evidence under profiles/:
 
-    python scripts/make_profile_summaries.py r02
+    python scripts/make_profile_summaries.py r02 [commit-of-the-capture]
 
   - profiles/launches_bench_<R>.csv / launches_c5_<R>.csv     the ncu launch lists, copied
   - profiles/launch_shares_<R>.txt                            per-kernel share of one forward + DRAM bytes
@@ -79,7 +79,8 @@ def raw_metric(rep, metric, pat):
 
 def main():
     os.makedirs(P, exist_ok=True)
-    stamp = "commit %s" % head()
+    # the commit the captures were taken at (gpurun snapshots have no .git): second argument, else the current HEAD
+    stamp = "commit %s" % (sys.argv[2] if len(sys.argv) > 2 else head())
     traffic = {"unit": "bytes per forward", "stamp": stamp}
     lb = os.path.join(O, "launches_%s.csv" % R)
     if os.path.exists(lb):
@@ -121,6 +122,16 @@ def main():
                 mm = re.search(re.escape(metric) + r"\s+([0-9.]+)", txt)
                 if mm:
                     traffic[key % m.group(1)] = float(mm.group(1))
+    b1 = os.path.join(P, "b1_wavefront_%s.txt" % R)
+    if os.path.exists(b1):
+        txt = open(b1).read()
+        wf = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum\s+([0-9.]+)", txt)
+        du = re.search(r"gpu__time_duration\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        if wf and du:
+            t_s = float(du.group(1)) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(du.group(2), 1e-6)
+            steps = 4096      # scripts/prof_batch1.py default T
+            traffic["b1_wavefront"] = {"shared_wavefronts_per_step": float(wf.group(1)) / steps, "shared_gbs": float(wf.group(1)) * 128 / t_s / 1e9,
+                                       "source": "profiles/b1_wavefront_%s.txt (%s): l1tex__data_pipe_lsu_wavefronts_mem_shared.sum x 128 B / gpu__time_duration, T=4096" % (R, stamp)}
     json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     # SASS opcode histogram of the shipped library
     lib = os.path.join(ROOT, "lstm-acceleration-with-singular-value-decomposition_b200", "libsvdlstm.so")
@@ -140,7 +151,7 @@ def main():
                 hist[op] += 1
                 per_fn[fn][op] += 1
         with open(os.path.join(P, "sass_histogram_%s.txt" % R), "w") as f:
-            f.write("# %s; cuobjdump -sass libsvdlstm.so (sm_100a), opcode counts over all kernels\n" % stamp)
+            f.write("# library built at commit %s (+ working tree); cuobjdump -sass libsvdlstm.so (sm_100a), opcode counts over all kernels\n" % head())
             key = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "MUFU", "FFMA2", "FFMA", "HMMA", "LDGSTS", "DFMA", "REDUX", "SHFL"]
             f.write("blackwell-native markers: " + ", ".join("%s=%d" % (k, hist.get(k, 0)) for k in key) + "\n\n")
             for op, n in hist.most_common(60):
