@@ -17,6 +17,8 @@
 //
 // Replaces SingularLSTMCell.call / ReducedLSTMCell.call + backend.rnn for batch-1 streaming
 // (reference code/svd_classes_v3.py:116-236, 317-368, 405-434; svd_acceleration_v3.py:151).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace svdlstm {
@@ -46,6 +48,7 @@ struct WfLayer {
   int S2;              // RT row stride
   int LU;              // lanes per unit (1,2,4); G = 4/LU gates per lane
   int off_LT, off_RT, off_scale, off_bias, off_p, off_vh, off_qmeta;  // float offsets into smem
+  int WS, off_we;      // dense mode: row stride and offset of W_eff [4H][WS] = [input part | recurrent part], each WS/2 wide
 };
 
 struct WfPlan {
@@ -60,7 +63,7 @@ struct WfPlan {
 };
 
 // Layout shared by host (support check + smem size) and device (prologue).
-__host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl) {
+__host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl, bool dense = false) {
   if (md.n_layers > 6) return false;
   if (md.input_dim > 32 || md.n_out > 1) return false;
   pl.L = md.n_layers;
@@ -99,6 +102,8 @@ __host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl) {
     w.off_p = off;       off += w.P_pad + 64;   // + zero tail: stage 2 reads a full K4*4 window
     w.off_vh = off;      off += 2 * w.S1;   // double-buffered h_l (zero padded to S1)
     w.off_qmeta = off;   off += w.P_pad;    // per-q: bit0 from_h, bits 8.. = padded input length
+    w.WS = 2 * round4(w.H > w.Din ? w.H : w.Din);
+    w.off_we = off;      off += dense ? 4 * w.H * w.WS : 0;
   }
   pl.xstride = pl.layers[0].S1;
   pl.off_x = off;      off += kXRing * pl.xstride;
@@ -162,7 +167,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // output warp writes the prediction straight into host-mapped memory.  No launch, no memcpy, no stream synchronisation per
 // sample; state (h, c) stays in registers / shared memory and is parked in device memory when the kernel leaves (host `stop`,
 // or no sample for `idle_ns`: a forgotten stream must never pin an SM -- or block a cudaDeviceSynchronize -- for ever).
-template <int KIN4, int MP, int K4, int G, bool STREAM = false>
+//
+// DENSE = true (small models: units, input_dim <= 16): the latency regime has nothing to gain from the factored evaluation order
+// -- at H = 15 one fused contraction [x_t | h(t-1)] . W_eff with W_eff = (L sigma) R costs 900 MACs against 1 125 for the two thin
+// ones at full rank, and, more to the point, removes one FFMA chain and one shared-memory round trip (p) from the dependent
+// chain of every tick.  W_eff is formed ONCE per launch in the prologue (float64 accumulation, so the 2-factor [I | C] forms
+// lose nothing to cancellation) and lives in registers; rank truncation is exactly preserved (W_eff has rank r).
+template <int KIN4, int MP, int K4, int G, bool STREAM = false, bool DENSE = false>
 __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a, StreamArgs sa) {
   extern __shared__ __align__(16) float smem[];
   __shared__ WfPlan pl;
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   const bool backwards = a.flags & SVDLSTM_GO_BACKWARDS;
   const bool time_major = a.flags & SVDLSTM_TIME_MAJOR;
 
-  if (tid == 0) wf_make_plan(md, pl);
+  if (tid == 0) wf_make_plan(md, pl, DENSE);
   __syncthreads();
   const int L = pl.L, D = pl.D;
 
@@ -245,6 +256,25 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
     }
   }
   __syncthreads();
+  if constexpr (DENSE) {
+    for (int l = 0; l < L; ++l) {
+      const WfLayer& w = pl.layers[l];
+      const int half = w.WS / 2;
+      for (int idx = tid; idx < 4 * w.H * w.WS; idx += nthr) {
+        const int n = idx / w.WS, c = idx - n * w.WS;
+        const int fh = c >= half ? 1 : 0, i = c - fh * half;
+        const int grp = w.n_groups == 1 ? 0 : n / w.H;
+        double acc = 0.0;
+        for (int kk = 0; kk < w.g_K[grp]; ++kk) {
+          const int q = w.g_start[grp] + kk;
+          if ((__float_as_int(smem[w.off_qmeta + q]) & 1) != fh) continue;
+          acc += (double)smem[w.off_RT + n * w.S2 + kk] * (double)smem[w.off_scale + q] * (double)smem[w.off_LT + q * w.S1 + i];
+        }
+        smem[w.off_we + idx] = (float)acc;
+      }
+    }
+    __syncthreads();
+  }
 
   // ---------------- per-warp persistent state: weights -> REGISTERS ---------------------------
   const int role = warp;  // 0: loader, 1..L: layers, L+1: output
@@ -257,13 +287,31 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
 
   // stage-1 weights of my columns over the concatenated input [x_t | h(t-1)] (packed pairs; the half a
   // column does not use is zero, so no per-lane select is needed; sigma is folded in: v.(L*sigma))
-  f2_t w1[MP][KIN4 * 4];
-  f2_t w2[G][K4 * 2];       // stage-2 weights of my gate columns (packed pairs)
+  f2_t w1[DENSE ? 1 : MP][DENSE ? 1 : KIN4 * 4];
+  f2_t w2[G][DENSE ? 1 : K4 * 2];       // stage-2 weights of my gate columns (packed pairs)
+  f2_t wd[G][DENSE ? KIN4 * 4 : 1];     // dense mode: W_eff columns of my gates over [x_t | h(t-1)] (packed pairs)
   float bias2[G];
   unsigned pofs[G];         // shared address of the p window each of my gates contracts with
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   float c_state = 0.f, h_last = 0.f;
-  if (is_layer) {
+  if (is_layer && DENSE) {
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      const int gate = sub * G + gi;
+      const bool ok = j < H;
+      const int n = gate * H + (ok ? j : 0);
+      const int half = wl.WS / 2;
+      pofs[gi] = 0;
+      bias2[gi] = ok ? smem[wl.off_bias + n] : 0.f;
+#pragma unroll
+      for (int i = 0; i < KIN4 * 2; ++i) {
+        const float* row = smem + wl.off_we + n * wl.WS;
+        wd[gi][i] = pack2((ok && 2 * i < half) ? row[2 * i] : 0.f, (ok && 2 * i + 1 < half) ? row[2 * i + 1] : 0.f);
+        wd[gi][KIN4 * 2 + i] = pack2((ok && 2 * i < half) ? row[half + 2 * i] : 0.f, (ok && 2 * i + 1 < half) ? row[half + 2 * i + 1] : 0.f);
+      }
+    }
+  }
+  if (is_layer && !DENSE) {
 #pragma unroll
     for (int m = 0; m < MP; ++m) {
       const int q = lane + 32 * m;
@@ -294,6 +342,8 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
         w2[gi][kk] = pack2(lo, hi);
       }
     }
+  }
+  if (is_layer) {
     if (a.c0 != nullptr) {
       size_t soff = 0;
       for (int l = 0; l < lyr; ++l) soff += (size_t)B * pl.layers[l].H;
@@ -340,13 +390,34 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
         const unsigned va = vin_addr + (unsigned)((lyr == 0) ? xslot : (step & 1)) * vin_sb;
         const unsigned ha = vh_addr + (unsigned)((step + 1) & 1) * vh_sb;       // h_l(step-1)
         const unsigned ho = vh_addr + (unsigned)(step & 1) * vh_sb + 4u * (unsigned)j;
-        // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
         float4 vi[KIN4], vh[KIN4];
 #pragma unroll
         for (int i = 0; i < KIN4; ++i) {
           vi[i] = lds128(va + 16u * i);
           vh[i] = lds128(ha + 16u * i);
         }
+        float zz[G];
+        if constexpr (DENSE) {
+          // ---- one fused contraction: z = bias + [x_t | h(t-1)] . W_eff, four independent FFMA2 chains of depth KIN4 per gate ----
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) {
+            f2_t a0 = pack2(bias2[gi], 0.f), a1 = 0ull, b0 = 0ull, b1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < KIN4; ++i) {
+              a0 = ffma2(pack2(vi[i].x, vi[i].y), wd[gi][2 * i + 0], a0);
+              a1 = ffma2(pack2(vi[i].z, vi[i].w), wd[gi][2 * i + 1], a1);
+              b0 = ffma2(pack2(vh[i].x, vh[i].y), wd[gi][KIN4 * 2 + 2 * i + 0], b0);
+              b1 = ffma2(pack2(vh[i].z, vh[i].w), wd[gi][KIN4 * 2 + 2 * i + 1], b1);
+            }
+            float s0, s1, s2, s3, u0, u1, u2, u3;
+            unpack2(a0, s0, s1);
+            unpack2(a1, s2, s3);
+            unpack2(b0, u0, u1);
+            unpack2(b1, u2, u3);
+            zz[gi] = ((s0 + s1) + (s2 + s3)) + ((u0 + u1) + (u2 + u3));
+          }
+        } else {
+        // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
 #pragma unroll
         for (int m = 0; m < MP; ++m) {
           f2_t a0 = 0ull, a1 = 0ull;
@@ -367,7 +438,6 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
         }
         __syncwarp();
         // ---- stage 2: z = bias + <p[window], RT[n,:]> ; stage 3: gates ---------------------------
-        float zz[G];
         if (same_window) {   // merged / full forms: every gate contracts with the same p window
           float4 pw[K4];
 #pragma unroll
@@ -402,6 +472,7 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
             unpack2(a1, s2, s3);
             zz[gi] = (s0 + s1) + (s2 + s3);
           }
+        }
         }
         float act[G];
 #pragma unroll
@@ -601,6 +672,16 @@ WfKernel wf_pick_mp(int mp, int k4, int g) {
 template <bool STREAM = false>
 inline WfKernel wf_pick(const WfShape& s) { return s.kin4 == 4 ? wf_pick_mp<4, STREAM>(s.mp, s.k4, s.g) : wf_pick_mp<8, STREAM>(s.mp, s.k4, s.g); }
 
+// Dense mode (one fused contraction per layer-tick, W_eff in registers) for the small-model latency regime: units and input
+// width <= 16 (G = 2, KIN4 = 4: 64 weight registers per lane).  SVDLSTM_WF_FACTORED=1 keeps the two-stage factored evaluation.
+inline bool wf_dense(const WfShape& s) {
+  const char* e = getenv("SVDLSTM_WF_FACTORED");     // read per call: bench.py times both evaluation orders in one process
+  const bool off = e && e[0] && e[0] != '0';
+  return !off && s.kin4 == 4 && s.g == 2;
+}
+template <bool STREAM>
+inline WfKernel wf_pick_dense() { return lstm_wavefront_kernel<4, 1, 2, 2, STREAM, true>; }
+
 }  // namespace
 
 bool wavefront_supported(const ModelDesc& md, const ForwardArgs& a) {
@@ -617,6 +698,13 @@ int run_wavefront(const ModelDesc& md, const ModelDesc* dev_md, const ForwardArg
   WfShape sh;
   WfKernel kern = wf_shape(pl, sh) ? wf_pick(sh) : nullptr;
   SVD_REQUIRE(kern != nullptr, "wavefront engine: factor shapes exceed the register-resident budget");
+  if (wf_dense(sh)) {
+    WfPlan pd;
+    if (wf_make_plan(md, pd, true)) {
+      pl = pd;
+      kern = wf_pick_dense<false>();
+    }
+  }
   const size_t smem = (size_t)pl.total_floats * sizeof(float);
   SVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = 32 * (md.n_layers + 2);
@@ -641,6 +729,13 @@ int launch_wavefront_stream(const ModelDesc& md, const ModelDesc* dev_md, float*
   WfShape sh;
   WfKernel kern = wf_shape(pl, sh) ? wf_pick<true>(sh) : nullptr;
   SVD_REQUIRE(kern != nullptr, "real-time stream: factor shapes exceed the register-resident budget");
+  if (wf_dense(sh)) {
+    WfPlan pd;
+    if (wf_make_plan(md, pd, true)) {
+      pl = pd;
+      kern = wf_pick_dense<true>();
+    }
+  }
   const size_t smem = (size_t)pl.total_floats * sizeof(float);
   SVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ForwardArgs a{nullptr, nullptr, state_h, state_c, state_h, state_c, nullptr, 1, 1, SVDLSTM_RETURN_SEQUENCES};
