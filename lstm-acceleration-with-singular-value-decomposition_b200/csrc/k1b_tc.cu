@@ -285,6 +285,8 @@ struct TcLayerParams {
   int n_slots_w, n_slots_u, n_slots_2;
   const float* bias;        // [nub][4][128]; gates i,f,o pre-scaled by 0.5 (sigmoid(x) = 0.5 tanh(x/2) + 0.5)
   const uint8_t* in_seq;    // activation tile images [cta][t], K = Kin
+  const float* x_raw;       // layer 0: the caller's x (B, T, D) float32 -- read and converted by the input warp itself (no pack_x pass,
+  int x_dim;                //          no FP16 image of x in HBM); nullptr: bulk copies from in_seq
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
   float* y;                 // (B, T, n_dense) fused Dense-top output            (n_dense > 0)
   const float* dense_bias;
@@ -458,6 +460,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
   static_assert(CPT == 8 || CPT == 16 || CPT == 32, "8, 16 or 32 accumulator columns per epilogue thread");
   constexpr uint32_t kRowBlk = (uint32_t)NS * 256u;   // bytes of 128 K-rows of an activation tile (16 k-groups)
   constexpr uint32_t kK64 = (uint32_t)NS * 8u;        // descriptor-lo step of 64 K-rows (8 k-groups of NS*16 bytes)
+  constexpr uint32_t kActLBOx = (uint32_t)NS * 16u;   // bytes between consecutive k-groups (8 K rows) of an activation tile
   constexpr int kS2Bufs = NS == 32 ? 2 : 1;   // S2 accumulator buffers that fit TMEM (4 gates x NS columns each)
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcSmemPlan sp = tc_plan(p);
@@ -573,8 +576,60 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       }
     }
   } else if (warp == 3) {
-    // ======================= input ring: one bulk copy per step, as early as the ring allows ======================
-    if (lane == 0) {
+    // ======================= input ring ==========================================================================
+    if (p.x_raw != nullptr) {
+      // layer 0: x(t) of this tile straight from the caller's (B, T, D) float32 array: every lane converts the rows of its
+      // sequences (n = lane, lane + 32, ...) to FP16 and scatters them into the MN-major operand tile; the ring depth (2-3
+      // steps = >10 us) hides the load latency.  Rows k >= D of the tile keep the zeros of the initial fill.
+      const int D = p.x_dim;
+      const bool vec = (D % 4) == 0;
+      int ld_s = 0;
+      uint32_t ld_n = 0;
+#pragma unroll 1
+      for (int ld_t = 0; ld_t < T; ++ld_t) {
+        if (ld_n > 0) {
+          if (lane == 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
+          __syncwarp();
+        }
+        const uint32_t tile = sbase + sp.inbuf + ld_s * in_tile;
+#pragma unroll 1
+        for (int n = lane; n < NS; n += 32) {
+          const int b = cta * NS + n;
+          const float* src = p.x_raw + ((size_t)b * T + ld_t) * D;
+          const uint32_t col = tile + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 2u;
+          if (b < p.B) {
+            if (vec) {
+#pragma unroll 1
+              for (int k = 0; k < D; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int kk = k + u;
+                  const __half hv = __float2half_rn(vv[u]);
+                  asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+                }
+              }
+            } else {
+#pragma unroll 1
+              for (int kk = 0; kk < D; ++kk) {
+                const __half hv = __float2half_rn(__ldg(src + kk));
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int kk = 0; kk < D; ++kk)
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"((unsigned short)0) : "memory");
+          }
+        }
+        fence_proxy_async();     // generic-proxy stores -> visible to the MMAs' async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_IN_FULL + ld_s));
+        if (++ld_s == nst) { ld_s = 0; ++ld_n; }
+      }
+    } else if (lane == 0) {
+      // one bulk copy per step, as early as the ring allows
       const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
       int ld_s = 0;          // ring stage of the next tile to load
       uint32_t ld_n = 0;     // how many times that stage has been used
@@ -1746,7 +1801,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   if (ws->done == nullptr) SVD_CUDA_TRY(cudaEventCreateWithFlags(&ws->done, cudaEventDisableTiming));
   else SVD_CUDA_TRY(cudaStreamWaitEvent(stream, ws->done, 0));   // the previous forward (any stream) owns the shared scratch until then
   const int Dpad = st->layers[0].prm.Kin;
-  const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad, ns);
+  const size_t xbytes = getenv("SVDLSTM_TC_PACKX") ? (size_t)n_cta * T * act_tile_bytes(Dpad, ns) : 0;
   if (ws->xseq_bytes < xbytes) {
     if (ws->xseq) {
       SVD_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1780,12 +1835,15 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     }
     SVD_CUDA_TRY(cudaMemsetAsync(ws->progress, 0, sizeof(int) * need, stream));
   }
-  {
+  // layer 0 reads the caller's float32 x itself (its input warp converts on the fly); SVDLSTM_TC_PACKX=1 restores the separate
+  // packing pass + FP16 image of x (round 1: 2.8 % of the step, 368 MB of DRAM traffic per forward)
+  const bool raw_x = getenv("SVDLSTM_TC_PACKX") == nullptr;
+  if (!raw_x) {
     const int D = md.input_dim;
     const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
     pack_x_kernel<<<dim3((T + TT - 1) / TT, n_cta), 256, sizeof(float) * ns * TT * D, stream>>>(a.x, B, T, D, Dpad, TT, ns, ws->xseq);
+    ++nl;
   }
-  ++nl;
   static long long* dbg_buf = nullptr;
   const char* dbg_env = getenv("SVDLSTM_TC_TIMELINE");
   if (dbg_env && !dbg_buf) {
@@ -1801,6 +1859,8 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
     const int in_slot = pipe ? l - 1 : ((l - 1) & 1), out_slot = pipe ? l : (l & 1);
     p.in_seq = (l == 0) ? ws->xseq : ws->seq[in_slot];
+    p.x_raw = (l == 0 && raw_x) ? a.x : nullptr;
+    p.x_dim = md.input_dim;
     p.out_seq = (p.store_h || p.store_x) ? ws->seq[out_slot] : nullptr;
     p.y = a.y;
     p.dense_bias = md.dense_bias;

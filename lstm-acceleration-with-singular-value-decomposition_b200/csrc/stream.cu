@@ -8,6 +8,7 @@
 //
 // The kernel parks its state and leaves on `stop` or after `idle_ms` without a sample (so that a forgotten stream can neither
 // pin an SM nor block a cudaDeviceSynchronize for ever); the next step relaunches it transparently from the parked state.
+#include <sched.h>
 #include <string.h>
 #include <time.h>
 
@@ -210,6 +211,22 @@ int svdlstm_stream_step(svdlstm_stream s, const float* x_t, float* y_t) {
 int svdlstm_stream_run(svdlstm_stream s, const float* x, int n, double period_us, float* y, float* latency_us) {
   SVD_REQUIRE(s != nullptr && x != nullptr && y != nullptr && n >= 0, "svdlstm_stream_run: bad argument");
   if (int e = ensure_running(s)) return e;
+  // best effort: a real-time producer runs at a real-time priority (a descheduled feeder thread shows up as a millisecond outlier
+  // that has nothing to do with the device); silently skipped without CAP_SYS_NICE
+  const int old_policy = sched_getscheduler(0);
+  sched_param old_param{};
+  sched_getparam(0, &old_param);
+  sched_param rt_param{};
+  rt_param.sched_priority = 10;
+  const bool rt = period_us > 0 && sched_setscheduler(0, SCHED_FIFO, &rt_param) == 0;
+  struct Restore {
+    bool on;
+    int pol;
+    sched_param par;
+    ~Restore() {
+      if (on) sched_setscheduler(0, pol, &par);
+    }
+  } restore{rt, old_policy, old_param};
   const double t_start = now_us();
   for (int i = 0; i < n; ++i) {
     if (period_us > 0) {
