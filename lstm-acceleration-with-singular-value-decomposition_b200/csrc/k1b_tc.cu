@@ -438,6 +438,76 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
   }
 }
 
+// Input warp of layer 0: x(t) of this tile straight from the caller's (B, T, D) float32 array (no separate packing pass, no FP16
+// image of x in HBM).  Every lane converts the rows of its sequences (n = lane, lane + 32) to FP16 and scatters them into the
+// MN-major operand tile.  The loads of step t+1 are issued -- all at once: one memory latency per step -- before this warp waits
+// for the next ring stage, and the ring runs 2-3 steps ahead of the MMAs.  Rows k >= D of the tile keep the zeros of the initial
+// fill.  Compiled only into the RAWX instantiations of the kernel (see tc_layer_body).
+template <int NS>
+__device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, int D, int B, int T, int cta, uint32_t inbuf, uint32_t in_tile, int nst,
+                                            uint32_t bar_full0, uint32_t bar_empty0) {
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kLBO = (uint32_t)NS * 16u;     // bytes between consecutive k-groups (8 K rows) of an activation tile
+  constexpr int SPL = NS / 32;                      // sequences per lane
+  const bool fast = (D % 4) == 0 && D <= 16;        // <= 4 float4 per sequence held in registers
+  float4 v[SPL][4];
+  auto st16 = [&](uint32_t addr, float f) {
+    const __half hv = __float2half_rn(f);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+  };
+  auto load_step = [&](int t) {
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+      const int b = cta * NS + lane + 32 * q;
+      const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * T + t) * D);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[q][c] = (b < B && 4 * c < D) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int ld_s = 0;
+  uint32_t ld_n = 0;
+  if (fast) load_step(0);
+#pragma unroll 1
+  for (int ld_t = 0; ld_t < T; ++ld_t) {
+    if (ld_n > 0) {
+      if (lane == 0) mbar_wait(bar_empty0 + 8u * (uint32_t)ld_s, (ld_n - 1u) & 1u);
+      __syncwarp();
+    }
+    const uint32_t tile = inbuf + (uint32_t)ld_s * in_tile;
+    if (fast) {
+#pragma unroll
+      for (int q = 0; q < SPL; ++q) {
+        const int n = lane + 32 * q;
+        const uint32_t col = tile + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 2u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (4 * c < D) {
+            const uint32_t a0 = col + (uint32_t)((4 * c) / 8) * kLBO + (uint32_t)((4 * c) % 8) * 16u;
+            st16(a0, v[q][c].x);
+            st16(a0 + 16u, v[q][c].y);
+            st16(a0 + 32u, v[q][c].z);
+            st16(a0 + 48u, v[q][c].w);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int n = lane; n < NS; n += 32) {
+        const int b = cta * NS + n;
+        const float* src = x + ((size_t)b * T + ld_t) * D;
+        const uint32_t col = tile + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 2u;
+#pragma unroll 4
+        for (int kk = 0; kk < D; ++kk) st16(col + (uint32_t)(kk / 8) * kLBO + (uint32_t)(kk % 8) * 16u, b < B ? __ldg(src + kk) : 0.f);
+      }
+    }
+    fence_proxy_async();     // generic-proxy stores -> visible to the MMAs' async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_full0 + 8u * (uint32_t)ld_s);
+    if (fast && ld_t + 1 < T) load_step(ld_t + 1);     // in flight while this warp waits for the next ring stage
+    if (++ld_s == nst) { ld_s = 0; ++ld_n; }
+  }
+}
+
 #ifdef SVDLSTM_TC_TIMELINE
 #define TC_STAMP(slot) do { if (p.dbg != nullptr && stamp_cta && t < 64) p.dbg[t * 16 + (slot)] = clock64(); } while (0)
 #define TC_CHUNK_STAMP() do { if (p.dbg != nullptr && stamp_cta && dbg_t == 20 && dbg_n < 250) p.dbg[64 * 16 + dbg_n++] = clock64(); } while (0)
@@ -452,7 +522,10 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 // EW = epilogue warps (8, or 16 for H > 512: the cell state of NUB x 128 cells x NS sequences lives in their registers).
 // STATE = initial_state / return_state plumbing compiled in (a separate instantiation: even untaken, its extra live pointers cost
 // the epilogue-bound ranks 20 %).
-template <int NUB, bool STREAM, int NS, int EW = kEpiWarps, bool STATE = false>
+// RAWX = layer 0 may read the caller's float32 x itself (tc_raw_x_loader inlined into the input warp).  A separate instantiation:
+// the epilogue warps sit at the register cap and ANY code compiled next to them perturbs their allocation -- with the loader
+// compiled in, ranks >= 128 gain 3 % (no pack_x pass) while the epilogue-bound ranks <= 64 lose 6-18 % (measured, same box).
+template <int NUB, bool STREAM, int NS, int EW = kEpiWarps, bool STATE = false, bool RAWX = false>
 __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta) {
   constexpr int CPT = NS * 4 / EW;            // accumulator columns per epilogue thread (EW / 4 warps per TMEM lane quarter)
   constexpr int kTcThreads = 32 * (4 + EW);   // (shadow the 8-warp defaults of the file scope)
@@ -460,7 +533,6 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
   static_assert(CPT == 8 || CPT == 16 || CPT == 32, "8, 16 or 32 accumulator columns per epilogue thread");
   constexpr uint32_t kRowBlk = (uint32_t)NS * 256u;   // bytes of 128 K-rows of an activation tile (16 k-groups)
   constexpr uint32_t kK64 = (uint32_t)NS * 8u;        // descriptor-lo step of 64 K-rows (8 k-groups of NS*16 bytes)
-  constexpr uint32_t kActLBOx = (uint32_t)NS * 16u;   // bytes between consecutive k-groups (8 K rows) of an activation tile
   constexpr int kS2Bufs = NS == 32 ? 2 : 1;   // S2 accumulator buffers that fit TMEM (4 gates x NS columns each)
   extern __shared__ __align__(1024) uint8_t smem[];
   const TcSmemPlan sp = tc_plan(p);
@@ -577,57 +649,8 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     }
   } else if (warp == 3) {
     // ======================= input ring ==========================================================================
-    if (p.x_raw != nullptr) {
-      // layer 0: x(t) of this tile straight from the caller's (B, T, D) float32 array: every lane converts the rows of its
-      // sequences (n = lane, lane + 32, ...) to FP16 and scatters them into the MN-major operand tile; the ring depth (2-3
-      // steps = >10 us) hides the load latency.  Rows k >= D of the tile keep the zeros of the initial fill.
-      const int D = p.x_dim;
-      const bool vec = (D % 4) == 0;
-      int ld_s = 0;
-      uint32_t ld_n = 0;
-#pragma unroll 1
-      for (int ld_t = 0; ld_t < T; ++ld_t) {
-        if (ld_n > 0) {
-          if (lane == 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
-          __syncwarp();
-        }
-        const uint32_t tile = sbase + sp.inbuf + ld_s * in_tile;
-#pragma unroll 1
-        for (int n = lane; n < NS; n += 32) {
-          const int b = cta * NS + n;
-          const float* src = p.x_raw + ((size_t)b * T + ld_t) * D;
-          const uint32_t col = tile + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 2u;
-          if (b < p.B) {
-            if (vec) {
-#pragma unroll 1
-              for (int k = 0; k < D; k += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int kk = k + u;
-                  const __half hv = __float2half_rn(vv[u]);
-                  asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
-                }
-              }
-            } else {
-#pragma unroll 1
-              for (int kk = 0; kk < D; ++kk) {
-                const __half hv = __float2half_rn(__ldg(src + kk));
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int kk = 0; kk < D; ++kk)
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(col + (uint32_t)(kk / 8) * kActLBOx + (uint32_t)(kk % 8) * 16u), "h"((unsigned short)0) : "memory");
-          }
-        }
-        fence_proxy_async();     // generic-proxy stores -> visible to the MMAs' async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_IN_FULL + ld_s));
-        if (++ld_s == nst) { ld_s = 0; ++ld_n; }
-      }
+    if (RAWX && p.x_raw != nullptr) {
+      if constexpr (RAWX) tc_raw_x_loader<NS>(p.x_raw, p.x_dim, p.B, T, cta, sbase + sp.inbuf, in_tile, nst, bar(BAR_IN_FULL), bar(BAR_IN_EMPTY));
     } else if (lane == 0) {
       // one bulk copy per step, as early as the ring allows
       const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
@@ -1170,14 +1193,14 @@ struct TcPipeParams {
   int n_layers, n_tiles;
   int* progress;   // [n_layers][n_tiles] steps published, zeroed before the launch
 };
-template <int NUB, int NS, int EW = kEpiWarps>
+template <int NUB, int NS, int EW = kEpiWarps, bool RAWX = false>
 __global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_pipe_kernel(const __grid_constant__ TcPipeParams pp) {
   const int layer = (int)blockIdx.x / pp.n_tiles, tile = (int)blockIdx.x - layer * pp.n_tiles;
   const TcLayerParams& p = pp.layer[layer];
   const int* prog_in = layer > 0 ? pp.progress + (size_t)(layer - 1) * pp.n_tiles + tile : nullptr;
   int* prog_out = layer + 1 < pp.n_layers ? pp.progress + (size_t)layer * pp.n_tiles + tile : nullptr;
-  if (p.streaming) tc_layer_body<NUB, true, NS, EW>(p, tile, prog_in, prog_out, tile == 0);
-  else if constexpr (NUB <= 4) tc_layer_body<NUB, false, NS, EW>(p, tile, prog_in, prog_out, tile == 0);   // (H > 512 never fits resident)
+  if (p.streaming) tc_layer_body<NUB, true, NS, EW, false, RAWX>(p, tile, prog_in, prog_out, tile == 0);
+  else if constexpr (NUB <= 4 && !RAWX) tc_layer_body<NUB, false, NS, EW>(p, tile, prog_in, prog_out, tile == 0);   // (H > 512 never fits resident; RAWX is a streamed-only build)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1596,12 +1619,12 @@ static int tc_launch_layer_1024(const TcLayerParams& p, int n_cta, uint32_t smem
 static int tc_launch_pipe_1024(const void* pp, int n_cta, uint32_t smem_bytes, cudaStream_t stream);
 
 // all layers in one cooperative launch (co-residency of every CTA is what makes the inter-layer waits safe)
-template <int NUB, int NS>
+template <int NUB, int NS, bool RAWX = false>
 static int tc_launch_pipe(const TcPipeParams& pp, uint32_t smem_bytes, cudaStream_t stream) {
-  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_pipe_kernel<NUB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  SVD_CUDA_TRY(cudaFuncSetAttribute(lstm_tc_pipe_kernel<NUB, NS, kEpiWarps, RAWX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   void* args[] = {const_cast<TcPipeParams*>(&pp)};
-  SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_tc_pipe_kernel<NUB, NS>), dim3((unsigned)(pp.n_layers * pp.n_tiles)),
-                                           dim3(kTcThreads), args, smem_bytes, stream));
+  SVD_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_tc_pipe_kernel<NUB, NS, kEpiWarps, RAWX>),
+                                           dim3((unsigned)(pp.n_layers * pp.n_tiles)), dim3(kTcThreads), args, smem_bytes, stream));
   return 0;
 }
 
@@ -1801,7 +1824,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   if (ws->done == nullptr) SVD_CUDA_TRY(cudaEventCreateWithFlags(&ws->done, cudaEventDisableTiming));
   else SVD_CUDA_TRY(cudaStreamWaitEvent(stream, ws->done, 0));   // the previous forward (any stream) owns the shared scratch until then
   const int Dpad = st->layers[0].prm.Kin;
-  const size_t xbytes = getenv("SVDLSTM_TC_PACKX") ? (size_t)n_cta * T * act_tile_bytes(Dpad, ns) : 0;
+  const size_t xbytes = (size_t)n_cta * T * act_tile_bytes(Dpad, ns);   // (allocated even when this forward reads x raw: a later one may not)
   if (ws->xseq_bytes < xbytes) {
     if (ws->xseq) {
       SVD_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1837,7 +1860,13 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
   }
   // layer 0 reads the caller's float32 x itself (its input warp converts on the fly); SVDLSTM_TC_PACKX=1 restores the separate
   // packing pass + FP16 image of x (round 1: 2.8 % of the step, 368 MB of DRAM traffic per forward)
-  const bool raw_x = getenv("SVDLSTM_TC_PACKX") == nullptr;
+  // Only the 64-sequence pipelined launch of units <= 256 with a long weight stream (issue-/port-bound, ranks >= ~96) has a RAWX
+  // build: there the pass is pure overhead; the epilogue-bound ranks keep the bulk-copy loader (see tc_layer_body).
+  bool raw_x = false;
+  if (pipe && ns == 64 && getenv("SVDLSTM_TC_PACKX") == nullptr) {
+    const TcLayerParams& lp = st->layers[L - 1].prm;
+    raw_x = lp.streaming && (lp.n_chunks_u + lp.n_chunks_2) >= 32 && st->layers[0].prm.streaming;
+  }
   if (!raw_x) {
     const int D = md.input_dim;
     const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
@@ -1901,9 +1930,9 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     int lrc = -1;
     switch ((st->layers[0].prm.H / 128) * 2 + (ns == 64 ? 1 : 0)) {
       case 2: lrc = tc_launch_pipe<1, 32>(pp, pipe_smem, stream); break;
-      case 3: lrc = tc_launch_pipe<1, 64>(pp, pipe_smem, stream); break;
+      case 3: lrc = raw_x ? tc_launch_pipe<1, 64, true>(pp, pipe_smem, stream) : tc_launch_pipe<1, 64>(pp, pipe_smem, stream); break;
       case 4: lrc = tc_launch_pipe<2, 32>(pp, pipe_smem, stream); break;
-      case 5: lrc = tc_launch_pipe<2, 64>(pp, pipe_smem, stream); break;   // (16 epilogue warps measured slower here: 5.75 vs 5.55 ms at rank 64)
+      case 5: lrc = raw_x ? tc_launch_pipe<2, 64, true>(pp, pipe_smem, stream) : tc_launch_pipe<2, 64>(pp, pipe_smem, stream); break;   // (16 epilogue warps measured slower here: 5.75 vs 5.55 ms at rank 64)
       case 6: lrc = tc_launch_pipe<3, 32>(pp, pipe_smem, stream); break;
       case 8: lrc = tc_launch_pipe<4, 32>(pp, pipe_smem, stream); break;
       case 16: lrc = tc_launch_pipe_1024(&pp, L * n_cta, pipe_smem, stream); break;
@@ -1912,6 +1941,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     if (lrc != 0) return lrc;
     ++nl;
   }
+  SVD_REQUIRE(!raw_x || (pipe && ns == 64 && st->layers[0].prm.H <= 256), "tensor-core engine: internal error (raw-x forward without a raw-x kernel)");
   if (st->layers[L - 1].prm.store_h) {
     const uint8_t* last_seq = ws->seq[pipe ? L - 1 : ((L - 1) & 1)];
     if (md.n_out > 0)      // Dense top that did not fit the S1u tiles
