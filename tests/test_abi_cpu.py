@@ -78,4 +78,50 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "svdlstm_oracle" not in txt and "import oracle" not in txt, f
+                assert "svdlstm_oracle" not in txt and "import oracle" not in txt and "svdlstm_torch_ref" not in txt, f
+
+
+def test_new_entry_points_validate_on_the_host():
+    """Round-2 surface (real-time stream, trainer, batched K2b, K5): argument / model checks are host-side and run without a
+    GPU; anything that would compute refuses."""
+    lib = svdlstm.lib()
+    fake7 = (ctypes.c_void_p * 7)(*[8] * 7)
+    # a model the wavefront engine cannot hold -> the stream says why
+    big = ctypes.c_void_p()
+    assert lib.svdlstm_create(ctypes.byref(big), 1, 16, C.int_array([64])) == 0
+    assert lib.svdlstm_set_singular_weights(big, 0, 1, fake7, 16, 64) == 0
+    st = ctypes.c_void_p()
+    assert lib.svdlstm_stream_open(big, 0, ctypes.byref(st)) < 0 and b"wavefront" in lib.svdlstm_last_error()
+    # weights never set
+    h = ctypes.c_void_p()
+    assert lib.svdlstm_create(ctypes.byref(h), 2, 16, C.int_array([15, 15])) == 0
+    assert lib.svdlstm_stream_open(h, 0, ctypes.byref(st)) < 0 and b"never set" in lib.svdlstm_last_error()
+    tr = ctypes.c_void_p()
+    assert lib.svdlstm_trainer_create(h, None, ctypes.byref(tr)) < 0 and b"never set" in lib.svdlstm_last_error()
+    # trainer: only 3-factor cells; flat layout = get_weights() order per layer, then the Dense top
+    assert lib.svdlstm_set_singular_weights(h, 0, 1, fake7, 16, 15) == 0
+    assert lib.svdlstm_set_full_weights(h, 1, 8, 8, 8) == 0
+    assert lib.svdlstm_trainer_create(h, None, ctypes.byref(tr)) < 0 and b"3-factor" in lib.svdlstm_last_error()
+    assert lib.svdlstm_set_singular_weights(h, 1, 0, fake7, 15, 15) == 0          # split: 4 per-gate blocks of rank 15
+    assert lib.svdlstm_set_dense_top(h, 8, 8, 1) == 0
+    assert lib.svdlstm_trainer_create(h, C.int_array([1, 0]), ctypes.byref(tr)) == 0
+    offs = (ctypes.c_int64 * (7 * 2 + 3))()
+    assert lib.svdlstm_trainer_layout(tr, offs) == 0
+    sizes0 = [16, 15, 16 * 16, 16 * 60, 15 * 15, 15 * 60, 60]                      # merged layer: D=16, H=15
+    sizes1 = [60, 60, 15 * 60, 15 * 60, 15 * 60, 15 * 60, 60]                       # split layer: sigma (1,4k), left (D,4k), right (k,4H)
+    exp, o = [], 0
+    for sz in sizes0 + sizes1:
+        exp.append(o)
+        o += sz
+    exp += [o, o + 15, o + 16]
+    assert list(offs) == exp and lib.svdlstm_trainer_num_params(tr) == o + 16
+    if not torch.cuda.is_available():
+        assert lib.svdlstm_stream_open(h, 0, ctypes.byref(st)) != 0 and b"no CUDA device" in lib.svdlstm_last_error()
+    lib.svdlstm_trainer_destroy(tr)
+    # batched K2b / K5 argument checks
+    item = C.ReduceItem(8, 8, 8, 8, None, None, 4, 4, 3, 5, 4)                       # r > n
+    assert lib.svdlstm_reduce_factors_batched(ctypes.byref(item), 1, None) < 0
+    assert lib.svdlstm_reduce_factors_batched(None, 0, None) < 0
+    assert lib.svdlstm_scaled_matmul(8, 2, None, 8, 4, None, 3, 5, 4, 8, 4, None) < 0 and b"bad shape" in lib.svdlstm_last_error()   # lda < k
+    lib.svdlstm_destroy(h)
+    lib.svdlstm_destroy(big)
