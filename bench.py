@@ -471,6 +471,26 @@ def dropbear_delta(svdlstm, torch):
     return out
 
 
+def training_step(svdlstm, torch):
+    """The reference's fine-tune step (svd_acceleration_v3.py:117-128): shipped model as a split 3-factor model with hoyer=0.01,
+    mini-batch 32 x 200 frames, loss = mse + Hoyer, Adam -- forward with cache, BPTT, regulariser gradients and the update on
+    device (K6)."""
+    layers, dense = svdlstm.load_model_weights_npz(os.path.join(ROOT, "tests", "golden", "dropbear_weights.npz"))
+    full = svdlstm.full_model_from_weights(layers, dense, return_sequences=False)
+    sm = svdlstm.make_LSTM_singular_model(full, hoyer=0.01, orthogonal=None, merged_kernel=False)
+    sm.compile(loss="mse", optimizer="adam")
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(32, 200, 16, generator=g).cuda()
+    y = torch.randn(32, generator=g).cuda()
+    for _ in range(3):
+        sm.train_on_batch(X, y)
+    l0 = svdlstm.launches()
+    ms = timed(torch, lambda: (sm._trainer.loss_and_grad(X, y), sm._trainer.apply()), 20, warm=1)
+    return {"ms_per_step": round(ms, 3), "batch": 32, "seq_len": 200, "model": "DROPBEAR 3x15, split 3-factor, hoyer=0.01",
+            "launches_per_step": (svdlstm.launches() - l0) // 21, "steps_per_reference_epoch": 625,
+            "note": "trainable: sigma_w, sigma_u of every layer + the Dense top (train_uv=False), as in the reference"}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -683,6 +703,7 @@ def main():
         line["c4_sweep"] = c4
     if not a.no_batch1 and world == 1:
         line["batch1_us_per_step"] = batch1_table(svdlstm, torch)
+        line["training_step"] = training_step(svdlstm, torch)
     if not a.no_cpu_baseline and world == 1:
         cores = all_host_threads()
         om = cpu_oracle_model(layers, dense, a.rank)

@@ -86,7 +86,7 @@ def main():
     if os.path.exists(lb):
         shutil.copy(lb, os.path.join(P, "launches_bench_%s.csv" % R))
         per = launch_table(lb)
-        n_fw = sum(1 for (_, n) in per if "pack_x_kernel" in n) or 1
+        n_fw = sum(1 for (_, n) in per if "lstm_tc_pipe_kernel" in n) or sum(1 for (_, n) in per if "pack_x_kernel" in n) or 1
         with open(os.path.join(P, "launch_shares_%s.txt" % R), "w") as f:
             f.write("# %s; bench.py --steps 3 --warmup 3 (profiled region = warm-up + timed forwards = %d forwards), C3 rank 128; ncu launch list: cold-cache, serialised\n" % (stamp, n_fw))
             agg, tot = shares(per, n_fw, f)
