@@ -377,3 +377,22 @@ def test_tc_sees_dense_and_variable_updates(oracle):
     _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "after Variable.assign")
     m.layers[-1].layer.bias.assign(np.array([1.25], np.float32))
     _check(m.predict(x, engine="tc"), oracle_twin(oracle, m).predict(x), "after Dense bias assign")
+
+
+@pytest.mark.parametrize("D", [16, 10, 24])
+def test_tc_raw_x_loader_paths(oracle, D):
+    """The 64-sequence pipelined launch with a long weight stream reads the caller's float32 x itself (RAWX kernel build):
+    vectorised register path (D % 4 == 0, D <= 16), generic path (D = 10: unaligned rows; D = 24: more than four float4 per row),
+    ragged last tile.  Same rows through the small-batch launch (bulk-copy loader + pack_x) must agree to FP32 rounding of the
+    Dense sum, and both with the float64 oracle."""
+    layers, dense = svdlstm.synthetic_layers(D, 256, 2, seed=3)
+    full = svdlstm.full_model_from_weights(layers, dense)
+    sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True, return_sequences=True)
+    m = svdlstm.truncate_singular_model(sm, 128)
+    x = torch.randn(2400 + 37, 5, D, generator=torch.Generator().manual_seed(31)).cuda()     # 39 tiles of 64 per layer: pipelined, ragged
+    y = m(x, engine="tc")
+    idx = torch.tensor([0, 63, 64, 1000, 2399, 2400, 2436]).cuda()
+    y_small = m(x[idx].contiguous(), engine="tc")
+    assert float((y_small - y[idx]).abs().max()) < 2e-6
+    _check(y[idx].cpu().numpy(), oracle_twin(oracle, m).predict(x[idx].cpu().numpy()), "tc raw-x D=%d" % D)
+    assert torch.equal(m(x, engine="tc"), y)
