@@ -285,6 +285,8 @@ struct TcLayerParams {
   int n_slots_w, n_slots_u, n_slots_2;
   const float* bias;        // [nub][4][128]; gates i,f,o pre-scaled by 0.5 (sigmoid(x) = 0.5 tanh(x/2) + 0.5)
   const uint8_t* in_seq;    // activation tile images [cta][t], K = Kin
+  int in_ring, out_ring;    // layer-pipelined launch: the hand-off images are RINGS of this many steps per tile (0 = one slot per step).
+                            // The layers run a few steps apart, so a short ring stays L2-resident: the hidden sequence never goes to HBM.
   const float* x_raw;       // layer 0: the caller's x (B, T, D) float32 -- read and converted by the input warp itself (no pack_x pass,
   int x_dim;                //          no FP16 image of x in HBM); nullptr: bulk copies from in_seq
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
@@ -526,7 +528,8 @@ __device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, int
 // the epilogue warps sit at the register cap and ANY code compiled next to them perturbs their allocation -- with the loader
 // compiled in, ranks >= 128 gain 3 % (no pack_x pass) while the epilogue-bound ranks <= 64 lose 6-18 % (measured, same box).
 template <int NUB, bool STREAM, int NS, int EW = kEpiWarps, bool STATE = false, bool RAWX = false>
-__device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta) {
+__device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int cta, const int* prog_in, int* prog_out, const bool stamp_cta,
+                                              int* cons_pub = nullptr, const int* cons_wait = nullptr) {
   constexpr int CPT = NS * 4 / EW;            // accumulator columns per epilogue thread (EW / 4 warps per TMEM lane quarter)
   constexpr int kTcThreads = 32 * (4 + EW);   // (shadow the 8-warp defaults of the file scope)
   constexpr int kEpiThreads = 32 * EW;
@@ -653,7 +656,8 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
       if constexpr (RAWX) tc_raw_x_loader<NS>(p.x_raw, p.x_dim, p.B, T, cta, sbase + sp.inbuf, in_tile, nst, bar(BAR_IN_FULL), bar(BAR_IN_EMPTY));
     } else if (lane == 0) {
       // one bulk copy per step, as early as the ring allows
-      const uint8_t* src = p.in_seq + (size_t)cta * T * in_tile;
+      const int iring = p.in_ring;
+      const uint8_t* src = p.in_seq + (size_t)cta * (iring ? iring : T) * in_tile;
       int ld_s = 0;          // ring stage of the next tile to load
       uint32_t ld_n = 0;     // how many times that stage has been used
 #pragma unroll 1
@@ -666,9 +670,14 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
           }
           fence_proxy_async_all();   // the tile was written through the async proxy of another SM
         }
-        if (ld_n > 0) mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
+        if (ld_n > 0) {
+          mbar_wait(bar(BAR_IN_EMPTY + ld_s), (ld_n - 1u) & 1u);
+          // the MMAs that read the tile of step ld_t - nst have completed, so its copy out of the hand-off ring has too:
+          // tell the producing layer that those ring slots may be overwritten
+          if (cons_pub != nullptr) st_release_gpu(cons_pub, ld_t - nst + 1);
+        }
         mbar_expect_tx(bar(BAR_IN_FULL + ld_s), in_tile);
-        bulk_g2s(sbase + sp.inbuf + ld_s * in_tile, src + (size_t)ld_t * in_tile, in_tile, bar(BAR_IN_FULL + ld_s));
+        bulk_g2s(sbase + sp.inbuf + ld_s * in_tile, src + (size_t)(iring ? ld_t % iring : ld_t) * in_tile, in_tile, bar(BAR_IN_FULL + ld_s));
         if (++ld_s == nst) { ld_s = 0; ++ld_n; }
       }
     }
@@ -677,12 +686,18 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
     if (lane == 0 && (p.store_h || p.store_x)) {
       const uint32_t o_tile = p.store_x ? act_tile_bytes(p.rx_pad, NS) : h_tile;   // what is handed over: t_w(t) of the next layer, or h(t)
       const uint32_t o_src = sbase + (p.store_x ? sp.xbuf : sp.hbuf);
-      uint8_t* out = p.out_seq + (size_t)cta * T * o_tile;
+      const int oring = p.out_ring;
+      uint8_t* out = p.out_seq + (size_t)cta * (oring ? oring : T) * o_tile;
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        // tile t complete in smem -> ship it to HBM, then let the epilogue overwrite the buffer
+        // tile t complete in smem -> ship it to the hand-off image, then let the epilogue overwrite the buffer
         mbar_wait(bar(BAR_H_DONE), (uint32_t)(t & 1));
-        bulk_s2g(out + (size_t)t * o_tile, o_src, o_tile);
+        if (oring && t >= oring && cons_wait != nullptr && ld_acquire_gpu(cons_wait) < t - oring + 1) {   // ring slot still unread downstream
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(cons_wait) < t - oring + 1)
+            if (clock64() - t0 > 8000000000LL) __trap();
+        }
+        bulk_s2g(out + (size_t)(oring ? t % oring : t) * o_tile, o_src, o_tile);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar(BAR_H_STORED));
@@ -1192,6 +1207,7 @@ struct TcPipeParams {
   TcLayerParams layer[kMaxLayers];
   int n_layers, n_tiles;
   int* progress;   // [n_layers][n_tiles] steps published, zeroed before the launch
+  int* consumed;   // [n_layers][n_tiles] steps of its INPUT hand-off ring a layer has finished reading, zeroed before the launch
 };
 template <int NUB, int NS, int EW = kEpiWarps, bool RAWX = false>
 __global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_pipe_kernel(const __grid_constant__ TcPipeParams pp) {
@@ -1199,8 +1215,10 @@ __global__ void __launch_bounds__(32 * (4 + EW), 1) lstm_tc_pipe_kernel(const __
   const TcLayerParams& p = pp.layer[layer];
   const int* prog_in = layer > 0 ? pp.progress + (size_t)(layer - 1) * pp.n_tiles + tile : nullptr;
   int* prog_out = layer + 1 < pp.n_layers ? pp.progress + (size_t)layer * pp.n_tiles + tile : nullptr;
-  if (p.streaming) tc_layer_body<NUB, true, NS, EW, false, RAWX>(p, tile, prog_in, prog_out, tile == 0);
-  else if constexpr (NUB <= 4 && !RAWX) tc_layer_body<NUB, false, NS, EW>(p, tile, prog_in, prog_out, tile == 0);   // (H > 512 never fits resident; RAWX is a streamed-only build)
+  int* cons_pub = layer > 0 ? pp.consumed + (size_t)layer * pp.n_tiles + tile : nullptr;
+  const int* cons_wait = layer + 1 < pp.n_layers ? pp.consumed + (size_t)(layer + 1) * pp.n_tiles + tile : nullptr;
+  if (p.streaming) tc_layer_body<NUB, true, NS, EW, false, RAWX>(p, tile, prog_in, prog_out, tile == 0, cons_pub, cons_wait);
+  else if constexpr (NUB <= 4 && !RAWX) tc_layer_body<NUB, false, NS, EW>(p, tile, prog_in, prog_out, tile == 0, cons_pub, cons_wait);   // (H > 512 never fits resident; RAWX is a streamed-only build)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1833,9 +1851,15 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     SVD_CUDA_TRY(cudaMalloc(&ws->xseq, xbytes));
     ws->xseq_bytes = xbytes;
   }
+  // Hand-off rings (pipelined launch): the layers run a few steps apart (ring stages + one step of pipeline skew), so 32 steps per
+  // tile are ample; C3 rank 128: 64 tiles x 32 x 16 KB = 32 MB, L2-resident (SVDLSTM_TC_RING=0: one slot per step, as in round 1).
+  int ring = 32;
+  if (const char* e = getenv("SVDLSTM_TC_RING")) ring = atoi(e);
+  if (ring < 4 || ring >= T) ring = 0;
   for (int l = 0; l < L; ++l) {
     if (!st->layers[l].prm.store_h && !st->layers[l].prm.store_x) continue;
-    const size_t hb = (size_t)n_cta * T * (st->layers[l].prm.store_x ? act_tile_bytes(st->layers[l].prm.rx_pad, ns) : act_tile_bytes(st->layers[l].prm.H, ns));
+    const int steps = (pipe && l + 1 < L && ring > 0) ? ring : T;      // inter-layer hand-off of a pipelined launch: a ring
+    const size_t hb = (size_t)n_cta * steps * (st->layers[l].prm.store_x ? act_tile_bytes(st->layers[l].prm.rx_pad, ns) : act_tile_bytes(st->layers[l].prm.H, ns));
     const int slot = pipe ? l : (l & 1);
     if (ws->seq_bytes[slot] < hb) {
       if (ws->seq[slot]) {
@@ -1847,7 +1871,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     }
   }
   if (pipe) {
-    const size_t need = (size_t)L * n_cta;
+    const size_t need = (size_t)2 * L * n_cta;     // [published | consumed]
     if (ws->progress_elems < need) {
       if (ws->progress) {
         SVD_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1888,6 +1912,8 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     p.dbg = dbg_env ? dbg_buf + (size_t)l * kDbgPerLayer : nullptr;
     const int in_slot = pipe ? l - 1 : ((l - 1) & 1), out_slot = pipe ? l : (l & 1);
     p.in_seq = (l == 0) ? ws->xseq : ws->seq[in_slot];
+    p.in_ring = (pipe && l > 0) ? ring : 0;
+    p.out_ring = (pipe && l + 1 < L) ? ring : 0;
     p.x_raw = (l == 0 && raw_x) ? a.x : nullptr;
     p.x_dim = md.input_dim;
     p.out_seq = (p.store_h || p.store_x) ? ws->seq[out_slot] : nullptr;
@@ -1927,6 +1953,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     pp.n_layers = L;
     pp.n_tiles = n_cta;
     pp.progress = ws->progress;
+    pp.consumed = ws->progress + (size_t)L * n_cta;
     int lrc = -1;
     switch ((st->layers[0].prm.H / 128) * 2 + (ns == 64 ? 1 : 0)) {
       case 2: lrc = tc_launch_pipe<1, 32>(pp, pipe_smem, stream); break;
