@@ -112,6 +112,11 @@ def test_adam_steps_and_fit(dropbear_weights):
     assert np.isfinite(y_r).all() and np.abs(y_r - y_s).max() < 0.25
     # the in-place update reached the inference engines of this model
     assert np.allclose(sm2.predict(Xm[:8], engine="general"), sm2.predict(Xm[:8], engine="wavefront"), atol=2e-5)
+    # the reference's own validation call: a last-step model against the whole target series of ONE long sequence (Keras broadcasts)
+    Xl = rng.standard_normal((1, 500, 16)).astype(np.float32)
+    yl = rng.standard_normal((1, 500, 1)).astype(np.float32)
+    v = sm2.evaluate(Xl, yl)
+    assert abs(v - float(np.mean((sm2.predict(Xl).reshape(1, 1, 1) - yl) ** 2))) < 1e-5 * v
     with pytest.raises(RuntimeError, match="compile"):
         svdlstm.make_LSTM_singular_model(full).fit(Xm, ym)
     with pytest.raises(ValueError, match="SingularLSTMCell"):
