@@ -349,6 +349,10 @@ def batch1_table(svdlstm, torch):
                               "frac_of_floor": round(floor_us / out["3F_r15"], 3), "chain_cycles": chain,
                               "factored_order": {"cycles": sum(chain_factored.values()), "us": round(sum(chain_factored.values()) / 1965.0, 4),
                                                  "measured_us": factored_out.get("3F_r15"), "chain_cycles": chain_factored},
+                              "measured_timeline_cycles": {"lds_inputs": 41, "fused_contraction_32_ffma2_14_fadd": 104, "gate_ex2_rcp": 51, "shuffle_gather": 16,
+                                                           "cell_update_tanh_c_sts": 82, "tail": 24, "barrier_release_and_loop": 180,
+                                                           "how": "clock64 stamps in the layer-0 warp of a debug build (DESIGN.md section 4.2); the FP32 pipe "
+                                                                  "issues one FFMA2 per 2 clocks per scheduler, so the contraction is issue-bound at ~64 + adds"},
                               "note": "one layer-tick is one dependent chain (the L layers overlap as a wavefront); this, not a memory pipe, bounds batch 1"},
             "streaming": out_streaming, "realtime_budget_us": 400.0}
 
