@@ -324,14 +324,17 @@ def batch1_table(svdlstm, torch):
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("b1_wavefront", {})
     except Exception:
         ncu = {}
-    # Dependent chain of ONE layer-tick of the wavefront kernel (what bounds batch 1: weights are register-resident, so neither
-    # HBM nor the shared-memory port is), from the latencies of the microarchitecture guide: LDS 29, FFMA/FFMA2 4, MUFU ~20,
-    # SHFL ~25, STS->LDS hand-over ~35, CTA barrier ~40 cycles.
-    chain = {"lds_inputs": 29, "fused_contraction_4_dependent_ffma2_plus_adds": 28, "gate_ex2_rcp_fma": 52, "shuffle_gather": 25,
-             "cell_update_fma": 8, "tanh_c_ex2_rcp_fma": 52, "h_mul_sts": 14, "cta_barrier": 40}
+    # Dependent chain of ONE layer-step of the wavefront kernel (what bounds batch 1: weights are register-resident, so neither
+    # HBM nor the shared-memory port is).  Two figures: an ESTIMATE from the microarchitecture guide's latencies (LDS 29, FFMA/FFMA2 4,
+    # CTA barrier ~40; MUFU and SHFL are not in the guide: 20 and 25 assumed) and the MEASURED split of a step (clock64 stamps in the
+    # layer-0 warp of a debug build).  The measured chain is ~60 instructions long -- 16 FFMA2, 4 MUFU in two
+    # dependent pairs, one shuffle, one shared-memory round trip of h -- so its ~410 cycles are latency, not issue: the kernel sits
+    # at the dependent-latency floor of this formulation; the barrier is paid once per 4 steps.
+    chain = {"lds_h": 29, "recurrent_contraction_4_dependent_ffma2_plus_adds": 28, "gate_ex2_rcp_fma": 52, "shuffle_gather": 25,
+             "cell_update_fma": 8, "tanh_c_ex2_rcp_fma": 52, "h_mul_sts_syncwarp": 14, "cta_barrier_per_4_steps": 10}
     chain_factored = {"lds_inputs": 29, "stage1_8_dependent_ffma2_plus_adds": 40, "p_through_smem_sts_syncwarp_lds": 35,
                       "stage2_8_dependent_ffma2_plus_adds": 40, "gate_ex2_rcp_fma": 52, "shuffle_gather": 25, "cell_update_fma": 8,
-                      "tanh_c_ex2_rcp_fma": 52, "h_mul_sts": 14, "cta_barrier": 40}
+                      "tanh_c_ex2_rcp_fma": 52, "h_mul_sts_syncwarp": 14, "cta_barrier_per_4_steps": 10}
     floor_cycles = sum(chain.values())
     floor_us = floor_cycles / 1965.0
     return {"unit": "us/timestep", "T": T, "model": "DROPBEAR 3x15 LSTM + Dense(1), batch 1", "us_per_step": out,
@@ -349,10 +352,12 @@ def batch1_table(svdlstm, torch):
                               "frac_of_floor": round(floor_us / out["3F_r15"], 3), "chain_cycles": chain,
                               "factored_order": {"cycles": sum(chain_factored.values()), "us": round(sum(chain_factored.values()) / 1965.0, 4),
                                                  "measured_us": factored_out.get("3F_r15"), "chain_cycles": chain_factored},
-                              "measured_timeline_cycles": {"lds_inputs": 41, "fused_contraction_32_ffma2_14_fadd": 104, "gate_ex2_rcp": 51, "shuffle_gather": 16,
-                                                           "cell_update_tanh_c_sts": 82, "tail": 24, "barrier_release_and_loop": 180,
-                                                           "how": "clock64 stamps in the layer-0 warp of a debug build (DESIGN.md section 4.2); the FP32 pipe "
-                                                                  "issues one FFMA2 per 2 clocks per scheduler, so the contraction is issue-bound at ~64 + adds"},
+                              "measured_timeline_cycles_one_step_per_barrier": {"lds_inputs": 41, "fused_contraction_32_ffma2_14_fadd": 104, "gate_ex2_rcp": 51,
+                                                                                "shuffle_gather": 16, "cell_update_tanh_c_sts": 82, "tail": 24,
+                                                                                "barrier_release_and_loop": 180,
+                                                                                "how": "clock64 stamps in the layer-0 warp of a debug build, before the barrier was amortised "
+                                                                                       "over 4 steps (tick 498 cycles then; DESIGN.md section 4.2)"},
+                              "measured_cycles_per_step": round(out["3F_r15"] * 1965.0, 1),
                               "note": "one layer-tick is one dependent chain (the L layers overlap as a wavefront); this, not a memory pipe, bounds batch 1"},
             "streaming": out_streaming, "realtime_budget_us": 400.0}
 

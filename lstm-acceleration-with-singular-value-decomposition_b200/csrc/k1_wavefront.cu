@@ -25,9 +25,15 @@ namespace svdlstm {
 
 namespace {
 
+// One CTA barrier costs about as much as one layer-step's whole dependent chain (measured: ~180 of a 498-cycle tick), so a
+// wavefront tick covers kSteps consecutive timesteps per layer: the recurrence inside a tick needs only a __syncwarp (a layer
+// is one warp), and the barrier is paid once per kSteps.
+constexpr int kSteps = 4;       // timesteps per wavefront tick and layer
+constexpr int kHRing = 2 * kSteps;   // h_l ring: the half being written this tick + the half the next layer reads
 constexpr int kXRing = 32;      // x_t ring depth (steps)
-constexpr int kPrefetch = 12;   // cp.async distance (ticks)
+constexpr int kPrefetch = 5;    // cp.async distance (ticks of kSteps steps): (kPrefetch + 1) * kSteps <= kXRing
 constexpr int kYRing = 32;      // y staging before a coalesced store
+static_assert((kPrefetch + 1) * kSteps <= kXRing && kYRing % kSteps == 0, "ring sizes");
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 // row stride (floats): multiple of 4 with an odd number of 16-byte units => conflict-free LDS.128
@@ -100,7 +106,7 @@ __host__ __device__ inline bool wf_make_plan(const ModelDesc& md, WfPlan& pl, bo
     w.off_scale = off;   off += w.P_pad;
     w.off_bias = off;    off += round4(4 * w.H);
     w.off_p = off;       off += w.P_pad + 64;   // + zero tail: stage 2 reads a full K4*4 window
-    w.off_vh = off;      off += 2 * w.S1;   // double-buffered h_l (zero padded to S1)
+    w.off_vh = off;      off += kHRing * w.S1;   // ring of h_l(t) slots, slot = t % kHRing (zero padded to S1)
     w.off_qmeta = off;   off += w.P_pad;    // per-q: bit0 from_h, bits 8.. = padded input length
     w.WS = 2 * round4(w.H > w.Din ? w.H : w.Din);
     w.off_we = off;      off += dense ? 4 * w.H * w.WS : 0;
@@ -244,8 +250,8 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
       // initial h into slot 1 (= slot of timestep -1)
       if (a.h0 != nullptr)
         for (int j = tid; j < H; j += nthr) {
-          smem[w.off_vh + w.S1 + j] = a.h0[soff + (size_t)b * H + j];
-          if (STREAM) smem[w.off_vh + j] = a.h0[soff + (size_t)b * H + j];   // a resumed stream may start on an odd step
+          for (int sl = 0; sl < kHRing; ++sl)      // h(-1) lives in slot kHRing-1; a resumed stream may start on any step
+            if (STREAM || sl == kHRing - 1) smem[w.off_vh + sl * w.S1 + j] = a.h0[soff + (size_t)b * H + j];
         }
       soff += (size_t)B * H;
     }
@@ -355,13 +361,16 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   }
   const float* xrow_base = a.x;
   const int off_x = pl.off_x, xstride = pl.xstride;
-  // loader prologue: prefetch the first kPrefetch steps
+  // loader prologue: prefetch the first kPrefetch ticks (kSteps steps each, one cp.async group per tick)
   if (!STREAM && role == 0) {
-    for (int s = 0; s < kPrefetch; ++s) {
-      if (s < T && lane < D) {
-        const int t = backwards ? (T - 1 - s) : s;
-        const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
-        cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
+    for (int tk = 0; tk < kPrefetch; ++tk) {
+      for (int u = 0; u < kSteps; ++u) {
+        const int s = tk * kSteps + u;
+        if (s < T && lane < D) {
+          const int t = backwards ? (T - 1 - s) : s;
+          const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
+          cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
+        }
       }
       cp_async_commit();
     }
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   }
   __syncthreads();
 
-  const int n_ticks = T + L;
+  const int n_ticks = (T + kSteps - 1) / kSteps + L;
   const int HL = pl.layers[L - 1].H;
   const int n_out = md.n_out;
   const int n_y = n_out > 0 ? 1 : HL;
@@ -385,39 +394,60 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   const float dense_w = (role == L + 1 && n_out > 0 && lane < HL) ? smem[off_dense + lane] : 0.f;
   const float dense_b = (n_out > 0) ? smem[off_dense + 32] : 0.f;
 
-  // one step of the layer this warp owns: `step` selects the double-buffered h slots, `xslot` the x ring slot (layer 0)
-  auto layer_step = [&](const int step, const int xslot) {
-        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? xslot : (step & 1)) * vin_sb;
-        const unsigned ha = vh_addr + (unsigned)((step + 1) & 1) * vh_sb;       // h_l(step-1)
-        const unsigned ho = vh_addr + (unsigned)(step & 1) * vh_sb + 4u * (unsigned)j;
+  // dense mode, input side of a step: zx = bias + x_t . W_eff[input part].  No recurrence: the wavefront tick computes it for all
+  // of its kSteps steps up front (pure issue-bound FFMA2 work), which takes it off the dependent chain of every step.
+  auto dense_x = [&](const int step, const int xslot, float (&zx)[G]) {
+        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? xslot : (step % kHRing)) * vin_sb;
+        float4 vi[KIN4];
+#pragma unroll
+        for (int i = 0; i < KIN4; ++i) vi[i] = lds128(va + 16u * i);
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          f2_t a0 = pack2(bias2[gi], 0.f), a1 = 0ull;
+#pragma unroll
+          for (int i = 0; i < KIN4; ++i) {
+            a0 = ffma2(pack2(vi[i].x, vi[i].y), wd[gi][2 * i + 0], a0);
+            a1 = ffma2(pack2(vi[i].z, vi[i].w), wd[gi][2 * i + 1], a1);
+          }
+          float s0, s1, s2, s3;
+          unpack2(a0, s0, s1);
+          unpack2(a1, s2, s3);
+          zx[gi] = (s0 + s1) + (s2 + s3);
+        }
+  };
+  // one step of the layer this warp owns: `step` selects the h ring slots, `xslot` the x ring slot (layer 0); dense mode: zx = the
+  // input side of this step from dense_x
+  auto layer_step = [&](const int step, const int xslot, const float (&zx)[G]) {
+        const unsigned va = vin_addr + (unsigned)((lyr == 0) ? xslot : (step % kHRing)) * vin_sb;
+        const unsigned ha = vh_addr + (unsigned)((step + kHRing - 1) % kHRing) * vh_sb;       // h_l(step-1)
+        const unsigned ho = vh_addr + (unsigned)(step % kHRing) * vh_sb + 4u * (unsigned)j;
+        float zz[G];
+        if constexpr (DENSE) {
+          // ---- recurrent side: z = zx + h(t-1) . W_eff[recurrent part], two independent FFMA2 chains of depth KIN4 per gate ----
+          float4 vh[KIN4];
+#pragma unroll
+          for (int i = 0; i < KIN4; ++i) vh[i] = lds128(ha + 16u * i);
+#pragma unroll
+          for (int gi = 0; gi < G; ++gi) {
+            f2_t b0 = pack2(zx[gi], 0.f), b1 = 0ull;
+#pragma unroll
+            for (int i = 0; i < KIN4; ++i) {
+              b0 = ffma2(pack2(vh[i].x, vh[i].y), wd[gi][KIN4 * 2 + 2 * i + 0], b0);
+              b1 = ffma2(pack2(vh[i].z, vh[i].w), wd[gi][KIN4 * 2 + 2 * i + 1], b1);
+            }
+            float u0, u1, u2, u3;
+            unpack2(b0, u0, u1);
+            unpack2(b1, u2, u3);
+            zz[gi] = (u0 + u1) + (u2 + u3);
+          }
+        } else {
+        // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
         float4 vi[KIN4], vh[KIN4];
 #pragma unroll
         for (int i = 0; i < KIN4; ++i) {
           vi[i] = lds128(va + 16u * i);
           vh[i] = lds128(ha + 16u * i);
         }
-        float zz[G];
-        if constexpr (DENSE) {
-          // ---- one fused contraction: z = bias + [x_t | h(t-1)] . W_eff, four independent FFMA2 chains of depth KIN4 per gate ----
-#pragma unroll
-          for (int gi = 0; gi < G; ++gi) {
-            f2_t a0 = pack2(bias2[gi], 0.f), a1 = 0ull, b0 = 0ull, b1 = 0ull;
-#pragma unroll
-            for (int i = 0; i < KIN4; ++i) {
-              a0 = ffma2(pack2(vi[i].x, vi[i].y), wd[gi][2 * i + 0], a0);
-              a1 = ffma2(pack2(vi[i].z, vi[i].w), wd[gi][2 * i + 1], a1);
-              b0 = ffma2(pack2(vh[i].x, vh[i].y), wd[gi][KIN4 * 2 + 2 * i + 0], b0);
-              b1 = ffma2(pack2(vh[i].z, vh[i].w), wd[gi][KIN4 * 2 + 2 * i + 1], b1);
-            }
-            float s0, s1, s2, s3, u0, u1, u2, u3;
-            unpack2(a0, s0, s1);
-            unpack2(a1, s2, s3);
-            unpack2(b0, u0, u1);
-            unpack2(b1, u2, u3);
-            zz[gi] = ((s0 + s1) + (s2 + s3)) + ((u0 + u1) + (u2 + u3));
-          }
-        } else {
-        // ---- stage 1: p[q] = scale * <v, LT[q,:]> ----------------------------------------------
 #pragma unroll
         for (int m = 0; m < MP; ++m) {
           f2_t a0 = 0ull, a1 = 0ull;
@@ -496,7 +526,7 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
         if (sub == 0 && j < H) sts32(ho, h_last);
   };
   auto output_step = [&](const int step) {
-        const float* hv = &smem[out_vh_off + (step & 1) * out_vh_stride];
+        const float* hv = &smem[out_vh_off + (step % kHRing) * out_vh_stride];
         if (n_out > 0) {
           float v = (lane < HL) ? hv[lane] * dense_w : 0.f;
 #pragma unroll
@@ -534,21 +564,46 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
   if constexpr (!STREAM) {
     for (int tick = 0; tick < n_ticks; ++tick) {
       if (role == 0) {
-        // ---- loader: x for step tick+kPrefetch -------------------------------------------------
-        const int s = tick + kPrefetch;
-        if (s < T && lane < D) {
-          const int t = backwards ? (T - 1 - s) : s;
-          const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
-          cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
+        // ---- loader: x for the steps of tick + kPrefetch -----------------------------------------
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+          const int s = (tick + kPrefetch) * kSteps + u;
+          if (s < T && lane < D) {
+            const int t = backwards ? (T - 1 - s) : s;
+            const float* src = time_major ? xrow_base + ((size_t)t * B + b) * D + lane : xrow_base + ((size_t)b * T + t) * D + lane;
+            cp_async4(&smem[off_x + (s % kXRing) * xstride + lane], src);
+          }
         }
         cp_async_commit();
-        cp_async_wait<kPrefetch - 2>();   // everything up to step tick+1 has landed before the barrier
+        cp_async_wait<kPrefetch - 2>();   // everything up to the steps of tick+1 has landed before the barrier
       } else if (is_layer) {
-        const int step = tick - lyr;
-        if (step >= 0 && step < T) layer_step(step, step % kXRing);
+        const int s0 = (tick - lyr) * kSteps;
+        if (s0 >= 0) {
+#pragma unroll 1
+          float zx[kSteps][G];
+          if constexpr (DENSE) {
+#pragma unroll
+            for (int u = 0; u < kSteps; ++u) dense_x(s0 + u, (s0 + u) % kXRing, zx[u]);   // (steps >= T read stale ring slots: unused)
+          }
+#pragma unroll
+          for (int u = 0; u < kSteps; ++u) {
+            const int step = s0 + u;
+            if (step < T) {
+              layer_step(step, step % kXRing, zx[u]);
+              __syncwarp();     // h_l(step) written by this warp's lanes is read by all of them in the next step
+            }
+          }
+        }
       } else if (role == L + 1) {
-        const int step = tick - L;
-        if (step >= 0 && step < T) output_step(step);
+        const int s0 = (tick - L) * kSteps;
+        if (s0 >= 0) {
+#pragma unroll 1
+          for (int u = 0; u < kSteps; ++u) {
+            const int step = s0 + u;
+            if (step >= T) break;
+            output_step(step);
+          }
+        }
       }
       __syncthreads();
     }
@@ -595,7 +650,11 @@ __global__ void __launch_bounds__(256, 1) lstm_wavefront_kernel(const ModelDesc*
       if (s_exit) break;
       const int step = (int)(seq & 0x7fffffffu);
       for (int sub = 0; sub <= L; ++sub) {
-        if (is_layer && lyr == sub) layer_step(step, 0);
+        if (is_layer && lyr == sub) {
+          float zx[G];
+          if constexpr (DENSE) dense_x(step, 0, zx);
+          layer_step(step, 0, zx);
+        }
         else if (role == L + 1 && sub == L) output_step(step);
         __syncthreads();
       }
