@@ -231,12 +231,8 @@ def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
     n = int(np.prod(shape))
     blk = _PinnedBlock(max(4 * n, 4), write_combined)
     buf = (ctypes.c_float * n).from_address(blk.p.value)
-    arr = np.ctypeslib.as_array(buf).reshape(shape)
-    t = torch.from_numpy(arr)
-    t._svdlstm_block = blk          # keeps the allocation alive as long as this tensor object
-    arr_owner = getattr(t, "_svdlstm_block")
-    assert arr_owner is blk
-    return t
+    buf._svdlstm_block = blk        # lifetime: torch storage -> ndarray -> ctypes view -> block (views of the tensor keep it alive too)
+    return torch.from_numpy(np.ctypeslib.as_array(buf).reshape(shape))
 
 
 def add_launches(n: int) -> None:
