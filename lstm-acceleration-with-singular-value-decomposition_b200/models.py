@@ -256,7 +256,8 @@ class Sequential:
         A serving loop keeps two requests in flight: the host->device copy of request i+1 (own copy stream, second device
         buffer) overlaps the forward pass of request i, and each result is copied into one of two pinned host buffers on
         the compute stream.  ``.result()`` returns a numpy VIEW of that pinned buffer, valid until the second-next request
-        of the same shape is issued (copy it to keep it longer)."""
+        of the same shape is issued (copy it to keep it longer).  A host input must stay unmodified until ``.result()``
+        returns (its copy to the device is asynchronous when the buffer is pinned)."""
         dev = C.require_cuda()
         if isinstance(X, torch.Tensor) and X.is_cuda:
             y = self.__call__(X, engine=engine)
