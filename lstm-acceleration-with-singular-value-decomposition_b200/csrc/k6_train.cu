@@ -30,6 +30,8 @@ struct TrBlock {
   const float* scale;
   const float* right;
   int left_ld, right_ld, rank, ncols, out0, from_h, p_off;
+  int g_left_ld, g_right_ld;            // row strides of the weight tensors = of their gradients (left_ld / right_ld change when
+                                        // the kernel stages the block compactly in shared memory)
   long long g_left, g_scale, g_right;   // offsets into the flat gradient vector, -1 = not trainable
 };
 struct TrLayer {
@@ -47,6 +49,7 @@ struct TrModel {
   long long n_params;
   long long cache_stride;   // floats per (sequence, step)
   int max_units, max_p, max_in;
+  int stage_floats;         // > 0: every weight of the model fits shared memory (this many floats) and is staged there once per launch
   TrLayer layers[kMaxLayers];
 };
 
@@ -88,6 +91,47 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
   float* yp = ypred + (size_t)b * n_steps_out * n_y;
 
   for (int i = tid; i < 4 * L * HM; i += kTrThreads) hst[i] = 0.f;   // hst, cst, dhn, dcn
+  // Small models (the reference's 3 x 15 fine-tune): every factor, bias and the Dense top are copied ONCE into shared memory,
+  // compactly per block, and the block table (itself in shared memory) is re-pointed at the copies: the ~10 dependent phases
+  // of a layer-step then wait on shared-memory instead of L2 latencies.  The gradient strides keep the tensors' own layout.
+  if (M.stage_floats > 0) {
+    float* wbuf = dy + (M.n_out > 0 ? M.n_out : HM) + 8;
+    __syncthreads();
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+      TrLayer& Ly = M.layers[l];
+      for (int bi = 0; bi < Ly.n_blocks; ++bi) {
+        TrBlock& bk = Ly.blocks[bi];
+        const int n_in = bk.from_h ? Ly.units : Ly.d_in;
+        float* l_s = wbuf + off;
+        float* s_s = l_s + n_in * bk.rank;
+        float* r_s = s_s + bk.rank;
+        for (int idx = tid; idx < n_in * bk.rank; idx += kTrThreads) l_s[idx] = bk.left[(size_t)(idx / bk.rank) * bk.left_ld + idx % bk.rank];
+        for (int idx = tid; idx < bk.rank; idx += kTrThreads) s_s[idx] = bk.scale[idx];
+        for (int idx = tid; idx < bk.rank * bk.ncols; idx += kTrThreads) r_s[idx] = bk.right[(size_t)(idx / bk.ncols) * bk.right_ld + idx % bk.ncols];
+        off += n_in * bk.rank + bk.rank + bk.rank * bk.ncols;
+        __syncthreads();
+        if (tid == 0) {
+          bk.left = l_s; bk.scale = s_s; bk.right = r_s;
+          bk.left_ld = bk.rank; bk.right_ld = bk.ncols;
+        }
+      }
+      float* b_s = wbuf + off;
+      for (int idx = tid; idx < 4 * Ly.units; idx += kTrThreads) b_s[idx] = Ly.bias[idx];
+      off += 4 * Ly.units;
+      __syncthreads();
+      if (tid == 0) Ly.bias = b_s;
+    }
+    if (M.n_out > 0) {
+      const int HL = M.layers[L - 1].units;
+      float* k_s = wbuf + off;
+      float* d_s = k_s + HL * M.n_out;
+      for (int idx = tid; idx < HL * M.n_out; idx += kTrThreads) k_s[idx] = M.dense_kernel[idx];
+      for (int idx = tid; idx < M.n_out; idx += kTrThreads) d_s[idx] = M.dense_bias[idx];
+      __syncthreads();
+      if (tid == 0) { M.dense_kernel = k_s; M.dense_bias = d_s; }
+    }
+  }
   __syncthreads();
 
   // =============================== forward ===============================
@@ -251,7 +295,7 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
         }
         if (bk.g_right >= 0) {
           const float sq = bk.scale[kk] * q[k];
-          float* grow = gp + bk.g_right + (size_t)kk * bk.right_ld;
+          float* grow = gp + bk.g_right + (size_t)kk * bk.g_right_ld;
           for (int n = lane; n < bk.ncols; n += 32) grow[n] += sq * z[bk.out0 + n];
         }
       }
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
           for (int kk = lane; kk < bk.rank; kk += 32) {
             const float sdp = bk.scale[kk] * dp[bk.p_off + kk];
             acc = fmaf(row[kk], sdp, acc);
-            if (bk.g_left >= 0) gp[bk.g_left + (size_t)i * bk.left_ld + kk] += in_i * sdp;
+            if (bk.g_left >= 0) gp[bk.g_left + (size_t)i * bk.g_left_ld + kk] += in_i * sdp;
           }
           acc = warp_sum_f(acc);
           if (lane == 0) {
@@ -460,6 +504,8 @@ int grow(float** p, size_t* have, size_t need) {
 
 // (Re)derive the training view of the model from the handle's block lists.  Flat parameter layout per layer:
 // [sigma_w | sigma_u | w_left | w_right | u_left | u_right | bias], then [dense kernel | dense bias].
+size_t train_smem_floats(const TrModel& M);
+
 int build_train_model(svdlstm_trainer_s* tr) {
   const ModelDesc& md = tr->h->md;
   TrModel& M = tr->tm;
@@ -469,10 +515,11 @@ int build_train_model(svdlstm_trainer_s* tr) {
   M.n_out = md.n_out;
   M.dense_kernel = md.dense_kernel;
   M.dense_bias = md.dense_bias;
-  long long off = 0, coff = 0;
+  long long off = 0, coff = 0, stage = 0;
   for (int l = 0; l < md.n_layers; ++l) {
     const LayerDesc& Ld = md.layers[l];
     TrLayer& T = M.layers[l];
+    stage += 4 * Ld.units;
     SVD_REQUIRE(Ld.n_blocks == 2 || Ld.n_blocks == 8, "svdlstm_trainer: layer %d is not a factored cell", l);
     const int ng = Ld.n_blocks / 2;
     for (int bi = 0; bi < Ld.n_blocks; ++bi)
@@ -498,6 +545,8 @@ int build_train_model(svdlstm_trainer_s* tr) {
       const Block& base = Ld.blocks[isu ? ng : 0];
       d.left = s.left; d.scale = s.scale; d.right = s.right;
       d.left_ld = s.left_ld; d.right_ld = s.right_ld; d.rank = s.rank; d.ncols = s.ncols; d.out0 = s.out0; d.from_h = s.from_h; d.p_off = s.p_off;
+      d.g_left_ld = s.left_ld; d.g_right_ld = s.right_ld;
+      stage += (long long)(s.from_h ? H : D) * s.rank + s.rank + (long long)s.rank * s.ncols;
       d.g_scale = (isu ? o_su : o_sw) + (s.scale - base.scale);
       d.g_left = uv ? (isu ? o_ul : o_wl) + (s.left - base.left) : -1;
       d.g_right = uv ? (isu ? o_ur : o_wr) + (s.right - base.right) : -1;
@@ -518,10 +567,13 @@ int build_train_model(svdlstm_trainer_s* tr) {
   }
   M.n_params = off;
   M.cache_stride = coff;
+  if (md.n_out > 0) stage += (long long)md.layers[md.n_layers - 1].units * md.n_out + md.n_out;
+  M.stage_floats = 0;
+  if (sizeof(float) * (train_smem_floats(M) + (size_t)stage + 16) <= 180 * 1024) M.stage_floats = (int)stage + 16;
   return 0;
 }
 
-size_t train_smem_floats(const TrModel& M) {
+size_t train_smem_floats(const TrModel& M) {   // activations / scratch (the staged weights follow)
   const int HM = M.max_units, L = M.n_layers;
   const int mx = HM > M.max_in ? HM : M.max_in;
   const int n_y = M.n_out > 0 ? M.n_out : HM;
@@ -633,7 +685,7 @@ int svdlstm_trainer_gradients(svdlstm_trainer tr, const float* x, const float* y
     if (int e = grow(&tr->gpart, &tr->gpart_floats, (size_t)B * M.n_params)) return e;
     SVD_CUDA_TRY(cudaMemsetAsync(tr->gpart, 0, sizeof(float) * (size_t)B * M.n_params, stream));
   }
-  const size_t smem = sizeof(float) * train_smem_floats(M);
+  const size_t smem = sizeof(float) * (train_smem_floats(M) + (size_t)M.stage_floats);
   SVD_REQUIRE(smem <= 200 * 1024, "svdlstm_trainer: model too large for the training kernel's shared memory (%zu bytes)", smem);
   SVD_CUDA_TRY(cudaFuncSetAttribute(train_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   train_step_kernel<<<B, kTrThreads, smem, stream>>>(tr->dev_tm, x, y_true, B, T, return_sequences ? 1 : 0, tr->cache, tr->ypred,
