@@ -50,6 +50,7 @@ struct TrModel {
   long long cache_stride;   // floats per (sequence, step)
   int max_units, max_p, max_in;
   int stage_floats;         // > 0: every weight of the model fits shared memory (this many floats) and is staged there once per launch
+  int grad_floats;          // > 0 (only with stage_floats): the CTA's gradient slice accumulates in shared memory too, written out once
   TrLayer layers[kMaxLayers];
 };
 
@@ -82,20 +83,36 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
   float* dha = z + 4 * HM;               // [max(HM, max_in)] gradient arriving from the layer above
   float* dhb = dha + (HM > M.max_in ? HM : M.max_in);   // [same] gradient for the layer below (double buffer)
   float* vin = dhb + (HM > M.max_in ? HM : M.max_in);   // [max_in] staged input vector
-  float* dy = vin + M.max_in;            // [n_out or HM]
+  float* part = vin + M.max_in;          // [kMaxBlocks][max(HM, max_in)] per-block partial input gradients (narrow layers)
+  int* kblk = reinterpret_cast<int*>(part + kMaxBlocks * (HM > M.max_in ? HM : M.max_in));   // [L][max_p] block owning projection k
+  float* dy = reinterpret_cast<float*>(kblk + L * M.max_p);   // [n_out or HM]
   const int n_y = M.n_out > 0 ? M.n_out : M.layers[L - 1].units;
   const int n_steps_out = ret_seq ? T : 1;
   const float inv_count = 1.0f / ((float)B * (float)n_steps_out * (float)n_y);
   float* cb = cache + (size_t)b * T * M.cache_stride;
   float* gp = gpart + (size_t)b * M.n_params;
+  float* gp_out = nullptr;
   float* yp = ypred + (size_t)b * n_steps_out * n_y;
 
   for (int i = tid; i < 4 * L * HM; i += kTrThreads) hst[i] = 0.f;   // hst, cst, dhn, dcn
+  for (int i = tid; i < L * M.max_p; i += kTrThreads) {
+    const TrLayer& Ly = M.layers[i / M.max_p];
+    const int k = i % M.max_p;
+    int bi = 0;
+    while (bi + 1 < Ly.n_blocks && k >= Ly.blocks[bi + 1].p_off) ++bi;
+    kblk[i] = bi;
+  }
   // Small models (the reference's 3 x 15 fine-tune): every factor, bias and the Dense top are copied ONCE into shared memory,
   // compactly per block, and the block table (itself in shared memory) is re-pointed at the copies: the ~10 dependent phases
   // of a layer-step then wait on shared-memory instead of L2 latencies.  The gradient strides keep the tensors' own layout.
   if (M.stage_floats > 0) {
     float* wbuf = dy + (M.n_out > 0 ? M.n_out : HM) + 8;
+    if (M.grad_floats > 0 && gpart != nullptr) {
+      // per-step "+=" on a gradient entry is a dependent read-modify-write: in shared memory it costs ~30 cycles, in L2 ~700
+      gp_out = gp;
+      gp = wbuf + M.stage_floats;
+      for (int i = tid; i < M.grad_floats; i += kTrThreads) gp[i] = 0.f;
+    }
     __syncthreads();
     int off = 0;
     for (int l = 0; l < L; ++l) {
@@ -146,9 +163,7 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
       __syncthreads();
       // q[k] = in . left[:, k]
       for (int k = tid; k < Ly.p_total; k += kTrThreads) {
-        int bi = 0;
-        while (bi + 1 < Ly.n_blocks && k >= Ly.blocks[bi + 1].p_off) ++bi;
-        const TrBlock& bk = Ly.blocks[bi];
+        const TrBlock& bk = Ly.blocks[kblk[l * M.max_p + k]];
         const int kk = k - bk.p_off;
         const float* src = bk.from_h ? hst + l * HM : vin;
         const int n_in = bk.from_h ? H : D;
@@ -279,11 +294,30 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
         for (int i = tid; i < D; i += kTrThreads) vin[i] = xin[i];
       }
       __syncthreads();
+      // Narrow layers (the reference's 15 units): a warp per projection leaves 8 warps walking 120 projections of 15 columns in
+      // turn, a shuffle reduction each -- one THREAD per projection (and per (block, input) below) finishes the same work in one
+      // pass of short serial loops over shared memory.
+      const bool narrow = 4 * H <= 128;
+      if (narrow) {
+        for (int k = tid; k < Ly.p_total; k += kTrThreads) {
+          const TrBlock& bk = Ly.blocks[kblk[l * M.max_p + k]];
+          const int kk = k - bk.p_off;
+          const float* row = bk.right + (size_t)kk * bk.right_ld;
+          const float* dz = z + bk.out0;
+          float acc = 0.f;
+          for (int n = 0; n < bk.ncols; ++n) acc = fmaf(dz[n], row[n], acc);
+          dp[k] = acc;
+          if (bk.g_scale >= 0) gp[bk.g_scale + kk] += q[k] * acc;
+          if (bk.g_right >= 0) {
+            const float sq = bk.scale[kk] * q[k];
+            float* grow = gp + bk.g_right + (size_t)kk * bk.g_right_ld;
+            for (int n = 0; n < bk.ncols; ++n) grow[n] = fmaf(sq, dz[n], grow[n]);
+          }
+        }
+      }
       // dp[k] = sum_n dz[out0 + n] right[k][n]   (warp per k: rows of `right` are contiguous)
-      for (int k = warp; k < Ly.p_total; k += kTrWarps) {
-        int bi = 0;
-        while (bi + 1 < Ly.n_blocks && k >= Ly.blocks[bi + 1].p_off) ++bi;
-        const TrBlock& bk = Ly.blocks[bi];
+      for (int k = narrow ? Ly.p_total : warp; k < Ly.p_total; k += kTrWarps) {
+        const TrBlock& bk = Ly.blocks[kblk[l * M.max_p + k]];
         const int kk = k - bk.p_off;
         const float* row = bk.right + (size_t)kk * bk.right_ld;
         float acc = 0.f;
@@ -304,7 +338,42 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
       __syncthreads();
       // input gradients: d in[i] = sum_k left[i][k] scale[k] dp[k]   (warp per i: rows of `left` are contiguous in k)
       const float* hprev = prev ? prev + 5 * H : nullptr;
-      for (int bi = 0; bi < Ly.n_blocks; ++bi) {
+      if (narrow) {
+        const int NIN = H > D ? H : D;
+        for (int e = tid; e < Ly.n_blocks * NIN; e += kTrThreads) {
+          const int bi = e / NIN, i = e - bi * NIN;
+          const TrBlock& bk = Ly.blocks[bi];
+          const int n_in = bk.from_h ? H : D;
+          if (i >= n_in || (!bk.from_h && l == 0 && bk.g_left < 0)) continue;
+          const float* row = bk.left + (size_t)i * bk.left_ld;
+          const float* dpk = dp + bk.p_off;
+          float acc = 0.f;
+          if (bk.g_left >= 0) {
+            const float in_i = bk.from_h ? (hprev ? hprev[i] : 0.f) : vin[i];
+            float* grow = gp + bk.g_left + (size_t)i * bk.g_left_ld;
+            for (int kk = 0; kk < bk.rank; ++kk) {
+              const float sdp = bk.scale[kk] * dpk[kk];
+              acc = fmaf(row[kk], sdp, acc);
+              grow[kk] = fmaf(in_i, sdp, grow[kk]);
+            }
+          } else {
+            for (int kk = 0; kk < bk.rank; ++kk) acc = fmaf(row[kk], bk.scale[kk] * dpk[kk], acc);
+          }
+          part[e] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < D + H; e += kTrThreads) {
+          const bool rec_side = e >= D;
+          const int i = rec_side ? e - D : e;
+          if (!rec_side && l == 0) continue;   // nobody needs d x
+          float acc = 0.f;
+          for (int bi = 0; bi < Ly.n_blocks; ++bi)
+            if ((Ly.blocks[bi].from_h != 0) == rec_side) acc += part[bi * NIN + i];
+          (rec_side ? dhn + l * HM : d_nxt)[i] = acc;
+        }
+        __syncthreads();
+      }
+      for (int bi = narrow ? Ly.n_blocks : 0; bi < Ly.n_blocks; ++bi) {
         const TrBlock& bk = Ly.blocks[bi];
         const int n_in = bk.from_h ? H : D;
         if (!bk.from_h && l == 0 && bk.g_left < 0) continue;   // nobody needs d x
@@ -331,6 +400,10 @@ __global__ void __launch_bounds__(kTrThreads) train_step_kernel(const TrModel* _
       d_cur = d_nxt;
       d_nxt = tmp;
     }
+  }
+  if (gp_out != nullptr) {
+    __syncthreads();
+    for (int i = tid; i < M.grad_floats; i += kTrThreads) gp_out[i] = gp[i];
   }
 }
 
@@ -569,7 +642,11 @@ int build_train_model(svdlstm_trainer_s* tr) {
   M.cache_stride = coff;
   if (md.n_out > 0) stage += (long long)md.layers[md.n_layers - 1].units * md.n_out + md.n_out;
   M.stage_floats = 0;
-  if (sizeof(float) * (train_smem_floats(M) + (size_t)stage + 16) <= 180 * 1024) M.stage_floats = (int)stage + 16;
+  M.grad_floats = 0;
+  if (sizeof(float) * (train_smem_floats(M) + (size_t)stage + 16) <= 180 * 1024) {
+    M.stage_floats = (int)stage + 16;
+    if (sizeof(float) * (train_smem_floats(M) + (size_t)M.stage_floats + (size_t)M.n_params) <= 200 * 1024) M.grad_floats = (int)M.n_params;
+  }
   return 0;
 }
 
@@ -577,7 +654,8 @@ size_t train_smem_floats(const TrModel& M) {   // activations / scratch (the sta
   const int HM = M.max_units, L = M.n_layers;
   const int mx = HM > M.max_in ? HM : M.max_in;
   const int n_y = M.n_out > 0 ? M.n_out : HM;
-  return (size_t)4 * L * HM + 2 * (size_t)M.max_p + 4 * (size_t)HM + 2 * (size_t)mx + M.max_in + n_y + 8;
+  return (size_t)4 * L * HM + 2 * (size_t)M.max_p + 4 * (size_t)HM + 2 * (size_t)mx + M.max_in + (size_t)kMaxBlocks * mx +
+         (size_t)L * M.max_p + n_y + 8;
 }
 
 int sync_model(svdlstm_trainer_s* tr, cudaStream_t stream) {
@@ -685,7 +763,7 @@ int svdlstm_trainer_gradients(svdlstm_trainer tr, const float* x, const float* y
     if (int e = grow(&tr->gpart, &tr->gpart_floats, (size_t)B * M.n_params)) return e;
     SVD_CUDA_TRY(cudaMemsetAsync(tr->gpart, 0, sizeof(float) * (size_t)B * M.n_params, stream));
   }
-  const size_t smem = sizeof(float) * (train_smem_floats(M) + (size_t)M.stage_floats);
+  const size_t smem = sizeof(float) * (train_smem_floats(M) + (size_t)M.stage_floats + (size_t)M.grad_floats);
   SVD_REQUIRE(smem <= 200 * 1024, "svdlstm_trainer: model too large for the training kernel's shared memory (%zu bytes)", smem);
   SVD_CUDA_TRY(cudaFuncSetAttribute(train_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   train_step_kernel<<<B, kTrThreads, smem, stream>>>(tr->dev_tm, x, y_true, B, T, return_sequences ? 1 : 0, tr->cache, tr->ypred,

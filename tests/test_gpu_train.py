@@ -74,6 +74,30 @@ def test_gradients_train_uv_with_orthogonal_regularizer(dropbear_weights, merged
     assert loss2 == loss and all(np.array_equal(a, b) for a, b in zip(grads, grads2)), "training step is not deterministic"
 
 
+@pytest.mark.parametrize("merged", [True, False])
+def test_gradients_wide_layers(merged):
+    """Layers wider than 32 units take the warp-per-projection backward path of K6 (the 15-unit shipped model takes the
+    thread-per-projection one): 40- and 48-unit layers with every tensor trainable, against the autograd twin."""
+    rng = np.random.default_rng(7)
+    dims = [16, 40, 48]
+    layers = [((0.3 * rng.standard_normal((dims[i], 4 * dims[i + 1]))).astype(np.float32),
+               (0.3 * rng.standard_normal((dims[i + 1], 4 * dims[i + 1]))).astype(np.float32),
+               (0.1 * rng.standard_normal(4 * dims[i + 1])).astype(np.float32)) for i in range(2)]
+    dense = ((0.3 * rng.standard_normal((48, 2))).astype(np.float32), np.zeros(2, np.float32))
+    full = svdlstm.full_model_from_weights(layers, dense, return_sequences=False)
+    sm = svdlstm.make_LSTM_singular_model(full, hoyer=0.02, orthogonal=0.05, merged_kernel=merged, return_sequences=False)
+    for l in sm.layers[:-1]:
+        l.set_weights([w + (0.02 * rng.standard_normal(w.shape)).astype(np.float32) if i in (2, 3, 4, 5) else w
+                       for i, w in enumerate(l.get_weights())])
+    sm.compile()
+    X = rng.standard_normal((4, 20, 16)).astype(np.float32)
+    y = rng.standard_normal((4, 2)).astype(np.float32)
+    loss, grads = sm.gradients(X, y)
+    _, t_ref, g_ref = R.loss_and_grads(_twin(sm, merged, False), X, y, hoyer_coef=0.02, orth_factor=0.05, train_uv=True)
+    assert abs(loss - t_ref) <= 2e-5 * abs(t_ref)
+    _cmp(grads, g_ref, "wide merged=%s" % merged)
+
+
 def test_adam_steps_and_fit(dropbear_weights):
     """Three train_on_batch steps equal three Keras-Adam steps on the autograd gradients (float64 twin); then `fit` runs the
     reference recipe end to end -- compile, fit with Hoyer, rebuild the reduced model with cutoff=.05 -- and the fine-tuned
