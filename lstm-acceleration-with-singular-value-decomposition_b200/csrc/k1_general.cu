@@ -8,6 +8,9 @@
 //   stage 3  i,f,c,o pointwise + c/h update      thread per (sequence, unit)
 // and the Dense top of the last layer.  Factor matrices are read through the read-only path (they are
 // L1/L2 resident: <= a few MB for every configuration of BASELINE.json).
+// Every activation array in shared memory is SEQUENCE-MINOR ([feature][BT]): the BT operands a thread multiplies one weight
+// with are one or two 128-bit broadcast loads instead of BT scalar ones (the inner loops were LSU-bound: 1 + BT loads per BT
+// FMAs).  The order of every floating-point sum is unchanged.
 //
 // This is the parity workhorse (every form x merged/split x mask/go_backwards/time_major/state);
 // the latency-optimised batch-1 path is k1_wavefront.cu, the tensor-core path k1b_tc.cu.
@@ -21,9 +24,67 @@ namespace {
 
 constexpr int kThreads = 256;
 
+template <int BT>
+__device__ __forceinline__ void store_bt(float* __restrict__ p, const float (&v)[BT]) {
+  if constexpr (BT >= 4) {
+#pragma unroll
+    for (int q = 0; q < BT / 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < BT; ++q) p[q] = v[q];
+  }
+}
+
+// acc[bt] += sum_k in[k][bt] * w[k * ld]  (k ascending, one fma per term: the order of the scalar loop).  The weights come from
+// L2 (a layer's factors are far larger than L1): kUnroll loads are issued before the first is used, so each warp keeps
+// kUnroll cache lines in flight instead of one or two -- the loop was bound by exactly that latency.
+constexpr int kUnroll = 8;
+template <int BT>
+__device__ __forceinline__ void load_bt(const float* __restrict__ p, float (&v)[BT]);
+template <int BT>
+__device__ __forceinline__ void dot_bt(const float* __restrict__ w, int ld, const float* __restrict__ in, int n, float (&acc)[BT]) {
+  int k = 0;
+  for (; k + kUnroll <= n; k += kUnroll) {   // (requesting batch k+1 before consuming batch k was tried: slower, 52 -> 56 ms)
+    float wv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) wv[u] = __ldg(w + (size_t)(k + u) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float v[BT];
+      load_bt<BT>(in + (k + u) * BT, v);
+#pragma unroll
+      for (int bt = 0; bt < BT; ++bt) acc[bt] = fmaf(v[bt], wv[u], acc[bt]);
+    }
+  }
+  for (; k < n; ++k) {
+    const float wk = __ldg(w + (size_t)k * ld);
+    float v[BT];
+    load_bt<BT>(in + k * BT, v);
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt) acc[bt] = fmaf(v[bt], wk, acc[bt]);
+  }
+}
+
+// BT consecutive floats (one feature of the CTA's BT sequences; 16-byte aligned when BT >= 4) -> registers
+template <int BT>
+__device__ __forceinline__ void load_bt(const float* __restrict__ p, float (&v)[BT]) {
+  if constexpr (BT >= 4) {
+#pragma unroll
+    for (int q = 0; q < BT / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else if constexpr (BT == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = p[0];
+  }
+}
+
 template <int BT, bool HAS_MASK>
 __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc* __restrict__ mdp, ForwardArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const ModelDesc& md = *mdp;
   const int L = md.n_layers;
   const int tid = threadIdx.x;
@@ -36,27 +97,29 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
   const int D = md.input_dim;
 
   // ---- shared-memory carve-up ---------------------------------------------------------------
-  __shared__ float* s_h[kMaxLayers];
-  __shared__ float* s_c[kMaxLayers];
-  __shared__ float* s_o[kMaxLayers];
-  float* cur = smem;
-  int max4h = 0, maxp = 0;
+  // (offsets, not pointers: `smem + offset` keeps the address space known to the compiler -> LDS/STS, not generic LD/ST)
+  __shared__ int o_h[kMaxLayers];
+  __shared__ int o_c[kMaxLayers];
+  __shared__ int o_o[kMaxLayers];
+#define s_h(l) (smem + o_h[l])
+#define s_c(l) (smem + o_c[l])
+#define s_o(l) (smem + o_o[l])
+  int cur = 0;
+  int maxp = 0;
   for (int l = 0; l < L; ++l) {
     const int H = md.layers[l].units;
     if (tid == 0) {
-      s_h[l] = cur;
-      s_c[l] = cur + BT * H;
-      s_o[l] = HAS_MASK ? cur + 2 * BT * H : cur;
+      o_h[l] = cur;
+      o_c[l] = cur + BT * H;
+      o_o[l] = HAS_MASK ? cur + 2 * BT * H : cur;
     }
     cur += (HAS_MASK ? 3 : 2) * BT * H;
-    max4h = max(max4h, 4 * H);
     maxp = max(maxp, md.layers[l].p_total);
   }
-  float* s_x = cur;
+  float* s_x = smem + cur;
+  const int x_off = cur;
   cur += BT * D;
-  float* s_p = cur;
-  cur += BT * maxp;
-  float* s_z = cur;
+  float* s_p = smem + cur;
   __syncthreads();
 
   // ---- initial state ------------------------------------------------------------------------
@@ -72,9 +135,9 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
           hv = a.h0[off + (size_t)b * H + j];
           cv = a.c0[off + (size_t)b * H + j];
         }
-        s_h[l][idx] = hv;
-        s_c[l][idx] = cv;
-        if (HAS_MASK) s_o[l][idx] = 0.f;
+        s_h(l)[j * BT + bt] = hv;
+        s_c(l)[j * BT + bt] = cv;
+        if (HAS_MASK) s_o(l)[j * BT + bt] = 0.f;
       }
       off += (size_t)B * H;
     }
@@ -92,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
       const int b = b0 + bt;
       float v = 0.f;
       if (b < B) v = time_major ? a.x[((size_t)t * B + b) * D + d] : a.x[((size_t)b * T + t) * D + d];
-      s_x[idx] = v;
+      s_x[d * BT + bt] = v;
     }
     __syncthreads();
 
@@ -100,8 +163,8 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
       const LayerDesc& Ld = md.layers[l];
       const int H = Ld.units;
       const int Din = Ld.d_in;
-      const float* lin = (l == 0) ? s_x : s_o[l - 1];
-      const float* hprev = s_h[l];
+      const int lin_off = (l == 0) ? x_off : o_o[l - 1];
+      const int h_off = o_h[l];
       const int P = Ld.p_total;
 
       // ---- stage 1 ---------------------------------------------------------------------------
@@ -110,90 +173,82 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
         while (bi + 1 < Ld.n_blocks && q >= Ld.blocks[bi + 1].p_off) ++bi;
         const Block& blk = Ld.blocks[bi];
         const int k = q - blk.p_off;
-        const float* in = blk.from_h ? hprev : lin;
+        const float* in = smem + (blk.from_h ? h_off : lin_off);
         const int kin = blk.from_h ? H : Din;
         float acc[BT];
         if (blk.left == nullptr) {
 #pragma unroll
-          for (int bt = 0; bt < BT; ++bt) acc[bt] = in[bt * kin + k];
+          for (int bt = 0; bt < BT; ++bt) acc[bt] = in[k * BT + bt];
         } else {
 #pragma unroll
           for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
-          const float* lp = blk.left + k;
-          const int ld = blk.left_ld;
-          for (int i = 0; i < kin; ++i) {
-            const float w = __ldg(lp + (size_t)i * ld);
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = fmaf(in[bt * kin + i], w, acc[bt]);
-          }
+          dot_bt<BT>(blk.left + k, blk.left_ld, in, kin, acc);
           if (blk.scale != nullptr) {
             const float s = __ldg(blk.scale + k);
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) acc[bt] *= s;
           }
         }
-#pragma unroll
-        for (int bt = 0; bt < BT; ++bt) s_p[bt * P + q] = acc[bt];
+        store_bt<BT>(s_p + q * BT, acc);
       }
       __syncthreads();
 
-      // ---- stage 2 ---------------------------------------------------------------------------
-      for (int n = tid; n < 4 * H; n += kThreads) {
-        float acc[BT];
-        const float bv = __ldg(Ld.bias + n);
+      // ---- stages 2 + 3: one thread = the four gate columns of one unit, for the CTA's BT sequences; gates + state update
+      //      (Keras _compute_carry_and_output_fused) straight from the accumulators.  Column order i, c~, f, o keeps only the
+      //      running product / new cell state live between columns. ----------------------------------------------------------
+      for (int j = tid; j < H; j += kThreads) {
+        float keep[BT];   // sigmoid(i) -> sigmoid(i) tanh(c~) -> c_new
+        float h_new[BT];
 #pragma unroll
-        for (int bt = 0; bt < BT; ++bt) acc[bt] = bv;
-        for (int bi = 0; bi < Ld.n_blocks; ++bi) {
-          const Block& blk = Ld.blocks[bi];
-          int rel = n - blk.out0;
-          if (rel < 0) continue;
-          const float* pp = s_p + blk.p_off;
-          if (blk.ident) {
-            if (rel < blk.rank) {
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = gi == 0 ? 0 : (gi == 1 ? 2 : (gi == 2 ? 1 : 3));
+          const int n = g * H + j;
+          float acc[BT];
+          const float bv = __ldg(Ld.bias + n);
 #pragma unroll
-              for (int bt = 0; bt < BT; ++bt) acc[bt] += pp[bt * P + rel];
-              continue;
+          for (int bt = 0; bt < BT; ++bt) acc[bt] = bv;
+          for (int bi = 0; bi < Ld.n_blocks; ++bi) {
+            const Block& blk = Ld.blocks[bi];
+            int rel = n - blk.out0;
+            if (rel < 0) continue;
+            const float* pp = s_p + blk.p_off * BT;
+            if (blk.ident) {
+              if (rel < blk.rank) {
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) acc[bt] += pp[rel * BT + bt];
+                continue;
+              }
+              rel -= blk.rank;
             }
-            rel -= blk.rank;
+            if (rel >= blk.ncols) continue;
+            dot_bt<BT>(blk.right + rel, blk.right_ld, pp, blk.rank, acc);
           }
-          if (rel >= blk.ncols) continue;
-          const float* rp = blk.right + rel;
-          const int ld = blk.right_ld;
-          const int r = blk.rank;
-          for (int k = 0; k < r; ++k) {
-            const float w = __ldg(rp + (size_t)k * ld);
+          const float* c_old = s_c(l) + j * BT;
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = fmaf(pp[bt * P + k], w, acc[bt]);
+          for (int bt = 0; bt < BT; ++bt) {
+            if (gi == 0) keep[bt] = sigmoid_acc(acc[bt]);
+            else if (gi == 1) keep[bt] *= tanhf(acc[bt]);
+            else if (gi == 2) keep[bt] = sigmoid_acc(acc[bt]) * c_old[bt] + keep[bt];
+            else h_new[bt] = sigmoid_acc(acc[bt]) * tanhf(keep[bt]);
           }
         }
 #pragma unroll
-        for (int bt = 0; bt < BT; ++bt) s_z[bt * 4 * H + n] = acc[bt];
-      }
-      __syncthreads();
-
-      // ---- stage 3: gates + state update (Keras _compute_carry_and_output_fused) ---------------
-      for (int idx = tid; idx < BT * H; idx += kThreads) {
-        const int bt = idx / H, j = idx - bt * H;
-        const float* z = s_z + bt * 4 * H;
-        const float ig = sigmoid_acc(z[j]);
-        const float fg = sigmoid_acc(z[H + j]);
-        const float gg = tanhf(z[2 * H + j]);
-        const float og = sigmoid_acc(z[3 * H + j]);
-        const float c_new = fg * s_c[l][idx] + ig * gg;
-        const float h_new = og * tanhf(c_new);
-        if (HAS_MASK) {
-          const int b = b0 + bt;
-          const bool valid = (b < B) ? (a.mask[(size_t)b * T + t] != 0) : true;
-          if (valid) {
-            s_c[l][idx] = c_new;
-            s_h[l][idx] = h_new;
-            s_o[l][idx] = h_new;
-          } else if (zero_mask_out) {
-            s_o[l][idx] = 0.f;
+        for (int bt = 0; bt < BT; ++bt) {
+          const int idx = j * BT + bt;
+          if (HAS_MASK) {
+            const int b = b0 + bt;
+            const bool valid = (b < B) ? (a.mask[(size_t)b * T + t] != 0) : true;
+            if (valid) {
+              s_c(l)[idx] = keep[bt];
+              s_h(l)[idx] = h_new[bt];
+              s_o(l)[idx] = h_new[bt];
+            } else if (zero_mask_out) {
+              s_o(l)[idx] = 0.f;
+            }
+          } else {
+            s_c(l)[idx] = keep[bt];
+            s_h(l)[idx] = h_new[bt];
           }
-        } else {
-          s_c[l][idx] = c_new;
-          s_h[l][idx] = h_new;
         }
       }
       __syncthreads();
@@ -201,13 +256,13 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
 
     // ---- output of this step -----------------------------------------------------------------
     if (ret_seq || step == T - 1) {
-      const float* ho = s_o[L - 1];
+      const float* ho = s_o(L - 1);
       const int HL = md.layers[L - 1].units;
       if (md.n_out > 0) {
         for (int pair = warp; pair < BT * md.n_out; pair += kThreads / 32) {
           const int bt = pair / md.n_out, o = pair - bt * md.n_out;
           float acc = 0.f;
-          for (int j = lane; j < HL; j += 32) acc = fmaf(ho[bt * HL + j], __ldg(md.dense_kernel + (size_t)j * md.n_out + o), acc);
+          for (int j = lane; j < HL; j += 32) acc = fmaf(ho[j * BT + bt], __ldg(md.dense_kernel + (size_t)j * md.n_out + o), acc);
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
           const int b = b0 + bt;
@@ -227,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
             size_t yi;
             if (!ret_seq) yi = (size_t)b * n_y + j;
             else yi = time_major ? ((size_t)step * B + b) * n_y + j : ((size_t)b * T + step) * n_y + j;
-            a.y[yi] = ho[idx];
+            a.y[yi] = ho[j * BT + bt];
           }
         }
       }
@@ -246,8 +301,8 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
         const int bt = idx / H, j = idx - bt * H;
         const int b = b0 + bt;
         if (b < B) {
-          if (a.h_n) a.h_n[off + (size_t)b * H + j] = s_h[l][idx];
-          if (a.c_n) a.c_n[off + (size_t)b * H + j] = s_c[l][idx];
+          if (a.h_n) a.h_n[off + (size_t)b * H + j] = s_h(l)[j * BT + bt];
+          if (a.c_n) a.c_n[off + (size_t)b * H + j] = s_c(l)[j * BT + bt];
         }
       }
       off += (size_t)B * H;
@@ -255,16 +310,19 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
   }
 }
 
+#undef s_h
+#undef s_c
+#undef s_o
+
 size_t general_smem_bytes(const ModelDesc& md, int BT, bool has_mask) {
   size_t f = 0;
-  int max4h = 0, maxp = 0;
+  int maxp = 0;
   for (int l = 0; l < md.n_layers; ++l) {
     const int H = md.layers[l].units;
     f += (size_t)(has_mask ? 3 : 2) * BT * H;
-    if (4 * H > max4h) max4h = 4 * H;
     if (md.layers[l].p_total > maxp) maxp = md.layers[l].p_total;
   }
-  f += (size_t)BT * md.input_dim + (size_t)BT * maxp + (size_t)BT * max4h;
+  f += (size_t)BT * md.input_dim + (size_t)BT * maxp;
   return f * sizeof(float);
 }
 
@@ -286,13 +344,19 @@ int launch_general(const ModelDesc& md, const ModelDesc* dev_md, const ForwardAr
 
 int run_general(const ModelDesc& md, const ModelDesc* dev_md, const ForwardArgs& a, cudaStream_t stream, int* launches) {
   const size_t kMaxSmem = 227 * 1024;
-  // sequences per CTA: as many as keep >= 2 CTAs per SM in flight, subject to shared memory
-  int BT = 8;
-  while (BT > 1 && ((a.B + BT - 1) / BT < 296 || general_smem_bytes(md, BT, a.mask != nullptr) > kMaxSmem)) BT >>= 1;
+  // sequences per CTA: every weight load (L2) serves BT sequences, so as many as still leave ~one CTA per SM, subject to shared
+  // memory (measured, C3 rank 128, T=256: B=4096 BT 4/8/16 = 73/58/52 ms; B=512 BT 1/4/8/16 = 38/26/28/33 ms)
+  int BT = 16;
+  while (BT > 1 && ((a.B + BT - 1) / BT < 120 || general_smem_bytes(md, BT, a.mask != nullptr) > kMaxSmem)) BT >>= 1;
+  if (const char* e = getenv("SVDLSTM_GEN_BT")) {   // experiments
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16) && general_smem_bytes(md, v, a.mask != nullptr) <= kMaxSmem) BT = v;
+  }
   const size_t smem = general_smem_bytes(md, BT, a.mask != nullptr);
   SVD_REQUIRE(smem <= kMaxSmem, "svdlstm_forward(general): model state needs %zu B of shared memory per sequence (> %zu)", smem, kMaxSmem);
   int rc;
   switch (BT) {
+    case 16: rc = launch_general<16>(md, dev_md, a, smem, stream); break;
     case 8: rc = launch_general<8>(md, dev_md, a, smem, stream); break;
     case 4: rc = launch_general<4>(md, dev_md, a, smem, stream); break;
     case 2: rc = launch_general<2>(md, dev_md, a, smem, stream); break;
