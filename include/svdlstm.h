@@ -45,7 +45,8 @@ typedef struct svdlstm_model_s* svdlstm_handle;
 #define SVDLSTM_ENGINE_GENERAL  1   /* FP32 CUDA-core batched persistent kernel (any shape)                                    */
 #define SVDLSTM_ENGINE_WAVEFRONT 2  /* FP32 register-resident warp-per-layer wavefront (H,D,r<=32)                             */
 #define SVDLSTM_ENGINE_TC       3   /* tcgen05 tensor-core persistent kernel: FP16 operands, FP32 accumulate + cell state
-                                       (reduced precision; merged 3-/2-factor or full cells, units <= 512 or <= 1024 padded to
+                                       (reduced precision; 3-/2-factor or full cells, merged or split -- a split layer's gate
+                                       blocks are merged when the weights are packed --, units <= 512 or <= 1024 padded to
                                        128-row tiles, ranks <= 256, return_sequences, no mask)                                 */
 #define SVDLSTM_ENGINE_FP32     4   /* strict FP32 (the 1e-5 parity path): wavefront when the model fits it, else general     */
 #define SVDLSTM_TC_MIN_BATCH    128

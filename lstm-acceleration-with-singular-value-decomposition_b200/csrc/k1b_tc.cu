@@ -1476,6 +1476,167 @@ void tc_free(TcState* s) {
 // 128 rows at 64-sequence tiles, 3 at 32 -- or 4 when the layer has no S1w of its own (layer 0, and every layer that itself receives
 // t_w: its S1w TMEM region is free).  Needs merged factored cells on both sides.  SVDLSTM_TC_HANDOFF=h disables it.
 static int tc_s1u_tiles_max(int ns, bool no_s1w) { return no_s1w ? 4 : (ns == 64 ? 2 : 3); }
+// ---- split cell forms (svd_classes_v3.py:146-232, 330-363: one factorisation per gate) ------------------------------------------
+// The kernel consumes ONE (left, scale, right) triple per side (input / recurrent) of a layer.  A split layer's four per-gate
+// blocks of a side are merged into such a triple when the weights are packed, by one of two routes:
+//   concat  left = [L_i | L_f | L_c | L_o] (kin x R), scale likewise, right = the block-diagonal (R x 4H) matrix of the R_g:
+//           the same contractions as the reference's split form (zero blocks are multiplied too); needs R = sum of the gate
+//           ranks <= 256 and pays off when R < kin;
+//   dense   W = sum_g (L_g sigma_g) R_g placed at gate g's columns (float64 accumulation), run as I . W like an unfactored cell:
+//           for R >= kin (a split model at full rank: R = 4 min(D, H)) and for the 2-factor split form, whose C = V1^-1 V2
+//           blocks are no FP16 material (see tc_reorthogonalise); needs kin <= 256.
+// kTcRouteNone = neither fits.
+enum { kTcRouteNone = 0, kTcRouteConcat = 1, kTcRouteDense = 2 };
+static int tc_side_route(const LayerDesc& Ld, int side, int* rank_out) {
+  const int kin = side == 0 ? Ld.d_in : Ld.units;
+  int R = 0;
+  bool ident = false;
+  for (int bi = 0; bi < Ld.n_blocks; ++bi)
+    if (Ld.blocks[bi].from_h == side) {
+      R += Ld.blocks[bi].rank;
+      ident = ident || Ld.blocks[bi].ident;
+    }
+  if (!ident && R <= 256 && R < kin) { *rank_out = R; return kTcRouteConcat; }
+  if (kin <= 256) { *rank_out = kin; return kTcRouteDense; }
+  *rank_out = R;
+  return kTcRouteNone;
+}
+
+// Shape-level merged equivalent of `md`: merged layers are copied, split layers become two blocks (pointers null: the device
+// tensors are built by tc_merge_side when the weights are packed).  False if a split layer has no route.
+static bool tc_effective_desc(const ModelDesc& md, ModelDesc& emd, const char** why) {
+  emd = md;
+  for (int l = 0; l < md.n_layers; ++l) {
+    const LayerDesc& Ld = md.layers[l];
+    if (Ld.n_blocks == 2) continue;
+    LayerDesc& E = emd.layers[l];
+    E.n_blocks = 2;
+    int p = 0;
+    for (int side = 0; side < 2; ++side) {
+      int rank = 0;
+      if (tc_side_route(Ld, side, &rank) == kTcRouteNone) {
+        *why = "split cell form: the gate ranks of one side sum to more than 256 and its input is wider than 256";
+        return false;
+      }
+      Block b{};
+      b.rank = rank;
+      b.ncols = 4 * Ld.units;
+      b.right_ld = 4 * Ld.units;
+      b.left_ld = rank;
+      b.from_h = side;
+      b.p_off = p;
+      p += rank;
+      E.blocks[side] = b;
+    }
+    E.p_total = p;
+  }
+  return true;
+}
+
+struct TcSideBlocks {
+  Block b[4];
+  int n;
+};
+// concat route: left_cat (kin x R), scale_cat (R), right_bd (R x 4H, zero outside the gates' own columns)
+__global__ void tc_concat_side_kernel(TcSideBlocks sb, int kin, int R, int H4, float* __restrict__ left_cat, float* __restrict__ scale_cat,
+                                      float* __restrict__ right_bd) {
+  const int n_left = kin * R, n_right = R * H4;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_left + R + n_right; idx += gridDim.x * blockDim.x) {
+    int p0 = 0;
+    if (idx < n_left + R) {
+      const bool is_scale = idx >= n_left;
+      const int i = is_scale ? 0 : idx / R, k = is_scale ? idx - n_left : idx - i * R;
+      float v = 0.f;
+      for (int q = 0; q < sb.n; ++q) {
+        const Block& b = sb.b[q];
+        if (k >= p0 && k < p0 + b.rank) {
+          const int kk = k - p0;
+          v = is_scale ? (b.scale ? b.scale[kk] : 1.f) : (b.left ? b.left[(size_t)i * b.left_ld + kk] : (i == kk ? 1.f : 0.f));
+        }
+        p0 += b.rank;
+      }
+      if (is_scale) scale_cat[k] = v;
+      else left_cat[idx] = v;
+    } else {
+      const int r = idx - n_left - R;
+      const int k = r / H4, n = r - k * H4;
+      float v = 0.f;
+      for (int q = 0; q < sb.n; ++q) {
+        const Block& b = sb.b[q];
+        if (k >= p0 && k < p0 + b.rank) {
+          const int rel = n - b.out0;
+          if (rel >= 0 && rel < b.ncols) v = b.right[(size_t)(k - p0) * b.right_ld + rel];
+        }
+        p0 += b.rank;
+      }
+      right_bd[r] = v;
+    }
+  }
+}
+// dense route: W (kin x 4H) = sum over the side's blocks of (L sigma) [I |] R at the block's columns
+__global__ void tc_dense_side_kernel(TcSideBlocks sb, int kin, int H4, float* __restrict__ w) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kin * H4; idx += gridDim.x * blockDim.x) {
+    const int i = idx / H4, n = idx - i * H4;
+    double acc = 0.0;
+    for (int q = 0; q < sb.n; ++q) {
+      const Block& b = sb.b[q];
+      int rel = n - b.out0;
+      if (rel < 0) continue;
+      if (b.ident) {
+        if (rel < b.rank) {
+          acc += (double)(b.left ? b.left[(size_t)i * b.left_ld + rel] : (i == rel ? 1.f : 0.f)) * (double)(b.scale ? b.scale[rel] : 1.f);
+          continue;
+        }
+        rel -= b.rank;
+      }
+      if (rel >= b.ncols) continue;
+      for (int kk = 0; kk < b.rank; ++kk) {
+        const double lv = b.left ? (double)b.left[(size_t)i * b.left_ld + kk] : (i == kk ? 1.0 : 0.0);
+        acc += lv * (double)(b.scale ? b.scale[kk] : 1.f) * (double)b.right[(size_t)kk * b.right_ld + rel];
+      }
+    }
+    w[idx] = (float)acc;
+  }
+}
+// One side of a split layer -> the merged block `out` (shape from tc_effective_desc) with device tensors in `temps`.
+static int tc_merge_side(const LayerDesc& Ld, int side, cudaStream_t stream, Block* out, std::vector<void*>& temps, int* launches) {
+  TcSideBlocks sb{};
+  for (int bi = 0; bi < Ld.n_blocks; ++bi)
+    if (Ld.blocks[bi].from_h == side) {
+      SVD_REQUIRE(sb.n < 4, "tensor-core engine: more than four blocks on one side of a split layer");
+      sb.b[sb.n++] = Ld.blocks[bi];
+    }
+  const int kin = side == 0 ? Ld.d_in : Ld.units, H4 = 4 * Ld.units;
+  int rank = 0;
+  const int route = tc_side_route(Ld, side, &rank);
+  SVD_REQUIRE(route != kTcRouteNone && rank == out->rank, "tensor-core engine: internal error (split-form route)");
+  auto alloc = [&](float** q, size_t n) -> int {
+    SVD_CUDA_TRY(cudaMalloc(q, sizeof(float) * n));
+    temps.push_back(*q);
+    return 0;
+  };
+  if (route == kTcRouteConcat) {
+    float *lc = nullptr, *sc = nullptr, *rb = nullptr;
+    if (int e = alloc(&lc, (size_t)kin * rank)) return e;
+    if (int e = alloc(&sc, (size_t)rank)) return e;
+    if (int e = alloc(&rb, (size_t)rank * H4)) return e;
+    tc_concat_side_kernel<<<296, 256, 0, stream>>>(sb, kin, rank, H4, lc, sc, rb);
+    out->left = lc;
+    out->scale = sc;
+    out->right = rb;
+  } else {
+    float* w = nullptr;
+    if (int e = alloc(&w, (size_t)kin * H4)) return e;
+    tc_dense_side_kernel<<<296, 256, 0, stream>>>(sb, kin, H4, w);
+    out->left = nullptr;
+    out->scale = nullptr;
+    out->right = w;
+  }
+  SVD_CUDA_TRY(cudaGetLastError());
+  ++*launches;
+  return 0;
+}
+
 static void tc_handoff_chain(const ModelDesc& md, int ns, bool out[kMaxLayers]) {
   const char* e = getenv("SVDLSTM_TC_HANDOFF");
   const bool off = e && e[0] == 'h';
@@ -1597,9 +1758,11 @@ bool tc_supported(const ModelDesc& md, const ForwardArgs& a, const char** why) {
   if ((a.h0 == nullptr) != (a.c0 == nullptr)) { *why = "initial_state needs both h and c"; return false; }
   if (a.flags & (SVDLSTM_GO_BACKWARDS | SVDLSTM_TIME_MAJOR)) { *why = "go_backwards / time_major are FP32-engine features"; return false; }
   if (!(a.flags & SVDLSTM_RETURN_SEQUENCES)) { *why = "return_sequences=False is an FP32-engine feature"; return false; }
-  for (int l = 0; l < md.n_layers; ++l) {
+  ModelDesc emd;
+  if (!tc_effective_desc(md, emd, why)) return false;
+  for (int l = 0; l < emd.n_layers; ++l) {
     TcLayerParams p;
-    if (!tc_layer_params(md, l, 32, p, why)) return false;
+    if (!tc_layer_params(emd, l, 32, p, why)) return false;
   }
   return true;
 }
@@ -1655,13 +1818,19 @@ static int tc_launch_pipe_1024(const void* pp_, int n_cta, uint32_t smem_bytes, 
   return 0;
 }
 
-static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches, int force_ns);
+static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream,
+                      int* launches, int force_ns);
 
-int run_tc(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
-  return run_tc_one(md, state, weights_dirty, a, stream, launches, 0);
+int run_tc(const ModelDesc& raw, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches) {
+  ModelDesc emd;   // split layers as their merged equivalents (shapes; the tensors are built when the weights are packed)
+  const char* why = "";
+  SVD_REQUIRE(tc_effective_desc(raw, emd, &why), "tensor-core engine: %s", why);
+  return run_tc_one(emd, raw, state, weights_dirty, a, stream, launches, 0);
 }
 
-static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream, int* launches, int force_ns) {
+// md = the effective (all-merged) description, raw = the handle's own
+static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state, bool weights_dirty, const ForwardArgs& a, cudaStream_t stream,
+                      int* launches, int force_ns) {
   const char* why = "";
   int nl = 0;
   if (*state == nullptr) {
@@ -1721,7 +1890,7 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
         sub.x = a.x + (size_t)b0 * a.T * md.input_dim;
         sub.y = a.y + (size_t)b0 * a.T * (md.n_out > 0 ? md.n_out : md.layers[L - 1].units);
         int nl_sub = 0;
-        const int rc = run_tc_one(md, state, weights_dirty && b0 == 0, sub, stream, &nl_sub, nsc);
+        const int rc = run_tc_one(md, raw, state, weights_dirty && b0 == 0, sub, stream, &nl_sub, nsc);
         if (rc != 0) return rc;
         total += nl_sub;
       }
@@ -1746,7 +1915,9 @@ static int run_tc_one(const ModelDesc& md, TcState** state, bool weights_dirty, 
     for (int l = 0; l < L; ++l)
       for (int j = 0; j < 2; ++j) {
         eff[l][j] = md.layers[l].blocks[j];
-        if (eff[l][j].ident) {
+        if (raw.layers[l].n_blocks != 2) {
+          if (int rc = tc_merge_side(raw.layers[l], j, stream, &eff[l][j], temps, &nl)) return rc;
+        } else if (eff[l][j].ident) {
           const int rows = j == 0 ? md.layers[l].d_in : md.layers[l].units;
           if (int rc = tc_reorthogonalise(md.layers[l].blocks[j], rows, stream, &eff[l][j], temps, &nl)) return rc;
         }

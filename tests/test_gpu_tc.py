@@ -114,6 +114,45 @@ def test_tc_without_dense_top_returns_hidden_sequence():
     assert float((htc - h32).abs().max()) < 3e-3
 
 
+@pytest.mark.parametrize("H,L", [(128, 2), (256, 2)])
+def test_tc_split_forms_match_oracle(oracle, H, L):
+    """merged_kernel=False -- the form the reference driver itself builds (svd_acceleration_v3.py:117,143) -- on the tensor-core
+    engine: the four per-gate blocks of a side are merged when the weights are packed, either concatenated (block-diagonal right
+    factor: truncated 3-factor models) or multiplied out to the dense matrix (full rank, 2-factor form).  Same bar as merged."""
+    full, _ = _models(H, L)
+    split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
+    x = np.random.default_rng(11).standard_normal((70, 16, 16)).astype(np.float32)
+    y = split.predict(x, engine="tc")                                   # full rank: R = 4 min(D, H) >= kin -> dense route
+    assert split.last_engine() == svdlstm.ENGINE_TC
+    _check(y, oracle_twin(oracle, split).predict(x), "tc split 3F full rank H=%d" % H)
+    for r in (8, 24):
+        m3 = svdlstm.truncate_singular_model(split, r)                  # recurrent side: 4r < H -> concat route
+        _check(m3.predict(x, engine="tc"), oracle_twin(oracle, m3).predict(x), "tc split 3F r=%d H=%d" % (r, H))
+        m2 = svdlstm.make_LSTM_reduced_model(split, rank=r, merged_kernel=False)   # 2-factor split -> dense route
+        _check(m2.predict(x, engine="tc"), oracle_twin(oracle, m2).predict(x), "tc split 2F r=%d H=%d" % (r, H))
+    # the regime switch takes split models to the tensor cores as well
+    xb = np.random.default_rng(12).standard_normal((256, 8, 16)).astype(np.float32)
+    m3 = svdlstm.truncate_singular_model(split, 8)
+    m3.predict(xb)
+    assert m3.last_engine() == svdlstm.ENGINE_TC
+
+
+def test_tc_split_dropbear_model(dropbear_weights):
+    """The shipped 3 x 15 model in the reference's own configuration (split 3-factor and its 2-factor reduction) on the
+    tensor-core engine, against the FP32 engine: RMSE <= 3e-3 of the output RMS (the bar of the merged DROPBEAR tests)."""
+    layers, dense = dropbear_weights
+    full = svdlstm.full_model_from_weights(layers, dense)
+    split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
+    red = svdlstm.make_LSTM_reduced_model(split, rank=8, merged_kernel=False)
+    x = torch.randn(64, 300, 16, generator=torch.Generator().manual_seed(13)).cuda()
+    for m, what in ((split, "split 3F"), (red, "split 2F r=8")):
+        y32 = m(x, engine="general")
+        ytc = m(x, engine="tc")
+        rms = float((y32 ** 2).mean().sqrt())
+        rmse = float(((ytc - y32) ** 2).mean().sqrt())
+        assert rmse <= 3e-3 * rms, (what, rmse, rms)
+
+
 def test_tc_rejects_what_it_cannot_run():
     """No silent fallback: unsupported models / calls raise with the reason."""
     full, sm = _models(128, 1)
@@ -123,9 +162,6 @@ def test_tc_rejects_what_it_cannot_run():
     layers512, dense512 = svdlstm.synthetic_layers(16, 512, 1, seed=0)
     with pytest.raises((RuntimeError, ValueError), match="ranks above 256"):
         svdlstm.full_model_from_weights(layers512, dense512, return_sequences=True)(x, engine="tc")
-    split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
-    with pytest.raises((RuntimeError, ValueError), match="merged"):
-        split(x, engine="tc")
     layers, dense = svdlstm.synthetic_layers(16, 1100, 1, seed=0)   # more than 1024 units
     with pytest.raises((RuntimeError, ValueError), match="units|ranks"):
         svdlstm.full_model_from_weights(layers, dense, return_sequences=True)(x, engine="tc")
@@ -351,7 +387,10 @@ def test_auto_engine_regime_switch(monkeypatch):
     assert r2.last_engine() == svdlstm.ENGINE_TC
     split = svdlstm.make_LSTM_singular_model(_models(256, 1)[0], merged_kernel=False, return_sequences=True)
     split(xb[:256])
-    assert split.last_engine() == svdlstm.ENGINE_GENERAL  # split cells are an FP32-engine form
+    assert split.last_engine() == svdlstm.ENGINE_TC       # split cells (the reference driver's form) take the fast path too
+    split512 = svdlstm.make_LSTM_singular_model(_models(512, 1)[0], merged_kernel=False, return_sequences=True)
+    split512(xb[:256])
+    assert split512.last_engine() == svdlstm.ENGINE_GENERAL  # ... unless neither merge route fits (gate ranks sum > 256, kin > 256)
     layers, dense = svdlstm.load_model_weights_npz(GOLDEN_W)
     small = svdlstm.full_model_from_weights(layers, dense)
     small(xb[:512])
