@@ -102,7 +102,8 @@ def main():
     summ = os.path.join(ROOT, "scripts", "ncu_summary.py")
     for rep, pat, dst in [("tc_layer_rank256_%s" % R, "lstm_tc", "tc_pipe_rank256_%s.txt" % R), ("tc_layer_rank128_%s" % R, "lstm_tc", "tc_pipe_rank128_%s.txt" % R),
                           ("tc_layer_rank32_%s" % R, "lstm_tc", "tc_pipe_rank32_%s.txt" % R), ("tc_pipe_c5_%s" % R, "lstm_tc", "tc_pipe_c5_%s.txt" % R),
-                          ("b1_wavefront_%s" % R, "lstm_wavefront", "b1_wavefront_%s.txt" % R)]:
+                          ("b1_wavefront_%s" % R, "lstm_wavefront", "b1_wavefront_%s.txt" % R),
+                          ("general_fp32_%s" % R, "lstm_general", "general_fp32_%s.txt" % R)]:
         rp = os.path.join(O, rep + ".ncu-rep")
         pre = os.path.join(O, rep + ".txt")          # condensed on the GPU box by profile_round.sh (the reports exceed gpurun's 64 MiB)
         if os.path.exists(pre) and os.path.getsize(pre) > 200:

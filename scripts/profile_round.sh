@@ -26,6 +26,11 @@ CMD="python scripts/prof_batch1.py"
 $CMD > $O/plain_b1.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:lstm_wavefront_kernel -s 1 -c 1 -f -o $O/b1_wavefront_$R $CMD > $O/ncu_b1.log 2>&1
 summarise b1_wavefront_$R lstm_wavefront
+# the FP32 (parity) engine at the headline batch
+CMD="python scripts/fp32_engine_time.py"
+$CMD > $O/plain_fp32.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:lstm_general_kernel -s 1 -c 1 -f -o $O/general_fp32_$R $CMD > $O/ncu_fp32.log 2>&1
+summarise general_fp32_$R lstm_general
 for f in $O/plain_tc_128.log $O/plain_tc_32.log $O/plain_b1.log; do tail -n 2 $f; done
 # C5 shard: launch list (K2 Jacobi, K3 fused penalties, packing, the units = 1024 tensor-core kernel) at T = 128, then the full set on that kernel
 CMD="python scripts/c5_parts.py 128"
