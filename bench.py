@@ -429,7 +429,12 @@ def c4_sweep(a, svdlstm, torch, dist, dev, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    svdlstm.rank_sweep(full, Xc, ranks[:2], models=models[:2], last_step_only=True, sse_over="all", target_engine="fp32")   # warm-up
+    # warm-up on THROW-AWAY models of every launch regime (each kernel instantiation is loaded lazily by the CUDA runtime on its
+    # first launch, ~0.1 s apiece, and the engine's workspaces grow with the rank): the timed sweep still packs all its own models
+    wr = sorted({min(r, R) for r in (1, 2, 24, 64, 100, 128, 200, 256)})
+    _, wmodels = svdlstm.build_rank_models(full, wr, form="singular")
+    svdlstm.rank_sweep(full, Xc, wr, models=wmodels, last_step_only=True, sse_over="all", target_engine="fp32")
+    del wmodels
     barrier()
     l0 = svdlstm.launches()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))

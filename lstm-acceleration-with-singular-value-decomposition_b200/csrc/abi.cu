@@ -247,7 +247,6 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
     return -2;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (int e = upload_model_desc(h, stream)) return e;
   ForwardArgs a{x, y, h0, c0, h_n, c_n, mask, B, T, flags};
   int launches = 0;
   int rc = 0;
@@ -265,10 +264,14 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
   if (used == SVDLSTM_ENGINE_FP32) used = wavefront_supported(h->md, a) ? SVDLSTM_ENGINE_WAVEFRONT : SVDLSTM_ENGINE_GENERAL;
   switch (used) {
     case SVDLSTM_ENGINE_GENERAL:
+      // (the device copy of the descriptor -- a device + a pinned allocation per handle -- only for the engines that read it: a
+      //  rank sweep builds hundreds of handles that only ever run on the tensor-core engine, which packs its own images)
+      if (int e = upload_model_desc(h, stream)) return e;
       rc = run_general(h->md, h->dev_md, a, stream, &launches);
       break;
     case SVDLSTM_ENGINE_WAVEFRONT:
       SVD_REQUIRE(wavefront_supported(h->md, a), "svdlstm_forward: wavefront engine needs units,input_dim,ranks <= 32, <= %d layers, n_out <= 1, no mask, and factors within the register budget", 6);
+      if (int e = upload_model_desc(h, stream)) return e;
       rc = run_wavefront(h->md, h->dev_md, a, stream, &launches);
       break;
     case SVDLSTM_ENGINE_TC: {

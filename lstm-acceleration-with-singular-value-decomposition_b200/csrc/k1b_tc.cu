@@ -1984,7 +1984,9 @@ static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state
         SVD_REQUIRE((int)slots.size() == p.n_slots_w + p.n_slots_u + p.n_slots_2, "tensor-core engine: slot table mismatch (%d vs %d)",
                     (int)slots.size(), p.n_slots_w + p.n_slots_u + p.n_slots_2);
         SVD_CUDA_TRY(cudaMalloc(&li.slots, sizeof(uint32_t) * slots.size()));
-        SVD_CUDA_TRY(cudaMemcpy(li.slots, slots.data(), sizeof(uint32_t) * slots.size(), cudaMemcpyHostToDevice));
+        // (async like the chunk table: a blocking cudaMemcpy waits for everything queued before it -- in a rank sweep that is the
+        //  previous model's whole forward, and the host then packs this model with the GPU idle)
+        SVD_CUDA_TRY(cudaMemcpyAsync(li.slots, slots.data(), sizeof(uint32_t) * slots.size(), cudaMemcpyHostToDevice, stream));
         p.slots = li.slots;
       }
       SVD_REQUIRE((int)chunks.size() == p.n_chunks_w + p.n_chunks_u + p.n_chunks_2, "tensor-core engine: chunk table mismatch");

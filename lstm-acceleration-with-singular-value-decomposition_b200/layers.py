@@ -139,8 +139,21 @@ class Handle:
             B, T = int(x.shape[0]), int(x.shape[1])
         n = self.n_out if self.n_out > 0 else self.units[-1]
         eid = _engine_id(engine)
+        dense_regime = eid == C.ENGINE_TC or (eid == C.ENGINE_AUTO and B >= C.TC_MIN_BATCH and max(self.units) >= C.TC_MIN_UNITS)
+        if (time_major or go_backwards) and mask is None and dense_regime:
+            # The tensor-core kernel walks a batch-major sequence forwards.  time_major (svd_classes_v3.py:408-419 via backend.rnn)
+            # is a transpose of the input and of the output sequence; go_backwards is the time-reversed input, outputs staying in
+            # processing order as Keras returns them.  Two cheap passes over x instead of the FP32 engine for the whole forward.
+            xs = x.transpose(0, 1) if time_major else x
+            if go_backwards:
+                xs = xs.flip(1)
+            y, hs_out, cs_out = self.forward(xs.contiguous(), initial_state=initial_state, return_sequences=return_sequences,
+                                             want_state=want_state, engine=engine)
+            if return_sequences and time_major:
+                y = y.transpose(0, 1).contiguous()
+            return y, hs_out, cs_out
         if (not return_sequences and not time_major and not go_backwards and initial_state is None and mask is None and not want_state
-                and (eid == C.ENGINE_TC or (eid == C.ENGINE_AUTO and B >= C.TC_MIN_BATCH and max(self.units) >= C.TC_MIN_UNITS))):
+                and dense_regime):
             # The tensor-core kernel always produces the whole output sequence (the Dense top is fused into its S1 tiles, one
             # step behind); return_sequences=False (svd_classes_v3.py:428-431: last output only) is the last step of it.
             try:

@@ -153,6 +153,23 @@ def test_tc_split_dropbear_model(dropbear_weights):
         assert rmse <= 3e-3 * rms, (what, rmse, rms)
 
 
+def test_tc_time_major_and_go_backwards():
+    """SingularLSTM kwargs time_major / go_backwards (svd_classes_v3.py:377-437) in the dense regime: the host feeds the
+    tensor-core kernel the batch-major / time-reversed sequence; same results as the FP32 engine's own handling of the flags."""
+    _, sm = _models(128, 2)
+    layer_model = svdlstm.truncate_singular_model(sm, 24)
+    h = layer_model._fused_handle()
+    x = torch.randn(160, 12, 16, generator=torch.Generator().manual_seed(21)).cuda()
+    for kw in (dict(go_backwards=True), dict(time_major=True), dict(go_backwards=True, time_major=True),
+               dict(go_backwards=True, return_sequences=False)):
+        xin = x.transpose(0, 1).contiguous() if kw.get("time_major") else x
+        y32, _, _ = h.forward(xin, engine="fp32", **kw)
+        ytc, _, _ = h.forward(xin, **kw)                       # engine auto: 160 sequences x 128 units -> tensor cores
+        assert h.last_engine() == svdlstm.ENGINE_TC, kw
+        assert ytc.shape == y32.shape, kw
+        assert float((ytc - y32).abs().max()) < 2e-3 * float(y32.abs().max()) + 2e-4, kw
+
+
 def test_tc_rejects_what_it_cannot_run():
     """No silent fallback: unsupported models / calls raise with the reason."""
     full, sm = _models(128, 1)
