@@ -709,6 +709,17 @@ def main():
             ms2 = timed(torch, lambda: m2(x, engine=engine), n_it)
             sweep["2F_r%d" % a.rank] = {"ms": round(ms2, 3), "Mseqsteps_per_s": round(B * T / ms2 / 1e3, 1), "iters": n_it, "engine": int(m2.last_engine()),
                                         "note": "ReducedLSTMCell model (B, C factors); on tensor cores it runs as its re-orthogonalised 3-factor equivalent"}
+            # the reference DRIVER's form (svd_acceleration_v3.py:117,143: merged_kernel=False), per-gate rank = rank / 4
+            split = svdlstm.make_LSTM_singular_model(model._full_parent, merged_kernel=False, return_sequences=True)
+            rg = max(1, a.rank // 4)
+            ms3 = svdlstm.truncate_singular_model(split, rg)
+            ms_s = timed(torch, lambda: ms3(x, engine=engine), n_it)
+            sweep["split_3F_r%d_per_gate" % rg] = {"ms": round(ms_s, 3), "Mseqsteps_per_s": round(B * T / ms_s / 1e3, 1), "iters": n_it, "engine": int(ms3.last_engine()),
+                                                   "note": "split (per-gate) SingularLSTMCell model; its gate blocks are merged when the weights are packed"}
+            ms2s = svdlstm.make_LSTM_reduced_model(split, rank=rg, merged_kernel=False)
+            ms_s2 = timed(torch, lambda: ms2s(x, engine=engine), n_it)
+            sweep["split_2F_r%d_per_gate" % rg] = {"ms": round(ms_s2, 3), "Mseqsteps_per_s": round(B * T / ms_s2 / 1e3, 1), "iters": n_it, "engine": int(ms2s.last_engine()),
+                                                   "note": "split ReducedLSTMCell model (the reference driver's timed object); gate blocks re-orthogonalised and merged at pack time"}
         line["rank_sweep"] = sweep
     if e2e is not None:
         line["e2e"] = e2e

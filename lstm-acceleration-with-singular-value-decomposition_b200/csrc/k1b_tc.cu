@@ -1481,22 +1481,18 @@ static int tc_s1u_tiles_max(int ns, bool no_s1w) { return no_s1w ? 4 : (ns == 64
 // blocks of a side are merged into such a triple when the weights are packed, by one of two routes:
 //   concat  left = [L_i | L_f | L_c | L_o] (kin x R), scale likewise, right = the block-diagonal (R x 4H) matrix of the R_g:
 //           the same contractions as the reference's split form (zero blocks are multiplied too); needs R = sum of the gate
-//           ranks <= 256 and pays off when R < kin;
+//           ranks <= 256 and pays off when R < kin.  2-factor gate blocks ([I | C_g]) are re-orthogonalised one by one first
+//           (tc_reorthogonalise), exactly like a merged 2-factor block;
 //   dense   W = sum_g (L_g sigma_g) R_g placed at gate g's columns (float64 accumulation), run as I . W like an unfactored cell:
-//           for R >= kin (a split model at full rank: R = 4 min(D, H)) and for the 2-factor split form, whose C = V1^-1 V2
-//           blocks are no FP16 material (see tc_reorthogonalise); needs kin <= 256.
+//           for R >= kin (a split model at full rank: R = 4 min(D, H)); needs kin <= 256.
 // kTcRouteNone = neither fits.
 enum { kTcRouteNone = 0, kTcRouteConcat = 1, kTcRouteDense = 2 };
 static int tc_side_route(const LayerDesc& Ld, int side, int* rank_out) {
   const int kin = side == 0 ? Ld.d_in : Ld.units;
   int R = 0;
-  bool ident = false;
   for (int bi = 0; bi < Ld.n_blocks; ++bi)
-    if (Ld.blocks[bi].from_h == side) {
-      R += Ld.blocks[bi].rank;
-      ident = ident || Ld.blocks[bi].ident;
-    }
-  if (!ident && R <= 256 && R < kin) { *rank_out = R; return kTcRouteConcat; }
+    if (Ld.blocks[bi].from_h == side) R += Ld.blocks[bi].rank;
+  if (R <= 256 && R < kin) { *rank_out = R; return kTcRouteConcat; }
   if (kin <= 256) { *rank_out = kin; return kTcRouteDense; }
   *rank_out = R;
   return kTcRouteNone;
@@ -1616,6 +1612,12 @@ static int tc_merge_side(const LayerDesc& Ld, int side, cudaStream_t stream, Blo
     return 0;
   };
   if (route == kTcRouteConcat) {
+    for (int q = 0; q < sb.n; ++q)
+      if (sb.b[q].ident) {
+        Block ortho;
+        if (int rc = tc_reorthogonalise(sb.b[q], kin, stream, &ortho, temps, launches)) return rc;
+        sb.b[q] = ortho;
+      }
     float *lc = nullptr, *sc = nullptr, *rb = nullptr;
     if (int e = alloc(&lc, (size_t)kin * rank)) return e;
     if (int e = alloc(&sc, (size_t)rank)) return e;
