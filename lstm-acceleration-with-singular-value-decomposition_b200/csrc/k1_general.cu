@@ -65,6 +65,42 @@ __device__ __forceinline__ void dot_bt(const float* __restrict__ w, int ld, cons
   }
 }
 
+// two weight columns against the same activations: half the shared-memory loads per FMA
+template <int BT>
+__device__ __forceinline__ void dot2_bt(const float* __restrict__ wa, const float* __restrict__ wb, int ld, const float* __restrict__ in, int n,
+                                        float (&accA)[BT], float (&accB)[BT]) {
+  constexpr int U = kUnroll;   // per column (4 deep per column: 47 -> 45 ms and much worse at small tiles; 16 deep: no further gain)
+  int k = 0;
+  for (; k + U <= n; k += U) {
+    float va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      va[u] = __ldg(wa + (size_t)(k + u) * ld);
+      vb[u] = __ldg(wb + (size_t)(k + u) * ld);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[BT];
+      load_bt<BT>(in + (k + u) * BT, v);
+#pragma unroll
+      for (int bt = 0; bt < BT; ++bt) {
+        accA[bt] = fmaf(v[bt], va[u], accA[bt]);
+        accB[bt] = fmaf(v[bt], vb[u], accB[bt]);
+      }
+    }
+  }
+  for (; k < n; ++k) {
+    const float a = __ldg(wa + (size_t)k * ld), b = __ldg(wb + (size_t)k * ld);
+    float v[BT];
+    load_bt<BT>(in + k * BT, v);
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt) {
+      accA[bt] = fmaf(v[bt], a, accA[bt]);
+      accB[bt] = fmaf(v[bt], b, accB[bt]);
+    }
+  }
+}
+
 // BT consecutive floats (one feature of the CTA's BT sequences; 16-byte aligned when BT >= 4) -> registers
 template <int BT>
 __device__ __forceinline__ void load_bt(const float* __restrict__ p, float (&v)[BT]) {
@@ -194,42 +230,54 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
       __syncthreads();
 
       // ---- stages 2 + 3: one thread = the four gate columns of one unit, for the CTA's BT sequences; gates + state update
-      //      (Keras _compute_carry_and_output_fused) straight from the accumulators.  Column order i, c~, f, o keeps only the
-      //      running product / new cell state live between columns. ----------------------------------------------------------
+      //      (Keras _compute_carry_and_output_fused) straight from the accumulators. ----------------------------------------------
       for (int j = tid; j < H; j += kThreads) {
         float keep[BT];   // sigmoid(i) -> sigmoid(i) tanh(c~) -> c_new
         float h_new[BT];
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int g = gi == 0 ? 0 : (gi == 1 ? 2 : (gi == 2 ? 1 : 3));
-          const int n = g * H + j;
-          float acc[BT];
-          const float bv = __ldg(Ld.bias + n);
+        for (int gp = 0; gp < 2; ++gp) {   // gate columns in pairs (i, c~) then (f, o): one load of p serves both
+          const int nA = (gp == 0 ? 0 : 1) * H + j, nB = (gp == 0 ? 2 : 3) * H + j;
+          float accA[BT], accB[BT];
+          const float bA = __ldg(Ld.bias + nA), bB = __ldg(Ld.bias + nB);
 #pragma unroll
-          for (int bt = 0; bt < BT; ++bt) acc[bt] = bv;
+          for (int bt = 0; bt < BT; ++bt) { accA[bt] = bA; accB[bt] = bB; }
           for (int bi = 0; bi < Ld.n_blocks; ++bi) {
             const Block& blk = Ld.blocks[bi];
-            int rel = n - blk.out0;
-            if (rel < 0) continue;
             const float* pp = s_p + blk.p_off * BT;
+            // where a column falls in this block: 0 nowhere, 1 the identity part of a 2-factor block, 2 the right factor
+            int relA = nA - blk.out0, relB = nB - blk.out0;
+            int kindA = relA < 0 ? 0 : 2, kindB = relB < 0 ? 0 : 2;
             if (blk.ident) {
-              if (rel < blk.rank) {
-#pragma unroll
-                for (int bt = 0; bt < BT; ++bt) acc[bt] += pp[rel * BT + bt];
-                continue;
-              }
-              rel -= blk.rank;
+              if (kindA) { if (relA < blk.rank) kindA = 1; else relA -= blk.rank; }
+              if (kindB) { if (relB < blk.rank) kindB = 1; else relB -= blk.rank; }
             }
-            if (rel >= blk.ncols) continue;
-            dot_bt<BT>(blk.right + rel, blk.right_ld, pp, blk.rank, acc);
+            if (kindA == 2 && relA >= blk.ncols) kindA = 0;
+            if (kindB == 2 && relB >= blk.ncols) kindB = 0;
+            if (kindA == 2 && kindB == 2) {
+              dot2_bt<BT>(blk.right + relA, blk.right + relB, blk.right_ld, pp, blk.rank, accA, accB);
+              continue;
+            }
+            if (kindA == 1) {
+#pragma unroll
+              for (int bt = 0; bt < BT; ++bt) accA[bt] += pp[relA * BT + bt];
+            } else if (kindA == 2) {
+              dot_bt<BT>(blk.right + relA, blk.right_ld, pp, blk.rank, accA);
+            }
+            if (kindB == 1) {
+#pragma unroll
+              for (int bt = 0; bt < BT; ++bt) accB[bt] += pp[relB * BT + bt];
+            } else if (kindB == 2) {
+              dot_bt<BT>(blk.right + relB, blk.right_ld, pp, blk.rank, accB);
+            }
           }
           const float* c_old = s_c(l) + j * BT;
 #pragma unroll
           for (int bt = 0; bt < BT; ++bt) {
-            if (gi == 0) keep[bt] = sigmoid_acc(acc[bt]);
-            else if (gi == 1) keep[bt] *= tanhf(acc[bt]);
-            else if (gi == 2) keep[bt] = sigmoid_acc(acc[bt]) * c_old[bt] + keep[bt];
-            else h_new[bt] = sigmoid_acc(acc[bt]) * tanhf(keep[bt]);
+            if (gp == 0) keep[bt] = sigmoid_acc(accA[bt]) * tanhf(accB[bt]);
+            else {
+              keep[bt] = sigmoid_acc(accA[bt]) * c_old[bt] + keep[bt];
+              h_new[bt] = sigmoid_acc(accB[bt]) * tanhf(keep[bt]);
+            }
           }
         }
 #pragma unroll
