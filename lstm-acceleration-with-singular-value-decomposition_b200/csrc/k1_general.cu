@@ -231,6 +231,63 @@ __global__ void __launch_bounds__(kThreads) lstm_general_kernel(const ModelDesc*
 
       // ---- stages 2 + 3: one thread = the four gate columns of one unit, for the CTA's BT sequences; gates + state update
       //      (Keras _compute_carry_and_output_fused) straight from the accumulators. ----------------------------------------------
+      if (4 * H <= kThreads) {
+        // Narrow layers (the shipped model: 15 units): a thread per UNIT would leave most of the CTA idle behind H long serial
+        // chains -- a thread per gate COLUMN instead (quad of lanes = the i, f, c~, o columns of one unit), the quad's four
+        // pre-activations gathered by shuffles, lane 0 of the quad updating the cell.
+        const int j = tid >> 2, q = tid & 3;
+        const bool act = j < H;
+        float acc[BT];
+#pragma unroll
+        for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+        if (act) {
+          const int n = q * H + j;
+          const float bv = __ldg(Ld.bias + n);
+#pragma unroll
+          for (int bt = 0; bt < BT; ++bt) acc[bt] = bv;
+          for (int bi = 0; bi < Ld.n_blocks; ++bi) {
+            const Block& blk = Ld.blocks[bi];
+            int rel = n - blk.out0;
+            if (rel < 0) continue;
+            const float* pp = s_p + blk.p_off * BT;
+            if (blk.ident) {
+              if (rel < blk.rank) {
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) acc[bt] += pp[rel * BT + bt];
+                continue;
+              }
+              rel -= blk.rank;
+            }
+            if (rel >= blk.ncols) continue;
+            dot_bt<BT>(blk.right + rel, blk.right_ld, pp, blk.rank, acc);
+          }
+        }
+        const int quad0 = (tid & 31) & ~3;
+#pragma unroll
+        for (int bt = 0; bt < BT; ++bt) {
+          const float zi = __shfl_sync(0xffffffffu, acc[bt], quad0), zf = __shfl_sync(0xffffffffu, acc[bt], quad0 + 1);
+          const float zc = __shfl_sync(0xffffffffu, acc[bt], quad0 + 2), zo = __shfl_sync(0xffffffffu, acc[bt], quad0 + 3);
+          if (act && q == 0) {
+            const int idx = j * BT + bt;
+            const float c_new = sigmoid_acc(zf) * s_c(l)[idx] + sigmoid_acc(zi) * tanhf(zc);
+            const float hv = sigmoid_acc(zo) * tanhf(c_new);
+            if (HAS_MASK) {
+              const int b = b0 + bt;
+              const bool valid = (b < B) ? (a.mask[(size_t)b * T + t] != 0) : true;
+              if (valid) {
+                s_c(l)[idx] = c_new;
+                s_h(l)[idx] = hv;
+                s_o(l)[idx] = hv;
+              } else if (zero_mask_out) {
+                s_o(l)[idx] = 0.f;
+              }
+            } else {
+              s_c(l)[idx] = c_new;
+              s_h(l)[idx] = hv;
+            }
+          }
+        }
+      } else
       for (int j = tid; j < H; j += kThreads) {
         float keep[BT];   // sigmoid(i) -> sigmoid(i) tanh(c~) -> c_new
         float h_new[BT];
