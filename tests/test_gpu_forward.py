@@ -126,6 +126,36 @@ def test_layer_kwargs(oracle, dropbear_weights):
         svdlstm.LSTM(15, weights=[W, U, b], engine="wavefront")(x, mask=mask)
 
 
+@pytest.mark.parametrize("H", [15, 80])
+def test_general_engine_tile_width_invariance(monkeypatch, H):
+    """The FP32 general engine processes BT = 1..16 sequences per CTA (chosen from the batch); every sequence's arithmetic is
+    the same at every width, so the outputs -- and the final states, with a mask, with both cell forms -- must be BIT-identical
+    across widths.  H = 15 takes the narrow-layer path (thread per gate column), H = 80 the wide one (thread per unit)."""
+    rng = np.random.default_rng(40 + H)
+    W = (0.4 * rng.standard_normal((16, 4 * H))).astype(np.float32)
+    U = (0.4 * rng.standard_normal((H, 4 * H))).astype(np.float32)
+    b = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    dense = ((0.3 * rng.standard_normal((H, 1))).astype(np.float32), np.zeros(1, np.float32))
+    full_m = svdlstm.full_model_from_weights([(W, U, b)], dense)
+    sm = svdlstm.make_LSTM_singular_model(full_m, merged_kernel=False, return_sequences=True)
+    models = [full_m, svdlstm.truncate_singular_model(sm, 5), svdlstm.make_LSTM_reduced_model(sm, rank=6, merged_kernel=False)]
+    x = torch.randn(2100, 5, 16, generator=torch.Generator().manual_seed(41)).cuda()
+    mask = (torch.rand(2100, 5, generator=torch.Generator().manual_seed(42)) > 0.3).cuda()
+    lay = svdlstm.LSTM(H, weights=[W, U, b], return_sequences=True, return_state=True, engine="general")
+    ref = None
+    for bt in ("1", "4", "16"):
+        monkeypatch.setenv("SVDLSTM_GEN_BT", bt)
+        outs = [m(x, engine="general") for m in models] + list(lay(x, mask=mask))
+        if ref is None:
+            ref = outs
+        else:
+            for i, (a, r) in enumerate(zip(outs, ref)):
+                assert torch.equal(a, r), "BT=%s output %d differs from BT=1" % (bt, i)
+    monkeypatch.delenv("SVDLSTM_GEN_BT")
+    for m, r in zip(models, ref):          # the library's own choice (2100 sequences -> 16 per CTA)
+        assert torch.equal(m(x, engine="general"), r)
+
+
 def test_cell_call_contract(oracle, full, dropbear_weights):
     sm = svdlstm.make_LSTM_singular_model(full, merged_kernel=True)
     rm = svdlstm.make_LSTM_reduced_model(sm, rank=7)
