@@ -255,7 +255,7 @@ class Sequential:
 
         A serving loop keeps two requests in flight: the host->device copy of request i+1 (own copy stream, second device
         buffer) overlaps the forward pass of request i, and each result is copied into one of two pinned host buffers on
-        the compute stream.  ``.result()`` returns a numpy VIEW of that pinned buffer, valid until the second-next request
+        a third stream (under the forward pass of request i+1).  ``.result()`` returns a numpy VIEW of that pinned buffer, valid until the second-next request
         of the same shape is issued (copy it to keep it longer).  A host input must stay unmodified until ``.result()``
         returns (its copy to the device is asynchronous when the buffer is pinned)."""
         dev = C.require_cuda()
@@ -271,7 +271,8 @@ class Sequential:
         st = getattr(self, "_serve", None)
         if st is None or st["key"] != key:
             st = {"key": key, "i": 0, "x_dev": [torch.empty(xh.shape, dtype=torch.float32, device=dev) for _ in range(2)],
-                  "y_host": [None, None], "copy_stream": torch.cuda.Stream(device=dev),
+                  "y_host": [None, None], "copy_stream": torch.cuda.Stream(device=dev), "d2h_stream": torch.cuda.Stream(device=dev),
+                  "fwd_done": [torch.cuda.Event() for _ in range(2)],
                   "h2d_done": [torch.cuda.Event() for _ in range(2)], "x_free": [torch.cuda.Event() for _ in range(2)],
                   "y_done": [torch.cuda.Event() for _ in range(2)]}
             main = torch.cuda.current_stream(dev)
@@ -290,8 +291,14 @@ class Sequential:
         st["x_free"][k].record(main)
         if st["y_host"][k] is None or tuple(st["y_host"][k].shape) != tuple(y.shape):
             st["y_host"][k] = torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory()
-        st["y_host"][k].copy_(y, non_blocking=True)
-        st["y_done"][k].record(main)
+        # the result goes home on its own stream: the next request's forward starts right behind this one instead of behind its copy
+        st["fwd_done"][k].record(main)
+        d2h = st["d2h_stream"]
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(st["fwd_done"][k])
+            st["y_host"][k].copy_(y, non_blocking=True)
+            y.record_stream(d2h)
+            st["y_done"][k].record(d2h)
         return _Pending(st["y_done"][k], None, st["y_host"][k])
 
     # ---- training (svd_acceleration_v3.py:111-128) ------------------------------------------------------------------------
