@@ -656,12 +656,12 @@ def main():
                 "traffic_source": (ncu or {}).get("source"),
                 "ncu_tensor_pipe_active_pct": (ncu or {}).get("tensor_pipe_active_pct_rank_%d" % a.rank),
                 "peak_source": pk["source"] + " (cuBLAS bf16: sustained = seconds-long loop under the power cap, burst = best of 10; f16 runs at the same tensor rate)",
-                "kernel": "lstm_tc_pipe_kernel: all %d layers in one co-resident launch, 64-sequence tiles (one forward = pack_x + this launch)"
-                          % a.layers if eng_id == 3 else eng_name,
+                "kernel": ("lstm_tc_pipe_kernel: all %d layers in one co-resident launch, 64-sequence tiles (one forward = %d launch(es); x is read "
+                           "raw by layer 0, no packing pass)" % (a.layers, max(1, launches // max(a.steps, 1)))) if eng_id == 3 else eng_name,
                 "algorithmic_flops_per_launch": fl, "kernel_ms": kern_ms,
                 "hbm_bytes_algorithmic": int(B * T * (D * 4 + 4)),
-                "hbm_bytes_note": "x in (float32) + y out (float32) only; the FP16 x image and the inter-layer hand-off images this design adds "
-                                  "show up in `traffic`, not here"}
+                "hbm_bytes_note": "x in (float32) + y out (float32) only; anything else the design moves through HBM shows up in `traffic` "
+                                  "(round 2: hand-off rings stay in L2, x is read raw -> traffic = 1.005x this figure)"}
     line = {"metric": "low-rank LSTM timesteps/sec (batch 4096)", "value": value, "unit": "sequence-timesteps/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16" if eng_id == 3 else "f32", "data": "synthetic", "config": workload_config(a),

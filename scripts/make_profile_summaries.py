@@ -93,7 +93,7 @@ def main():
         fw = sum(a[2] for k, a in agg.items() if "pack_x" in k or "lstm_tc" in k) / n_fw
         traffic["rank_128"] = fw
         traffic["source"] = ("profiles/launches_bench_%s.csv (%s): dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one forward "
-                             "(pack_x + lstm_tc_pipe_kernel), C3 rank 128, mean of %d forwards" % (R, stamp, n_fw))
+                             "(lstm_tc_pipe_kernel, plus pack_x when the build uses it), C3 rank 128, mean of %d forwards" % (R, stamp, n_fw))
         tc = sum(a[1] for k, a in agg.items() if "lstm_tc" in k)
         traffic["kernel_share_of_step_rank_128"] = tc / tot
     lc = os.path.join(O, "launches_c5_%s.csv" % R)
