@@ -137,6 +137,23 @@ def test_tc_split_forms_match_oracle(oracle, H, L):
     assert m3.last_engine() == svdlstm.ENGINE_TC
 
 
+def test_tc_split_ragged_ranks_from_cutoff(oracle):
+    """make_LSTM_reduced_model(smodel, cutoff=c, merged_kernel=False) (svd_acceleration_v3.py:143) keeps a different rank in every
+    gate block; the merged block the tensor-core engine builds from them must place every ragged piece where it belongs."""
+    full, _ = _models(128, 2, seed=3)
+    split = svdlstm.make_LSTM_singular_model(full, merged_kernel=False, return_sequences=True)
+    gate_max = [np.abs(w).reshape(4, -1).max(1).min() for l in split.layers[:-1] for w in l.get_weights()[:2]]
+    cutoff = 0.6 * float(min(gate_max))                # every gate block keeps something; how much differs from block to block
+    red = svdlstm.make_LSTM_reduced_model(split, cutoff=cutoff, merged_kernel=False)
+    ranks = {int(w.shape[1]) for l in red.layers[:-1] for w in l.get_weights()[:-1:2]}
+    assert len(ranks) > 1, "the cutoff did not produce ragged ranks: %s" % ranks
+    x = np.random.default_rng(14).standard_normal((130, 12, 16)).astype(np.float32)
+    y = red.predict(x, engine="tc")
+    assert red.last_engine() == svdlstm.ENGINE_TC
+    _check(y, oracle_twin(oracle, red).predict(x), "tc split 2F ragged ranks %s" % sorted(ranks))
+    assert np.abs(y - red.predict(x, engine="fp32")).max() < 2e-3 * np.abs(y).max() + 2e-4
+
+
 def test_tc_split_dropbear_model(dropbear_weights):
     """The shipped 3 x 15 model in the reference's own configuration (split 3-factor and its 2-factor reduction) on the
     tensor-core engine, against the FP32 engine: RMSE <= 3e-3 of the output RMS (the bar of the merged DROPBEAR tests)."""
