@@ -104,6 +104,14 @@ int svdlstm_host_alloc(void** out, size_t bytes, int write_combined);
 int svdlstm_host_free(void* p);
 
 /* Number of kernels the last forward on this handle launched, and which engine ran. */
+/* One forward from a PINNED host array with the upload INSIDE the forward (latency of a single `rmodel.predict(X)`,
+ * svd_acceleration_v3.py:150-151): x_host (B,T,D) is copied to x_dev in n_slices time slices on `copy_stream`; the tensor-core
+ * kernel is launched on `stream` as soon as the first slice has landed and follows the upload through a progress word (its layer-0
+ * input warp reads x(t) straight from x_dev).  Same result as svdlstm_forward(ENGINE_TC) on the uploaded array.  Returns -3 if the
+ * model / batch does not take the raw-x pipelined launch: the slices are enqueued all the same, so the caller falls back to
+ * svdlstm_forward on `stream` after waiting for `copy_stream`.  x_host must stay unmodified until `copy_stream` has drained.   */
+int svdlstm_forward_streamed_input(svdlstm_handle h, const float* x_host, float* x_dev, int B, int T, float* y, int n_slices,
+                                   void* copy_stream, void* stream);
 int svdlstm_last_launches(svdlstm_handle h);
 int svdlstm_last_engine(svdlstm_handle h);
 

@@ -32,7 +32,7 @@ ENGINE_NAMES = {"auto": 0, "general": 1, "wavefront": 2, "tc": 3, "tc_f16": 3, "
 
 EXPORTS = [
     "svdlstm_create", "svdlstm_destroy", "svdlstm_set_full_weights", "svdlstm_set_singular_weights",
-    "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_last_launches",
+    "svdlstm_set_reduced_weights", "svdlstm_set_dense_top", "svdlstm_forward", "svdlstm_forward_streamed_input", "svdlstm_last_launches",
     "svdlstm_last_engine", "svdlstm_count_weights", "svdlstm_host_alloc", "svdlstm_host_free", "svdlstm_svd_jacobi_batched",
     "svdlstm_reduce_factors", "svdlstm_reduce_factors_batched", "svdlstm_scaled_matmul", "svdlstm_penalties", "svdlstm_sweep_sse", "svdlstm_last_error",
     "svdlstm_version", "svdlstm_stream_open", "svdlstm_stream_step", "svdlstm_stream_run", "svdlstm_stream_reset",
@@ -83,6 +83,8 @@ def lib() -> ctypes.CDLL:
     L.svdlstm_set_dense_top.restype = ci
     L.svdlstm_forward.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]
     L.svdlstm_forward.restype = ci
+    L.svdlstm_forward_streamed_input.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp, vp]
+    L.svdlstm_forward_streamed_input.restype = ci
     L.svdlstm_last_launches.argtypes = [vp]
     L.svdlstm_last_launches.restype = ci
     L.svdlstm_last_engine.argtypes = [vp]

@@ -72,6 +72,10 @@ int svdlstm_create(svdlstm_handle* out, int n_layers, int input_dim, const int* 
     d = units[l];
   }
   m->dev_md = nullptr;
+  m->xr_dev = nullptr;
+  m->xr_host = nullptr;
+  m->xr_event = nullptr;
+  m->xr_done = nullptr;
   m->pinned_md = nullptr;
   m->md_event = nullptr;
   m->md_version = 0;
@@ -90,6 +94,10 @@ void svdlstm_destroy(svdlstm_handle h) {
   if (h->pinned_md) cudaFreeHost(h->pinned_md);
   if (h->md_event) cudaEventDestroy(h->md_event);
   if (h->tc) tc_free(h->tc);
+  if (h->xr_dev) cudaFree(h->xr_dev);
+  if (h->xr_host) cudaFreeHost(h->xr_host);
+  if (h->xr_event) cudaEventDestroy(h->xr_event);
+  if (h->xr_done) cudaEventDestroy(h->xr_done);
   delete h;
 }
 
@@ -294,6 +302,61 @@ int svdlstm_forward(svdlstm_handle h, const float* x, int B, int T, float* y, co
   }
   h->last_launches = launches;
   h->last_engine = used;
+  return rc;
+}
+
+constexpr int kMaxInputSlices = 64;
+
+int svdlstm_forward_streamed_input(svdlstm_handle h, const float* x_host, float* x_dev, int B, int T, float* y, int n_slices, void* copy_stream_,
+                                   void* stream_) {
+  SVD_REQUIRE(h != nullptr, "svdlstm_forward_streamed_input: null handle");
+  SVD_REQUIRE(x_host != nullptr && x_dev != nullptr && y != nullptr, "svdlstm_forward_streamed_input: null x_host / x_dev / y");
+  SVD_REQUIRE(B >= 1 && T >= 1, "svdlstm_forward_streamed_input: B=%d T=%d must be >= 1", B, T);
+  SVD_REQUIRE(n_slices >= 1 && n_slices <= kMaxInputSlices, "svdlstm_forward_streamed_input: n_slices=%d not in [1,%d]", n_slices, kMaxInputSlices);
+  SVD_REQUIRE(copy_stream_ != stream_, "svdlstm_forward_streamed_input: the upload needs a stream of its own");
+  for (int l = 0; l < h->md.n_layers; ++l) SVD_REQUIRE(h->layer_set[l], "svdlstm_forward_streamed_input: weights of layer %d were never set", l);
+  cudaStream_t cs = (cudaStream_t)copy_stream_, stream = (cudaStream_t)stream_;
+  ForwardArgs a{x_dev, y, nullptr, nullptr, nullptr, nullptr, nullptr, B, T, SVDLSTM_RETURN_SEQUENCES, nullptr};
+  const char* why = "";
+  if (!tc_supported(h->md, a, &why)) {
+    set_error("svdlstm_forward_streamed_input: tensor-core engine unsupported for this model/call: %s", why);
+    return -3;
+  }
+  if (!h->xr_dev) SVD_CUDA_TRY(cudaMalloc(&h->xr_dev, sizeof(int)));
+  if (!h->xr_host) {
+    SVD_CUDA_TRY(cudaMallocHost(&h->xr_host, sizeof(int) * (kMaxInputSlices + 1)));
+  }
+  if (!h->xr_event) SVD_CUDA_TRY(cudaEventCreateWithFlags(&h->xr_event, cudaEventDisableTiming));
+  if (!h->xr_done) SVD_CUDA_TRY(cudaEventCreateWithFlags(&h->xr_done, cudaEventDisableTiming));
+  else SVD_CUDA_TRY(cudaEventSynchronize(h->xr_done));   // the previous call's publishes still read the pinned table until then
+  // the previous forward of this handle (any stream) may still be polling the progress word / reading the table's DMA source
+  if (h->md_event) SVD_CUDA_TRY(cudaStreamWaitEvent(cs, h->md_event, 0));
+  const int D = h->md.input_dim;
+  const int per = ((T + n_slices - 1) / n_slices + 1) & ~1;   // even number of steps per slice
+  h->xr_host[0] = 0;
+  SVD_CUDA_TRY(cudaMemcpyAsync(h->xr_dev, h->xr_host, sizeof(int), cudaMemcpyHostToDevice, cs));
+  const size_t pitch = sizeof(float) * (size_t)T * D;
+  int k = 0;
+  for (int t0 = 0; t0 < T; t0 += per, ++k) {
+    const int t1 = t0 + per < T ? t0 + per : T;
+    SVD_CUDA_TRY(cudaMemcpy2DAsync(x_dev + (size_t)t0 * D, pitch, x_host + (size_t)t0 * D, pitch, sizeof(float) * (size_t)(t1 - t0) * D, (size_t)B,
+                                   cudaMemcpyHostToDevice, cs));
+    h->xr_host[k + 1] = t1;
+    SVD_CUDA_TRY(cudaMemcpyAsync(h->xr_dev, h->xr_host + k + 1, sizeof(int), cudaMemcpyHostToDevice, cs));
+    if (k == 0) SVD_CUDA_TRY(cudaEventRecord(h->xr_event, cs));
+  }
+  SVD_CUDA_TRY(cudaEventRecord(h->xr_done, cs));
+  SVD_CUDA_TRY(cudaStreamWaitEvent(stream, h->xr_event, 0));
+  a.x_ready = h->xr_dev;
+  int launches = 0;
+  const int rc = run_tc(h->md, &h->tc, h->tc_dirty, a, stream, &launches);
+  if (rc == 0) {
+    h->tc_dirty = false;
+    if (!h->md_event) SVD_CUDA_TRY(cudaEventCreateWithFlags(&h->md_event, cudaEventDisableTiming));
+    SVD_CUDA_TRY(cudaEventRecord(h->md_event, stream));
+    h->last_launches = launches;
+    h->last_engine = SVDLSTM_ENGINE_TC;
+  }
   return rc;
 }
 

@@ -76,6 +76,8 @@ struct ForwardArgs {
   float* c_n;
   const uint8_t* mask;
   int B, T, flags;
+  const int* x_ready;   // optional (tensor-core raw-x launch only): device word = number of leading time steps of x that have landed
+                        // (x is still being uploaded, time slice by time slice, while the kernel runs); nullptr: x is complete
 };
 
 // ---- real-time stream (k1_wavefront.cu <STREAM>, stream.cu): rings in host-mapped pinned memory -------------------------------
@@ -118,6 +120,10 @@ struct svdlstm_model_s {
   int last_launches;
   int last_engine;
   int64_t n_weights[svdlstm::kMaxLayers];
+  int* xr_dev;                       // svdlstm_forward_streamed_input: progress word on the device ...
+  int* xr_host;                      // ... and the pinned table of the values the copy stream publishes (slice ends)
+  cudaEvent_t xr_event;              // first slice landed
+  cudaEvent_t xr_done;               // whole upload enqueued by the last call has drained (the table may be rewritten)
 };
 
 namespace svdlstm {

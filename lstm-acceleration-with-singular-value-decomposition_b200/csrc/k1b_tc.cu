@@ -289,6 +289,7 @@ struct TcLayerParams {
                             // The layers run a few steps apart, so a short ring stays L2-resident: the hidden sequence never goes to HBM.
   const float* x_raw;       // layer 0: the caller's x (B, T, D) float32 -- read and converted by the input warp itself (no pack_x pass,
   int x_dim;                //          no FP16 image of x in HBM); nullptr: bulk copies from in_seq
+  const int* x_ready;       // with x_raw: steps of x uploaded so far (the host is still copying x in time slices), or nullptr
   uint8_t* out_seq;         // activation tile images [cta][t], K = H            (store_h)
   float* y;                 // (B, T, n_dense) fused Dense-top output            (n_dense > 0)
   const float* dense_bias;
@@ -446,8 +447,8 @@ __host__ __device__ inline void for_seg_2(const P& p, F&& f) {
 // for the next ring stage, and the ring runs 2-3 steps ahead of the MMAs.  Rows k >= D of the tile keep the zeros of the initial
 // fill.  Compiled only into the RAWX instantiations of the kernel (see tc_layer_body).
 template <int NS>
-__device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, int D, int B, int T, int cta, uint32_t inbuf, uint32_t in_tile, int nst,
-                                            uint32_t bar_full0, uint32_t bar_empty0) {
+__device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, const int* __restrict__ x_ready, int D, int B, int T, int cta,
+                                            uint32_t inbuf, uint32_t in_tile, int nst, uint32_t bar_full0, uint32_t bar_empty0) {
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kLBO = (uint32_t)NS * 16u;     // bytes between consecutive k-groups (8 K rows) of an activation tile
   constexpr int SPL = NS / 32;                      // sequences per lane
@@ -463,11 +464,27 @@ __device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, int
       const int b = cta * NS + lane + 32 * q;
       const float4* src = reinterpret_cast<const float4*>(x + ((size_t)b * T + t) * D);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[q][c] = (b < B && 4 * c < D) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 4; ++c) v[q][c] = (b < B && 4 * c < D) ? __ldcg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // (L2 only: x may
+    }                                                                                                               //  still be arriving by DMA)
+  };
+  // x uploaded in time slices while the kernel runs (svdlstm_forward_streamed_input): the host publishes, in stream order behind
+  // each slice, how many steps have landed; re-read only when the next step is not covered by the last value seen
+  int avail = x_ready != nullptr ? 0 : T;
+  auto wait_for = [&](int t) {
+    if (t < avail) return;
+    if (lane == 0) {
+      int a = ld_acquire_gpu(x_ready);
+      while (a <= t) {
+        __nanosleep(200);
+        a = ld_acquire_gpu(x_ready);
+      }
+      avail = a;
     }
+    avail = __shfl_sync(0xffffffffu, avail, 0);
   };
   int ld_s = 0;
   uint32_t ld_n = 0;
+  wait_for(0);
   if (fast) load_step(0);
 #pragma unroll 1
   for (int ld_t = 0; ld_t < T; ++ld_t) {
@@ -499,12 +516,13 @@ __device__ __forceinline__ void tc_raw_x_loader(const float* __restrict__ x, int
         const float* src = x + ((size_t)b * T + ld_t) * D;
         const uint32_t col = tile + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 2u;
 #pragma unroll 4
-        for (int kk = 0; kk < D; ++kk) st16(col + (uint32_t)(kk / 8) * kLBO + (uint32_t)(kk % 8) * 16u, b < B ? __ldg(src + kk) : 0.f);
+        for (int kk = 0; kk < D; ++kk) st16(col + (uint32_t)(kk / 8) * kLBO + (uint32_t)(kk % 8) * 16u, b < B ? __ldcg(src + kk) : 0.f);
       }
     }
     fence_proxy_async();     // generic-proxy stores -> visible to the MMAs' async proxy
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_full0 + 8u * (uint32_t)ld_s);
+    if (ld_t + 1 < T) wait_for(ld_t + 1);
     if (fast && ld_t + 1 < T) load_step(ld_t + 1);     // in flight while this warp waits for the next ring stage
     if (++ld_s == nst) { ld_s = 0; ++ld_n; }
   }
@@ -653,7 +671,7 @@ __device__ __forceinline__ void tc_layer_body(const TcLayerParams& p, const int 
   } else if (warp == 3) {
     // ======================= input ring ==========================================================================
     if (RAWX && p.x_raw != nullptr) {
-      if constexpr (RAWX) tc_raw_x_loader<NS>(p.x_raw, p.x_dim, p.B, T, cta, sbase + sp.inbuf, in_tile, nst, bar(BAR_IN_FULL), bar(BAR_IN_EMPTY));
+      if constexpr (RAWX) tc_raw_x_loader<NS>(p.x_raw, p.x_ready, p.x_dim, p.B, T, cta, sbase + sp.inbuf, in_tile, nst, bar(BAR_IN_FULL), bar(BAR_IN_EMPTY));
     } else if (lane == 0) {
       // one bulk copy per step, as early as the ring allows
       const int iring = p.in_ring;
@@ -2066,6 +2084,10 @@ static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state
     const TcLayerParams& lp = st->layers[L - 1].prm;
     raw_x = lp.streaming && (lp.n_chunks_u + lp.n_chunks_2) >= 32 && st->layers[0].prm.streaming;
   }
+  if (!raw_x && a.x_ready != nullptr) {
+    set_error("tensor-core engine: this model / batch does not take the raw-x pipelined launch (needed for a streamed input upload)");
+    return -3;
+  }
   if (!raw_x) {
     const int D = md.input_dim;
     const int TT = D <= 16 ? 8 : (D <= 32 ? 4 : 2);
@@ -2090,6 +2112,7 @@ static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state
     p.in_ring = (pipe && l > 0) ? ring : 0;
     p.out_ring = (pipe && l + 1 < L) ? ring : 0;
     p.x_raw = (l == 0 && raw_x) ? a.x : nullptr;
+    p.x_ready = (l == 0 && raw_x) ? a.x_ready : nullptr;
     p.x_dim = md.input_dim;
     p.out_seq = (p.store_h || p.store_x) ? ws->seq[out_slot] : nullptr;
     p.y = a.y;

@@ -13,6 +13,8 @@ from __future__ import annotations
 import warnings
 from typing import List, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -282,12 +284,31 @@ class Sequential:
         k = st["i"] & 1
         st["i"] += 1
         main = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(st["copy_stream"]):
-            st["copy_stream"].wait_event(st["x_free"][k])          # the forward that last read this buffer has finished
-            st["x_dev"][k].copy_(xh, non_blocking=True)
-            st["h2d_done"][k].record(st["copy_stream"])
-        main.wait_event(st["h2d_done"][k])
-        y = self.__call__(st["x_dev"][k], engine=engine)
+        y = None
+        st["copy_stream"].wait_event(st["x_free"][k])              # the forward that last read this buffer has finished
+        eng = engine if engine is not None else self.engine
+        B, T = int(xh.shape[0]), int(xh.shape[1])
+        # Nothing else in flight (a single blocking predict): put the upload inside the forward.  With a request already running the
+        # plain contiguous copy is the better upload -- it hides under that forward anyway, and sliced 2-D copies reach only ~35 of
+        # the ~55 GB/s a contiguous one does.
+        idle = st["i"] < 2 or st["y_done"][1 - k].query()
+        if (idle and xh.is_pinned() and eng in (None, "auto", "tc", "tc_f16") and B >= C.TC_MIN_BATCH and T >= 64
+                and os.environ.get("SVDLSTM_STREAMED_INPUT", "1") != "0"):
+            self.build((None, None, int(xh.shape[-1])))
+            if self._fusable() and self._lstm_layers()[-1].return_sequences:
+                # the upload goes INSIDE the forward: time slices on the copy stream, the kernel follows them (a single blocking
+                # predict then costs max(upload, forward) instead of their sum); None = not a launch that can do it
+                y = self._fused_handle().forward_streamed_input(xh, st["x_dev"][k], st["copy_stream"], n_slices=8)
+                if y is None:
+                    st["h2d_done"][k].record(st["copy_stream"])        # the slices were enqueued all the same
+                    main.wait_event(st["h2d_done"][k])
+                    y = self.__call__(st["x_dev"][k], engine=engine)
+        if y is None:
+            with torch.cuda.stream(st["copy_stream"]):
+                st["x_dev"][k].copy_(xh, non_blocking=True)
+                st["h2d_done"][k].record(st["copy_stream"])
+            main.wait_event(st["h2d_done"][k])
+            y = self.__call__(st["x_dev"][k], engine=engine)
         st["x_free"][k].record(main)
         if st["y_host"][k] is None or tuple(st["y_host"][k].shape) != tuple(y.shape):
             st["y_host"][k] = torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory()

@@ -187,6 +187,35 @@ def test_tc_time_major_and_go_backwards():
         assert float((ytc - y32).abs().max()) < 2e-3 * float(y32.abs().max()) + 2e-4, kw
 
 
+def test_predict_with_the_upload_inside_the_forward(monkeypatch):
+    """model.predict(pinned host x) in the dense regime uploads x in time slices while the tensor-core kernel already runs
+    (svdlstm_forward_streamed_input; the layer-0 input warp follows a progress word).  Bit-identical to the forward on the
+    fully uploaded array; launches that cannot do it (low ranks: separate packing pass) fall back to upload-then-forward."""
+    _, sm = _models(256, 2)
+    x = torch.randn(2400, 96, 16, generator=torch.Generator().manual_seed(50))   # 64-sequence tiles (32-wide ones would not fit the SMs)
+    xp = svdlstm.pinned_empty((2400, 96, 16))
+    xp.copy_(x)
+    assert xp.is_pinned()
+    for rank, streamed in ((128, True), (16, False)):
+        m = svdlstm.truncate_singular_model(sm, rank)
+        y_dev = m(x.cuda(), engine="tc").cpu().numpy()
+        l0 = svdlstm.launches()
+        y1 = m.predict(xp)
+        assert m.last_engine() == svdlstm.ENGINE_TC
+        assert np.array_equal(y1, y_dev), rank
+        assert (svdlstm.launches() - l0 == 1) == streamed, (rank, svdlstm.launches() - l0)   # streamed: the one pipelined launch, no packing pass
+        y2 = m.predict(xp)                                 # second request: buffers and progress word are reused
+        assert np.array_equal(y2, y_dev)
+        monkeypatch.setenv("SVDLSTM_STREAMED_INPUT", "0")
+        assert np.array_equal(m.predict(xp), y_dev)
+        monkeypatch.delenv("SVDLSTM_STREAMED_INPUT")
+    # odd lengths / slices that do not divide T
+    m = svdlstm.truncate_singular_model(sm, 128)
+    xo = svdlstm.pinned_empty((2500, 71, 16))
+    xo.copy_(torch.from_numpy(np.random.default_rng(51).standard_normal((2500, 71, 16)).astype(np.float32)))
+    assert np.array_equal(m.predict(xo), m(xo.cuda(), engine="tc").cpu().numpy())
+
+
 def test_tc_rejects_what_it_cannot_run():
     """No silent fallback: unsupported models / calls raise with the reason."""
     full, sm = _models(128, 1)
