@@ -123,5 +123,15 @@ def test_new_entry_points_validate_on_the_host():
     assert lib.svdlstm_reduce_factors_batched(ctypes.byref(item), 1, None) < 0
     assert lib.svdlstm_reduce_factors_batched(None, 0, None) < 0
     assert lib.svdlstm_scaled_matmul(8, 2, None, 8, 4, None, 3, 5, 4, 8, 4, None) < 0 and b"bad shape" in lib.svdlstm_last_error()   # lda < k
+    # forward with the upload inside: argument checks first, then "this model cannot" (-3) before anything touches a device
+    fsi = lib.svdlstm_forward_streamed_input
+    assert fsi(h, None, 8, 4, 8, 8, 4, 8, 16) < 0 and b"null" in lib.svdlstm_last_error()
+    assert fsi(h, 8, 8, 4, 8, 8, 0, 8, 16) < 0 and b"n_slices" in lib.svdlstm_last_error()
+    assert fsi(h, 8, 8, 4, 8, 8, 4, 8, 8) < 0 and b"stream of its own" in lib.svdlstm_last_error()
+    wide = ctypes.c_void_p()                                                           # 512 full-rank units: rank 512 > 256
+    assert lib.svdlstm_create(ctypes.byref(wide), 1, 16, C.int_array([512])) == 0
+    assert lib.svdlstm_set_full_weights(wide, 0, 8, 8, 8) == 0
+    assert fsi(wide, 8, 8, 256, 64, 8, 4, 8, 16) == -3 and b"ranks above 256" in lib.svdlstm_last_error()
+    lib.svdlstm_destroy(wide)
     lib.svdlstm_destroy(h)
     lib.svdlstm_destroy(big)
