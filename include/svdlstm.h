@@ -105,7 +105,8 @@ int svdlstm_host_free(void* p);
 
 /* Number of kernels the last forward on this handle launched, and which engine ran. */
 /* One forward from a PINNED host array with the upload INSIDE the forward (latency of a single `rmodel.predict(X)`,
- * svd_acceleration_v3.py:150-151): x_host (B,T,D) is copied to x_dev in n_slices time slices on `copy_stream`; the tensor-core
+ * svd_acceleration_v3.py:150-151): x_host (B,T,D) is copied to x_dev in n_slices equal time slices (0: slices of 64, 64, 128, 256 ...
+ * steps -- a short first one, long fast rows afterwards) on `copy_stream`; the tensor-core
  * kernel is launched on `stream` as soon as the first slice has landed and follows the upload through a progress word (its layer-0
  * input warp reads x(t) straight from x_dev).  Same result as svdlstm_forward(ENGINE_TC) on the uploaded array.  Returns -3 if the
  * model / batch does not take the raw-x pipelined launch: the slices are enqueued all the same, so the caller falls back to

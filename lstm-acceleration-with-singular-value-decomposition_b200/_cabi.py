@@ -227,6 +227,23 @@ class _PinnedBlock:
             pass
 
 
+_pinned_pool = {}      # nbytes -> free _PinnedBlocks
+
+
+def pooled_pinned_array(shape) -> np.ndarray:
+    """float32 numpy array in page-locked memory taken from a pool; the block returns to the pool when the array (and every view
+    of it) has died.  ``predict`` hands its result out this way: the device->host copy lands in memory the caller then OWNS -- no
+    second copy out of a staging buffer -- and page-locking (milliseconds per allocation) is paid once per size."""
+    import weakref
+    n = int(np.prod(shape))
+    nbytes = max(4 * n, 4)
+    free = _pinned_pool.setdefault(nbytes, [])
+    blk = free.pop() if free else _PinnedBlock(nbytes, False)
+    buf = (ctypes.c_float * n).from_address(blk.p.value)
+    weakref.finalize(buf, free.append, blk)      # (the callback keeps the block alive; it runs when the array's base is collected)
+    return np.ctypeslib.as_array(buf).reshape(shape)
+
+
 def pinned_empty(shape, write_combined: bool = False) -> torch.Tensor:
     """float32 CPU tensor in page-locked host memory (a staging buffer for ``predict`` / ``predict_async``).
     ``write_combined=True`` -> cudaHostAllocWriteCombined: fill it once from the CPU, let the GPU read it."""

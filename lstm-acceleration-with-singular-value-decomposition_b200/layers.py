@@ -207,7 +207,7 @@ class Handle:
             return y, hs_out, cs_out
         return y, None, None
 
-    def forward_streamed_input(self, x_host: torch.Tensor, x_dev: torch.Tensor, copy_stream, n_slices: int = 8):
+    def forward_streamed_input(self, x_host: torch.Tensor, x_dev: torch.Tensor, copy_stream, n_slices: int = 0):
         """Forward with the host->device upload of ``x_host`` (pinned, float32, (B,T,D)) INSIDE it: the array goes up in time
         slices on ``copy_stream`` and the tensor-core kernel follows the upload (``svdlstm_forward_streamed_input``).  Returns
         the output sequence, or None if this model / batch does not take that launch -- the slices are enqueued on

@@ -250,9 +250,9 @@ class Sequential:
         Sequences are independent, so the whole batch runs as one launch regardless of batch_size.
         Host input (numpy, or a torch CPU tensor -- pinned memory makes the copy asynchronous and full-speed) is staged through
         the serving pipeline of ``predict_async``; a CUDA tensor skips the input copy."""
-        return np.array(self.predict_async(X, engine=engine).result())      # an owned copy (the pinned buffer is recycled)
+        return self.predict_async(X, engine=engine, _own_result=True).result()   # an array the caller owns (pooled pinned memory)
 
-    def predict_async(self, X, engine=None):
+    def predict_async(self, X, engine=None, _own_result=False):
         """Enqueue one ``predict`` and return at once with a handle whose ``.result()`` blocks for the host array.
 
         A serving loop keeps two requests in flight: the host->device copy of request i+1 (own copy stream, second device
@@ -264,6 +264,10 @@ class Sequential:
         if isinstance(X, torch.Tensor) and X.is_cuda:
             y = self.__call__(X, engine=engine)
             return _Pending(None, y, None)
+        return self._predict_host(X, engine, _own_result)
+
+    def _predict_host(self, X, engine, own_result):
+        dev = C.require_cuda()
         xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float32)))
         if xh.dtype != torch.float32 or not xh.is_contiguous():
             xh = xh.to(torch.float32).contiguous()
@@ -298,7 +302,8 @@ class Sequential:
             if self._fusable() and self._lstm_layers()[-1].return_sequences:
                 # the upload goes INSIDE the forward: time slices on the copy stream, the kernel follows them (a single blocking
                 # predict then costs max(upload, forward) instead of their sum); None = not a launch that can do it
-                y = self._fused_handle().forward_streamed_input(xh, st["x_dev"][k], st["copy_stream"], n_slices=8)
+                y = self._fused_handle().forward_streamed_input(xh, st["x_dev"][k], st["copy_stream"],
+                                                               n_slices=int(os.environ.get("SVDLSTM_INPUT_SLICES", "32")))
                 if y is None:
                     st["h2d_done"][k].record(st["copy_stream"])        # the slices were enqueued all the same
                     main.wait_event(st["h2d_done"][k])
@@ -310,17 +315,22 @@ class Sequential:
             main.wait_event(st["h2d_done"][k])
             y = self.__call__(st["x_dev"][k], engine=engine)
         st["x_free"][k].record(main)
-        if st["y_host"][k] is None or tuple(st["y_host"][k].shape) != tuple(y.shape):
-            st["y_host"][k] = torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory()
+        if own_result:
+            y_np = C.pooled_pinned_array(tuple(y.shape))       # the caller keeps it: no copy out of a recycled staging buffer
+            y_host = torch.from_numpy(y_np)
+        else:
+            if st["y_host"][k] is None or tuple(st["y_host"][k].shape) != tuple(y.shape):
+                st["y_host"][k] = torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory()
+            y_host, y_np = st["y_host"][k], None
         # the result goes home on its own stream: the next request's forward starts right behind this one instead of behind its copy
         st["fwd_done"][k].record(main)
         d2h = st["d2h_stream"]
         with torch.cuda.stream(d2h):
             d2h.wait_event(st["fwd_done"][k])
-            st["y_host"][k].copy_(y, non_blocking=True)
+            y_host.copy_(y, non_blocking=True)
             y.record_stream(d2h)
             st["y_done"][k].record(d2h)
-        return _Pending(st["y_done"][k], None, st["y_host"][k])
+        return _Pending(st["y_done"][k], None, y_host, y_np)
 
     # ---- training (svd_acceleration_v3.py:111-128) ------------------------------------------------------------------------
     def compile(self, loss="mse", optimizer="adam", learning_rate=None, **kwargs):
@@ -466,13 +476,16 @@ def _host(a):
 class _Pending:
     """Handle of one in-flight ``predict_async`` request."""
 
-    def __init__(self, event, y_dev, y_host):
-        self._event, self._y_dev, self._y_host = event, y_dev, y_host
+    def __init__(self, event, y_dev, y_host, y_np=None):
+        self._event, self._y_dev, self._y_host, self._y_np = event, y_dev, y_host, y_np
 
     def result(self) -> np.ndarray:
         if self._y_host is None:
             return self._y_dev.cpu().numpy()
         self._event.synchronize()
+        if self._y_np is not None:          # predict(): pooled pinned memory owned by the caller from here on
+            y, self._y_np, self._y_host = self._y_np, None, None
+            return y
         return self._y_host.numpy()
 
 

@@ -126,7 +126,7 @@ def test_new_entry_points_validate_on_the_host():
     # forward with the upload inside: argument checks first, then "this model cannot" (-3) before anything touches a device
     fsi = lib.svdlstm_forward_streamed_input
     assert fsi(h, None, 8, 4, 8, 8, 4, 8, 16) < 0 and b"null" in lib.svdlstm_last_error()
-    assert fsi(h, 8, 8, 4, 8, 8, 0, 8, 16) < 0 and b"n_slices" in lib.svdlstm_last_error()
+    assert fsi(h, 8, 8, 4, 8, 8, -1, 8, 16) < 0 and b"n_slices" in lib.svdlstm_last_error()
     assert fsi(h, 8, 8, 4, 8, 8, 4, 8, 8) < 0 and b"stream of its own" in lib.svdlstm_last_error()
     wide = ctypes.c_void_p()                                                           # 512 full-rank units: rank 512 > 256
     assert lib.svdlstm_create(ctypes.byref(wide), 1, 16, C.int_array([512])) == 0
