@@ -621,7 +621,8 @@ def main():
         if dist is not None:
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         e2e_sync = {"value": world * B * T / (float(ts[0]) * 1e-3), "unit": "sequence-timesteps/s", "ms_per_step": float(ts[0]), "steps": n_sync,
-                    "how": "blocking model.predict(pinned host x) -> numpy, one request at a time (H2D, forward, D2H in series), wall clock"}
+                    "how": "blocking model.predict(pinned host x) -> numpy, one request at a time, wall clock; the upload runs INSIDE the forward "
+                           "(time slices + progress word, svdlstm_forward_streamed_input), the result lands in pooled pinned memory"}
 
     clocks = sampler.stop() if rank == 0 else None
 
