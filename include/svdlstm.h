@@ -109,8 +109,9 @@ int svdlstm_host_free(void* p);
  * steps -- a short first one, long fast rows afterwards) on `copy_stream`; the tensor-core
  * kernel is launched on `stream` as soon as the first slice has landed and follows the upload through a progress word (its layer-0
  * input warp reads x(t) straight from x_dev).  Same result as svdlstm_forward(ENGINE_TC) on the uploaded array.  Returns -3 if the
- * model / batch does not take the raw-x pipelined launch: the slices are enqueued all the same, so the caller falls back to
- * svdlstm_forward on `stream` after waiting for `copy_stream`.  x_host must stay unmodified until `copy_stream` has drained.   */
+ * tensor-core engine does not take this model at all (nothing was enqueued: upload and run it the plain way), -4 if the launch this
+ * batch takes cannot follow an upload (low ranks, small batches): the slices ARE enqueued, so the caller waits for `copy_stream`
+ * and calls svdlstm_forward on x_dev.  x_host must stay unmodified until `copy_stream` has drained.                              */
 int svdlstm_forward_streamed_input(svdlstm_handle h, const float* x_host, float* x_dev, int B, int T, float* y, int n_slices,
                                    void* copy_stream, void* stream);
 int svdlstm_last_launches(svdlstm_handle h);

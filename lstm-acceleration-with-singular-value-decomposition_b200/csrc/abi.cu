@@ -355,13 +355,15 @@ int svdlstm_forward_streamed_input(svdlstm_handle h, const float* x_host, float*
   SVD_CUDA_TRY(cudaStreamWaitEvent(stream, h->xr_event, 0));
   a.x_ready = h->xr_dev;
   int launches = 0;
-  const int rc = run_tc(h->md, &h->tc, h->tc_dirty, a, stream, &launches);
+  int rc = run_tc(h->md, &h->tc, h->tc_dirty, a, stream, &launches);
   if (rc == 0) {
     h->tc_dirty = false;
     if (!h->md_event) SVD_CUDA_TRY(cudaEventCreateWithFlags(&h->md_event, cudaEventDisableTiming));
     SVD_CUDA_TRY(cudaEventRecord(h->md_event, stream));
     h->last_launches = launches;
     h->last_engine = SVDLSTM_ENGINE_TC;
+  } else if (rc == -3) {
+    rc = -4;   // the launch this batch takes cannot follow an upload -- but the slices ARE on their way (unlike -3 above)
   }
   return rc;
 }

@@ -210,8 +210,9 @@ class Handle:
     def forward_streamed_input(self, x_host: torch.Tensor, x_dev: torch.Tensor, copy_stream, n_slices: int = 0):
         """Forward with the host->device upload of ``x_host`` (pinned, float32, (B,T,D)) INSIDE it: the array goes up in time
         slices on ``copy_stream`` and the tensor-core kernel follows the upload (``svdlstm_forward_streamed_input``).  Returns
-        the output sequence, or None if this model / batch does not take that launch -- the slices are enqueued on
-        ``copy_stream`` all the same, so the caller waits for it and calls :meth:`forward` on ``x_dev``."""
+        the output sequence; ``None`` if the launch this batch takes cannot follow an upload -- the slices are enqueued on
+        ``copy_stream`` all the same, so the caller waits for it and calls :meth:`forward` on ``x_dev``; ``False`` if the
+        tensor-core engine does not take the model at all (nothing was enqueued)."""
         B, T = int(x_host.shape[0]), int(x_host.shape[1])
         n = self.n_out if self.n_out > 0 else self.units[-1]
         y = torch.empty((B, T, n), dtype=torch.float32, device=x_dev.device)
@@ -219,6 +220,8 @@ class Handle:
         rc = L.svdlstm_forward_streamed_input(self._h, x_host.data_ptr(), C.ptr(x_dev), B, T, C.ptr(y), int(n_slices),
                                               copy_stream.cuda_stream, C.cur_stream())
         if rc == -3:
+            return False
+        if rc == -4:
             return None
         C.check(rc)
         C.add_launches(L.svdlstm_last_launches(self._h))

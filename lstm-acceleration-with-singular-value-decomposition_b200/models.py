@@ -308,6 +308,8 @@ class Sequential:
                     st["h2d_done"][k].record(st["copy_stream"])        # the slices were enqueued all the same
                     main.wait_event(st["h2d_done"][k])
                     y = self.__call__(st["x_dev"][k], engine=engine)
+                elif y is False:
+                    y = None                                           # not a tensor-core model: nothing was uploaded yet
         if y is None:
             with torch.cuda.stream(st["copy_stream"]):
                 st["x_dev"][k].copy_(xh, non_blocking=True)

@@ -209,6 +209,12 @@ def test_predict_with_the_upload_inside_the_forward(monkeypatch):
         monkeypatch.setenv("SVDLSTM_STREAMED_INPUT", "0")
         assert np.array_equal(m.predict(xp), y_dev)
         monkeypatch.delenv("SVDLSTM_STREAMED_INPUT")
+    # a model the tensor-core engine does not take at all (512 full-rank units): plain upload + FP32 engine, same answer as on device
+    layers512, dense512 = svdlstm.synthetic_layers(16, 512, 1, seed=0)
+    wide = svdlstm.full_model_from_weights(layers512, dense512, return_sequences=True)
+    xw = svdlstm.pinned_empty((256, 64, 16))
+    xw.copy_(torch.randn(256, 64, 16, generator=torch.Generator().manual_seed(52)))
+    assert np.array_equal(wide.predict(xw), wide(xw.cuda()).cpu().numpy()) and wide.last_engine() == svdlstm.ENGINE_GENERAL
     # odd lengths / slices that do not divide T
     m = svdlstm.truncate_singular_model(sm, 128)
     xo = svdlstm.pinned_empty((2500, 71, 16))
