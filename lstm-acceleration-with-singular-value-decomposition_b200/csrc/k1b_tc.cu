@@ -2082,7 +2082,9 @@ static int run_tc_one(const ModelDesc& md, const ModelDesc& raw, TcState** state
   bool raw_x = false;
   if (pipe && ns == 64 && getenv("SVDLSTM_TC_PACKX") == nullptr) {
     const TcLayerParams& lp = st->layers[L - 1].prm;
-    raw_x = lp.streaming && (lp.n_chunks_u + lp.n_chunks_2) >= 32 && st->layers[0].prm.streaming;
+    // (a forward that follows its own upload -- a.x_ready -- takes the raw-x build at every rank: a few per cent of kernel time
+    //  against the whole upload in series)
+    raw_x = lp.streaming && ((lp.n_chunks_u + lp.n_chunks_2) >= 32 || a.x_ready != nullptr) && st->layers[0].prm.streaming;
   }
   if (!raw_x && a.x_ready != nullptr) {
     set_error("tensor-core engine: this model / batch does not take the raw-x pipelined launch (needed for a streamed input upload)");

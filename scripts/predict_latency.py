@@ -3,10 +3,10 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, svdlstm, bench
-class A: hidden=256; layers=2; rank=128
+class A: hidden=256; layers=2; rank=int(sys.argv[1]) if len(sys.argv) > 1 else 128
 _,_,model = bench.build_workload(A, svdlstm)
 x = svdlstm.pinned_empty((4096,1024,16)); x.copy_(torch.randn(4096,1024,16))
-for ns in ("32", "8", "16", "64", "0", "32"):
+for ns in ("32", "8", "16", "64", "0", "32") if len(sys.argv) < 2 else ("32",):
     os.environ["SVDLSTM_INPUT_SLICES"]=ns
     model.predict(x); torch.cuda.synchronize()
     t0=time.perf_counter()

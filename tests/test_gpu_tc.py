@@ -190,13 +190,14 @@ def test_tc_time_major_and_go_backwards():
 def test_predict_with_the_upload_inside_the_forward(monkeypatch):
     """model.predict(pinned host x) in the dense regime uploads x in time slices while the tensor-core kernel already runs
     (svdlstm_forward_streamed_input; the layer-0 input warp follows a progress word).  Bit-identical to the forward on the
-    fully uploaded array; launches that cannot do it (low ranks: separate packing pass) fall back to upload-then-forward."""
+    fully uploaded array; launches that cannot do it (32-sequence tiles, models the engine does not take) fall back to
+    upload-then-forward."""
     _, sm = _models(256, 2)
     x = torch.randn(2400, 96, 16, generator=torch.Generator().manual_seed(50))   # 64-sequence tiles (32-wide ones would not fit the SMs)
     xp = svdlstm.pinned_empty((2400, 96, 16))
     xp.copy_(x)
     assert xp.is_pinned()
-    for rank, streamed in ((128, True), (16, False)):
+    for rank, streamed in ((128, True), (16, True)):
         m = svdlstm.truncate_singular_model(sm, rank)
         y_dev = m(x.cuda(), engine="tc").cpu().numpy()
         l0 = svdlstm.launches()
@@ -209,6 +210,12 @@ def test_predict_with_the_upload_inside_the_forward(monkeypatch):
         monkeypatch.setenv("SVDLSTM_STREAMED_INPUT", "0")
         assert np.array_equal(m.predict(xp), y_dev)
         monkeypatch.delenv("SVDLSTM_STREAMED_INPUT")
+    # a batch that runs as 32-sequence tiles (no raw-x build): the slices are uploaded, then the plain forward runs
+    m = svdlstm.truncate_singular_model(sm, 128)
+    xs = svdlstm.pinned_empty((300, 96, 16))
+    xs.copy_(x[:300])
+    l0 = svdlstm.launches()
+    assert np.array_equal(m.predict(xs), m(xs.cuda(), engine="tc").cpu().numpy())
     # a model the tensor-core engine does not take at all (512 full-rank units): plain upload + FP32 engine, same answer as on device
     layers512, dense512 = svdlstm.synthetic_layers(16, 512, 1, seed=0)
     wide = svdlstm.full_model_from_weights(layers512, dense512, return_sequences=True)
