@@ -237,7 +237,11 @@ def pooled_pinned_array(shape) -> np.ndarray:
     import weakref
     n = int(np.prod(shape))
     nbytes = max(4 * n, 4)
-    free = _pinned_pool.setdefault(nbytes, [])
+    if nbytes not in _pinned_pool:
+        # first result of this size: page-lock TWO blocks now (tens of ms each for a 16 MB result) -- `y = model.predict(x)` in a
+        # loop holds the previous result while the next one is produced, so a second block is needed by the second call anyway
+        _pinned_pool[nbytes] = [_PinnedBlock(nbytes, False)]
+    free = _pinned_pool[nbytes]
     blk = free.pop() if free else _PinnedBlock(nbytes, False)
     buf = (ctypes.c_float * n).from_address(blk.p.value)
     weakref.finalize(buf, free.append, blk)      # (the callback keeps the block alive; it runs when the array's base is collected)
